@@ -1,0 +1,161 @@
+/*
+ * mgcn.h — C-ABI of libmgcn.so: the B200 (sm_100a) message-passing engine that sits behind
+ * meta-gcn's Python model API.
+ *
+ * The reference (jzhou316/meta-gcn) is pure Python and has no FFI; its seams on this path are two
+ * Python call shapes:
+ *   primitive seam  scatter_(name, src, index, dim_size)            src/gcn_meta/models/common.py:37-66
+ *                   NodeModelBase.degnorm_const(...)                src/gcn_meta/models/gcn_base_models.py:65-146
+ *   layer seam      NodeModelAdditive.forward(x, edge_index, ...)   src/gcn_meta/models/gcn_base_models.py:199-243
+ *                   GCNConv / SAGEConv / GINConv / global_mean_pool kernel/gcn.py:26-29, gin.py:41-44,
+ *                                                                   graph_sage.py:26-29 (PyG 1.3 semantics)
+ * Every entry point below names the reference call it replaces. INTEGRATION.md shows the
+ * ctypes / torch.library binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host".
+ *   - the library allocates nothing and never synchronises: the caller owns inputs, outputs and
+ *     workspace, and all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - workspace query: call with workspace == NULL, the required bytes are written to
+ *     *workspace_bytes and MGCN_OK is returned without launching anything.
+ *   - return value: 0 = OK, < 0 = argument error (MGCN_ERR_*), > 0 = cudaError_t of a launch.
+ *   - indices are int64 at the boundary (the reference's edge_index dtype) and int32 inside.
+ *   - features are fp32, row-major, leading dimension = row width.
+ */
+#ifndef MGCN_H_
+#define MGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGCN_VERSION 100
+
+#define MGCN_OK 0
+#define MGCN_ERR_NULL (-1)      /* a required pointer is NULL                         */
+#define MGCN_ERR_RANGE (-2)     /* N or E outside [0, 2^31 - 2^20)                     */
+#define MGCN_ERR_SHAPE (-3)     /* unsupported width / stride / enum value            */
+#define MGCN_ERR_ALIGN (-4)     /* pointer not aligned for 128-bit access             */
+#define MGCN_ERR_WORKSPACE (-5) /* workspace smaller than the queried size            */
+
+/* Degree above which a row is aggregated by a whole CTA (fixed-shape tree combine) instead of one
+ * lane group (sequential, bit-identical to the reference's CPU edge-order sum). */
+#define MGCN_DEFAULT_HUB_THRESHOLD 256
+
+/* A row-owned adjacency (CSR when built by source, CSC when built by target).  All members are
+ * device pointers written by mgcn_csr_build and owned by the caller. */
+typedef struct mgcn_csr {
+  int64_t n_rows;          /* N                                                          */
+  int64_t nnz_cap;         /* allocated length of nbr/perm (E, or E+N when loops added)  */
+  const int32_t* rowptr;   /* [N+1]; rowptr[N] = number of kept edges                    */
+  const int32_t* nbr;      /* [nnz_cap] other endpoint of each kept edge, row-grouped    */
+  const int32_t* perm;     /* [nnz_cap] position in the input edge_index (E+i = loop i)  */
+  const int32_t* hub_rows; /* [hub_cap] rows with more than hub_threshold entries        */
+  const int32_t* hub_count;/* [1]                                                        */
+  int64_t hub_cap;
+  int32_t hub_threshold;
+} mgcn_csr_t;
+
+int mgcn_version(void);
+const char* mgcn_error_string(int code);
+/* kernels launched by this library in this process since load / last reset (host counters) */
+int64_t mgcn_launch_count(void);
+void mgcn_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * edge_index -> row-owned structure.  Replaces the sort-free COO bookkeeping the reference leaves
+ * to torch_scatter (common.py:56-59) and PyG's add_remaining_self_loops / remove_self_loops
+ * (inside GCNConv.norm, SAGEConv.forward, GINConv.forward; Appendix A of SURVEY.md).
+ *
+ * edge_index: int64 [2,E] row-major (row 0 = source, row 1 = target; gcn_base_models.py:28-41).
+ * by        : 0 = group by source (edge_index[0]), 1 = group by target (edge_index[1]).
+ * loop_mode : 0 keep edges as given; 1 drop self loops (remove_self_loops);
+ *             2 drop self loops then append one loop per node at the END of the edge list
+ *               (add_remaining_self_loops without weights) — nnz_cap must be E+N.
+ * The order of edges inside a row is their order in edge_index (stable LSD radix sort), which is
+ * the order the reference's CPU scatter_add sums them in.
+ * Outputs: rowptr int32[N+1], nbr int32[nnz_cap], perm int32[nnz_cap] (unused tail = -1),
+ *          hub_rows int32[hub_cap], hub_count int32[1], bad_index int32[1] (set to 1 if any
+ *          endpoint is outside [0,N); such edges are dropped).
+ */
+int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by, int loop_mode,
+                   int32_t hub_threshold, int32_t* rowptr, int32_t* nbr, int32_t* perm,
+                   int32_t* hub_rows, int64_t hub_cap, int32_t* hub_count, int32_t* bad_index,
+                   void* workspace, size_t* workspace_bytes, void* stream);
+
+/* deg[i] = float(rowptr[i+1]-rowptr[i]): the unweighted scatter_add(ones, row) of
+ * gcn_base_models.py:126 and data_procs/data_add_degree.py:60-63. */
+int mgcn_degree_from_rowptr(const int32_t* rowptr, int64_t N, float* deg, void* stream);
+
+/* Weighted degree: deg[i] = sum over the row's entries (in row order) of edge_weight[perm[k]]
+ * (loop entries, perm >= E, contribute loop_weight).  gcn_base_models.py:126 with edge_weight. */
+int mgcn_weighted_degree(const mgcn_csr_t* g, const float* edge_weight, int64_t E,
+                         float loop_weight, float* deg, void* stream);
+
+/* dis = deg^-1/2 (mode 0, 'sm') or deg^-1 (mode 1, 'rw') with inf -> 0:
+ * gcn_base_models.py:128-135.  Computed as correctly rounded 1/sqrt(d) resp. 1/d. */
+int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream);
+
+/* vals_out[k] = perm[k] < E ? vals_in[perm[k]] : loop_value  — edge weights into row order. */
+int mgcn_permute_edge_values(const mgcn_csr_t* g, const float* vals_in, int64_t E,
+                             float loop_value, float* vals_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-owned aggregation (the hot kernel).  Replaces index_select -> mul -> scatter_add of
+ * gcn_base_models.py:223-237 / MessagePassing.propagate, and its autograd (index_add_/gather)
+ * when called with the structure built by the other endpoint.
+ *
+ *   w_k   = nbr_scale[nbr[k]] * edge_val[k] * row_scale[i]     (absent factors skipped; each product
+ *                                                              rounded to fp32, left to right — the
+ *                                                              order of gcn_base_models.py:138-139)
+ *   acc_i = sum_k  x[nbr[k], :] * w_k                           (k in row order, mul and add rounded
+ *                                                              separately: no FMA contraction)
+ *   acc_i = acc_i / max(len_i, 1)                               if reduce == 1 (scatter_mean)
+ *   out_i = act( acc_i + bias + residual_i )                    act: 0 none, 1 relu
+ * x: [n_in, H], out/residual: [g->n_rows, H]; edge_val is in ROW order (see
+ * mgcn_permute_edge_values).  If gather_perm != 0 the gathered row is x[perm[k]] instead of
+ * x[nbr[k]] (scatter_add of per-edge messages src[E,H]: common.py:56-59).
+ */
+int mgcn_spmm(const mgcn_csr_t* g, const float* x, int64_t n_in, int64_t H, int gather_perm,
+              const float* edge_val, const float* nbr_scale, const float* row_scale, int reduce,
+              const float* bias, const float* residual, int act, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense transform on the FMA pipes (narrow widths) — torch.matmul(x, weight_node)
+ * (gcn_base_models.py:201) and nn.Linear (gcn_model.py:64,73,96).
+ *   y[n,c] = act( sum_k x[n,k] * W(k,c) + bias[c] + add[n,c] ),  W(k,c) = w[k*w_sk + c*w_sc]
+ * so weight_node [Hi,Ho] uses (w_sk,w_sc)=(Ho,1) and nn.Linear.weight [Ho,Hi] uses (1,Hi);
+ * the input-gradient dX = dY * W^T is the same call with the strides swapped.
+ */
+int mgcn_linear(const float* x, int64_t N, int64_t Hi, const float* w, int64_t w_sk, int64_t w_sc,
+                int64_t Ho, const float* bias, const float* add, int act, float* y, void* stream);
+
+/* dW(k,c) = sum_n x[n,k] * g[n,c]  (written at dw[k*dw_sk + c*dw_sc]),  db[c] = sum_n g[n,c].
+ * Two-stage fixed-order reduction: deterministic, no atomics.  db may be NULL. */
+int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, int64_t Ho, float* dw,
+                      int64_t dw_sk, int64_t dw_sc, float* db, void* workspace,
+                      size_t* workspace_bytes, void* stream);
+
+/* g_in[n,c] = relu'(y[n,c]) * g[n,c]  (y = saved activation output; mask is y > 0). */
+int mgcn_relu_backward(const float* g, const float* y, int64_t count, float* g_in, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segment reductions — global_mean_pool / global_add_pool (kernel/gcn.py:29, gin.py:44,
+ * graph_sage.py:29) and GCNModel's pred_on='graph' mean (gcn_model.py:112-123).
+ * offsets int32[G+1] delimit contiguous node ranges (batch vector sorted ascending).
+ */
+int mgcn_batch_to_offsets(const int64_t* batch, int64_t N, int64_t G, int32_t* offsets, void* stream);
+/* out[g,:] = sum (mode 0) or mean with count clamped to >= 1 (mode 1) of x[offsets[g]:offsets[g+1],:] */
+int mgcn_segment_reduce(const float* x, int64_t H, const int32_t* offsets, int64_t G, int mode,
+                        float* out, void* stream);
+/* dx[n,:] = gout[g(n),:] (mode 0) or gout[g(n),:] / max(len_g,1) (mode 1) */
+int mgcn_segment_broadcast(const float* gout, int64_t H, const int32_t* offsets, int64_t G,
+                           int64_t N, int mode, float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGCN_H_ */

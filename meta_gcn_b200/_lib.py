@@ -1,0 +1,93 @@
+"""ctypes binding of libmgcn.so (the C-ABI declared in include/mgcn.h).
+
+There is no CPU fallback: if the shared object is missing this module raises at import of the
+first op, and every entry point raises RuntimeError on a non-zero return code.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libmgcn.so")
+
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_int = ctypes.c_int
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+c_size_p = ctypes.POINTER(ctypes.c_size_t)
+
+
+class MgcnCsr(ctypes.Structure):
+    """mirror of mgcn_csr_t (include/mgcn.h)"""
+    _fields_ = [
+        ("n_rows", c_i64),
+        ("nnz_cap", c_i64),
+        ("rowptr", c_ptr),
+        ("nbr", c_ptr),
+        ("perm", c_ptr),
+        ("hub_rows", c_ptr),
+        ("hub_count", c_ptr),
+        ("hub_cap", c_i64),
+        ("hub_threshold", c_i32),
+    ]
+
+
+CSR_P = ctypes.POINTER(MgcnCsr)
+
+# name -> (restype, argtypes); must list every symbol include/mgcn.h declares
+SIGNATURES = {
+    "mgcn_version": (c_int, []),
+    "mgcn_error_string": (ctypes.c_char_p, [c_int]),
+    "mgcn_launch_count": (c_i64, []),
+    "mgcn_reset_launch_count": (None, []),
+    "mgcn_csr_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i32, c_ptr, c_ptr, c_ptr, c_ptr,
+                               c_i64, c_ptr, c_ptr, c_ptr, c_size_p, c_ptr]),
+    "mgcn_degree_from_rowptr": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "mgcn_weighted_degree": (c_int, [CSR_P, c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
+    "mgcn_gcn_norm": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "mgcn_permute_edge_values": (c_int, [CSR_P, c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
+    "mgcn_spmm": (c_int, [CSR_P, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
+                          c_ptr, c_int, c_ptr, c_ptr]),
+    "mgcn_linear": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
+                            c_ptr, c_ptr]),
+    "mgcn_linear_wgrad": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr,
+                                  c_ptr, c_size_p, c_ptr]),
+    "mgcn_relu_backward": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "mgcn_batch_to_offsets": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "mgcn_segment_reduce": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "mgcn_segment_broadcast": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libmgcn.so (once) and attach signatures.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m meta_gcn_b200.build` "
+            "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().mgcn_error_string(code).decode()
+        raise RuntimeError(f"libmgcn call failed ({code}): {msg}")
+
+
+def launch_count():
+    return int(load().mgcn_launch_count())
+
+
+def reset_launch_count():
+    load().mgcn_reset_launch_count()

@@ -1,0 +1,425 @@
+// edge_index (int64 COO) -> row-owned int32 structure: stable LSD radix sort + segment offsets.
+//
+// Ordering contract: inside a row, entries keep their edge_index order, which is
+// the order the reference's CPU scatter_add (common.py:56-59 -> torch_scatter 1.x ->
+// Tensor.scatter_add_) accumulates them in.  Everything here is integer work: results are
+// bit-exact and independent of scheduling (integer atomics only feed commutative counts).
+#include "common.cuh"
+
+namespace mgcn {
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan (int32), reduce-then-scan, in-place safe
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int32_t warp_inclusive_scan(int32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int32_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across a 1024-thread block; returns block total via *total
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* total) {
+  __shared__ int32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t inc = warp_inclusive_scan(v, lane);
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int32_t ws = warp_sums[lane];
+    int32_t winc = warp_inclusive_scan(ws, lane);
+    warp_sums[lane] = winc - ws;  // exclusive
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  int32_t res = warp_sums[warp] + inc - v;
+  __syncthreads();  // warp_sums reusable by the caller's next call
+  return res;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int32_t* __restrict__ in,
+                                                                 int64_t n,
+                                                                 int32_t* __restrict__ tile_sums) {
+  __shared__ int32_t total;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) s += in[base + i];
+  (void)block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of tile_sums[0..nt) in place
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_offsets(int32_t* tile_sums, int nt) {
+  __shared__ int32_t total;
+  int32_t carry = 0;
+  for (int base = 0; base < nt; base += kScanThreads) {
+    const int i = base + threadIdx.x;
+    const int32_t v = i < nt ? tile_sums[i] : 0;
+    const int32_t ex = block_exclusive_scan(v, &total);
+    if (i < nt) tile_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int32_t* in, int32_t* out,
+                                                             int64_t n,
+                                                             const int32_t* __restrict__ tile_off) {
+  __shared__ int32_t total;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int32_t v[kScanItems];
+  int32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = base + i < n ? in[base + i] : 0;
+    s += v[i];
+  }
+  int32_t run = tile_off[blockIdx.x] + block_exclusive_scan(s, &total);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+}
+
+static size_t scan_tiles(int64_t n) { return (size_t)ceil_div(n > 0 ? n : 1, kScanTile); }
+
+// tile_sums must hold scan_tiles(n) ints
+static int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* tile_sums,
+                              void* stream) {
+  if (n <= 0) return MGCN_OK;
+  const int nt = (int)scan_tiles(n);
+  MGCN_LAUNCH(k_scan_tile_sums, nt, kScanThreads, 0, stream, in, n, tile_sums);
+  MGCN_LAUNCH(k_scan_tile_offsets, 1, kScanThreads, 0, stream, tile_sums, nt);
+  MGCN_LAUNCH(k_scan_apply, nt, kScanThreads, 0, stream, in, out, n, tile_sums);
+  return MGCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// keys + row histogram
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_make_keys(const int64_t* __restrict__ ei, int64_t E,
+                                                   int64_t N, int by, int loop_mode,
+                                                   int64_t total, uint32_t* __restrict__ keys,
+                                                   int32_t* __restrict__ counts,
+                                                   int32_t* __restrict__ bad_index) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    uint32_t key;
+    if (e < E) {
+      const int64_t s = ei[e], d = ei[E + e];
+      const bool ok = s >= 0 && s < N && d >= 0 && d < N;
+      if (!ok) {
+        *bad_index = 1;
+        key = (uint32_t)N;
+      } else if (loop_mode != 0 && s == d) {
+        key = (uint32_t)N;  // dropped
+      } else {
+        key = (uint32_t)(by == 0 ? s : d);
+      }
+    } else {
+      key = (uint32_t)(e - E);  // appended self loop of node e-E (loop_mode 2)
+    }
+    keys[e] = key;
+    if (key < (uint32_t)N) atomicAdd(&counts[key], 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key, position) pairs, 8-bit digits.
+// Tile = 8 warps x 16 rounds x 32 lanes; a warp owns 512 consecutive items, so the stable order
+// inside a tile is (warp, round, lane).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRsWarps = 8;
+constexpr int kRsRounds = 16;
+constexpr int kRsTile = kRsWarps * 32 * kRsRounds;
+
+__global__ void __launch_bounds__(256) k_radix_hist(const uint32_t* __restrict__ keys, int64_t n,
+                                                    int shift, int32_t* __restrict__ block_hist,
+                                                    int num_blocks) {
+  __shared__ int32_t wh[kRsWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kRsWarps * 256; i += 256) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsRounds);
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 4
+  for (int r = 0; r < kRsRounds; ++r) {
+    const int64_t idx = wbase + r * 32 + lane;
+    const uint32_t d = idx < n ? ((keys[idx] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (d < 256u && (peers & lt) == 0u) wh[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  int32_t s = 0;
+#pragma unroll
+  for (int w = 0; w < kRsWarps; ++w) s += wh[w][threadIdx.x];
+  block_hist[(int64_t)threadIdx.x * num_blocks + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+    k_radix_scatter(const uint32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                    uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n,
+                    int shift, const int32_t* __restrict__ block_off, int num_blocks) {
+  __shared__ int32_t wh[kRsWarps][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kRsWarps * 256; i += 256) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsRounds);
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t key[kRsRounds];
+#pragma unroll
+  for (int r = 0; r < kRsRounds; ++r) {
+    const int64_t idx = wbase + r * 32 + lane;
+    key[r] = idx < n ? keys_in[idx] : 0u;
+    const uint32_t d = idx < n ? ((key[r] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (d < 256u && (peers & lt) == 0u) wh[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    int32_t base = block_off[(int64_t)threadIdx.x * num_blocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) {
+      const int32_t c = wh[w][threadIdx.x];
+      wh[w][threadIdx.x] = base;
+      base += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRsRounds; ++r) {
+    const int64_t idx = wbase + r * 32 + lane;
+    const bool valid = idx < n;
+    const uint32_t d = valid ? ((key[r] >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & lt);
+    int32_t dst = 0;
+    if (valid) dst = wh[warp][d] + rank;
+    __syncwarp();
+    if (valid && rank == 0) wh[warp][d] += __popc(peers);
+    __syncwarp();
+    if (valid) {
+      keys_out[dst] = key[r];
+      vals_out[dst] = vals_in ? vals_in[idx] : (int32_t)idx;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_finalize(const int64_t* __restrict__ ei, int64_t E, int by, int64_t total,
+               const int32_t* __restrict__ sorted_pos, const int32_t* __restrict__ rowptr,
+               int64_t N, int32_t* __restrict__ nbr, int32_t* __restrict__ perm) {
+  const int32_t kept = rowptr[N];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+    if (k < kept) {
+      const int32_t p = sorted_pos[k];
+      perm[k] = p;
+      nbr[k] = p < E ? (int32_t)(by == 0 ? ei[E + p] : ei[p]) : (int32_t)(p - E);
+    } else {
+      perm[k] = -1;
+      nbr[k] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_find_hubs(const int32_t* __restrict__ rowptr, int64_t N, int32_t threshold,
+                int32_t* __restrict__ hub_rows, int64_t hub_cap, int32_t* __restrict__ hub_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (rowptr[i + 1] - rowptr[i] > threshold) {
+    const int32_t k = atomicAdd(hub_count, 1);
+    if (k < hub_cap) hub_rows[k] = (int32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_degree(const int32_t* __restrict__ rowptr, int64_t N,
+                                                float* __restrict__ deg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) deg[i] = (float)(rowptr[i + 1] - rowptr[i]);
+}
+
+// one thread per row, sequential in row order: deterministic and equal to the reference's
+// edge-order scatter_add of weights (gcn_base_models.py:126)
+__global__ void __launch_bounds__(256)
+    k_weighted_degree(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm,
+                      const float* __restrict__ ew, int64_t E, float loop_w, int64_t N,
+                      float* __restrict__ deg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float s = 0.f;
+  for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+    const int32_t p = perm[k];
+    s = __fadd_rn(s, p < E ? ew[p] : loop_w);
+  }
+  deg[i] = s;
+}
+
+__global__ void __launch_bounds__(256) k_gcn_norm(const float* __restrict__ deg, int64_t N, int mode,
+                                                  float* __restrict__ dis) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float d = deg[i];
+  // deg.pow(-0.5) / deg.pow(-1) on the CPU reference are 1/sqrt(d) and 1/d, both correctly rounded
+  float v = mode == 0 ? __fdiv_rn(1.0f, __fsqrt_rn(d)) : __fdiv_rn(1.0f, d);
+  if (v == __int_as_float(0x7f800000)) v = 0.f;  // gcn_base_models.py:135 (only +inf is masked)
+  dis[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+    k_permute_vals(const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr, int64_t N,
+                   int64_t total, const float* __restrict__ vin, int64_t E, float loop_value,
+                   float* __restrict__ vout) {
+  const int32_t kept = rowptr[N];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+    float v = 0.f;
+    if (k < kept) {
+      const int32_t p = perm[k];
+      v = p < E ? vin[p] : loop_value;
+    }
+    vout[k] = v;
+  }
+}
+
+static int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 32) {
+  int64_t g = ceil_div(n > 0 ? n : 1, block);
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+static int radix_passes(int64_t N) {
+  int bits = 1;
+  while ((int64_t(1) << bits) <= N) ++bits;  // values 0..N inclusive
+  return (bits + 7) / 8;
+}
+
+}  // namespace mgcn
+
+using namespace mgcn;
+
+extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by,
+                              int loop_mode, int32_t hub_threshold, int32_t* rowptr, int32_t* nbr,
+                              int32_t* perm, int32_t* hub_rows, int64_t hub_cap,
+                              int32_t* hub_count, int32_t* bad_index, void* workspace,
+                              size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(by == 0 || by == 1, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(loop_mode >= 0 && loop_mode <= 2, MGCN_ERR_SHAPE);
+  const int64_t kMax = (int64_t(1) << 31) - (int64_t(1) << 20);
+  MGCN_REQUIRE(E >= 0 && N >= 0 && E < kMax && N < kMax, MGCN_ERR_RANGE);
+  const int64_t total = E + (loop_mode == 2 ? N : 0);
+  MGCN_REQUIRE(total < kMax, MGCN_ERR_RANGE);
+
+  const int num_blocks = (int)ceil_div(total > 0 ? total : 1, kRsTile);
+  const int64_t hist_len = (int64_t)256 * num_blocks;
+  WorkspaceCarver ws(workspace);
+  uint32_t* keys_a = ws.take<uint32_t>(total);
+  uint32_t* keys_b = ws.take<uint32_t>(total);
+  int32_t* vals_a = ws.take<int32_t>(total);
+  int32_t* vals_b = ws.take<int32_t>(total);
+  int32_t* block_hist = ws.take<int32_t>(hist_len);
+  int32_t* tile_sums = ws.take<int32_t>(scan_tiles(hist_len > N + 1 ? hist_len : N + 1));
+  if (workspace == nullptr) {
+    *workspace_bytes = ws.bytes();
+    return MGCN_OK;
+  }
+  MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
+  MGCN_REQUIRE(rowptr && nbr && perm && hub_count && bad_index, MGCN_ERR_NULL);
+  MGCN_REQUIRE(E == 0 || edge_index != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(hub_cap == 0 || hub_rows != nullptr, MGCN_ERR_NULL);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  MGCN_CHECK_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (N + 1), st));
+  MGCN_CHECK_CUDA(cudaMemsetAsync(hub_count, 0, sizeof(int32_t), st));
+  MGCN_CHECK_CUDA(cudaMemsetAsync(bad_index, 0, sizeof(int32_t), st));
+  if (total > 0) {
+    MGCN_LAUNCH(k_make_keys, grid_for(total, 256), 256, 0, stream, edge_index, E, N, by,
+                loop_mode, total, keys_a, rowptr, bad_index);
+  }
+  int rc = exclusive_scan_i32(rowptr, rowptr, N + 1, tile_sums, stream);
+  if (rc != MGCN_OK) return rc;
+
+  const int32_t* sorted_vals = nullptr;
+  if (total > 0) {
+    const int passes = radix_passes(N);
+    const uint32_t* kin = keys_a;
+    uint32_t* kout = keys_b;
+    const int32_t* vin = nullptr;  // identity on the first pass
+    int32_t* vout = vals_a;
+    for (int p = 0; p < passes; ++p) {
+      const int shift = 8 * p;
+      MGCN_LAUNCH(k_radix_hist, num_blocks, 256, 0, stream, kin, total, shift, block_hist,
+                  num_blocks);
+      rc = exclusive_scan_i32(block_hist, block_hist, hist_len, tile_sums, stream);
+      if (rc != MGCN_OK) return rc;
+      MGCN_LAUNCH(k_radix_scatter, num_blocks, 256, 0, stream, kin, vin, kout, vout, total, shift,
+                  block_hist, num_blocks);
+      // ping-pong
+      const uint32_t* nk = kout;
+      kout = const_cast<uint32_t*>(kin == keys_a ? keys_a : keys_b);
+      kin = nk;
+      vin = vout;
+      vout = (vout == vals_a) ? vals_b : vals_a;
+    }
+    sorted_vals = vin;
+    MGCN_LAUNCH(k_finalize, grid_for(total, 256), 256, 0, stream, edge_index, E, by, total,
+                sorted_vals, rowptr, N, nbr, perm);
+  }
+  if (N > 0 && hub_cap > 0) {
+    MGCN_LAUNCH(k_find_hubs, (int)ceil_div(N, 256), 256, 0, stream, rowptr, N, hub_threshold,
+                hub_rows, hub_cap, hub_count);
+  }
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_degree_from_rowptr(const int32_t* rowptr, int64_t N, float* deg, void* stream) {
+  MGCN_REQUIRE(N >= 0, MGCN_ERR_RANGE);
+  if (N == 0) return MGCN_OK;
+  MGCN_REQUIRE(rowptr && deg, MGCN_ERR_NULL);
+  MGCN_LAUNCH(k_degree, (int)ceil_div(N, 256), 256, 0, stream, rowptr, N, deg);
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_weighted_degree(const mgcn_csr_t* g, const float* edge_weight, int64_t E,
+                                    float loop_weight, float* deg, void* stream) {
+  MGCN_REQUIRE(g && deg, MGCN_ERR_NULL);
+  if (g->n_rows == 0) return MGCN_OK;
+  MGCN_REQUIRE(g->rowptr && g->perm, MGCN_ERR_NULL);
+  MGCN_REQUIRE(E == 0 || edge_weight, MGCN_ERR_NULL);
+  MGCN_LAUNCH(k_weighted_degree, (int)ceil_div(g->n_rows, 256), 256, 0, stream, g->rowptr, g->perm,
+              edge_weight, E, loop_weight, g->n_rows, deg);
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream) {
+  MGCN_REQUIRE(N >= 0, MGCN_ERR_RANGE);
+  MGCN_REQUIRE(mode == 0 || mode == 1, MGCN_ERR_SHAPE);
+  if (N == 0) return MGCN_OK;
+  MGCN_REQUIRE(deg && dis, MGCN_ERR_NULL);
+  MGCN_LAUNCH(k_gcn_norm, (int)ceil_div(N, 256), 256, 0, stream, deg, N, mode, dis);
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_permute_edge_values(const mgcn_csr_t* g, const float* vals_in, int64_t E,
+                                        float loop_value, float* vals_out, void* stream) {
+  MGCN_REQUIRE(g && vals_out, MGCN_ERR_NULL);
+  if (g->nnz_cap == 0) return MGCN_OK;
+  MGCN_REQUIRE(g->rowptr && g->perm, MGCN_ERR_NULL);
+  MGCN_REQUIRE(E == 0 || vals_in, MGCN_ERR_NULL);
+  MGCN_LAUNCH(k_permute_vals, grid_for(g->nnz_cap, 256), 256, 0, stream, g->perm, g->rowptr,
+              g->n_rows, g->nnz_cap, vals_in, E, loop_value, vals_out);
+  return MGCN_OK;
+}

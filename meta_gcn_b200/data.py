@@ -1,0 +1,182 @@
+"""Graph batches and synthetic workloads — host side of the hot path.
+
+``GraphBatch`` honours the batching contract of the reference (Batch.from_data_list,
+src/gcn_meta/data/dataloader.py:11; kernel/train_eval.py:37-39): ``x``/``y`` concatenated along
+dim 0, ``edge_index`` concatenated along dim 1 with a cumulative node offset, ``batch`` = graph id per
+node (sorted ascending), ``slices_x`` = cumulative node boundaries (``batch.__slices__['x']``,
+optim/train_eval_gc.py:17).  Synthetic generators are seeded numpy and deterministic, so the CPU
+oracle and the GPU path see identical inputs.
+"""
+import numpy as np
+import torch
+
+BOTNET_NODES = 143107          # botnet_paper/botnet_plot.ipynb:408-409
+BOTNET_EDGE_ENTRIES = 1_500_000
+BOTNET_EVIL = 10_000
+
+
+class GraphBatch:
+    """x [N,F] f32, edge_index [2,E] i64, y, batch [N] i64, slices_x [G+1] (host list)."""
+
+    def __init__(self, x, edge_index, y=None, batch=None, slices_x=None, slices_e=None):
+        self.x, self.edge_index, self.y = x, edge_index, y
+        if batch is None:
+            batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
+        self.batch = batch
+        self.slices_x = list(slices_x) if slices_x is not None else [0, int(x.size(0))]
+        self.slices_e = list(slices_e) if slices_e is not None else [0, int(edge_index.size(1))]
+        self.__slices__ = {"x": self.slices_x, "edge_index": self.slices_e}
+
+    @property
+    def num_graphs(self):
+        return len(self.slices_x) - 1
+
+    @property
+    def num_nodes(self):
+        return int(self.x.size(0))
+
+    @property
+    def num_edges(self):
+        return int(self.edge_index.size(1))
+
+    @property
+    def num_features(self):
+        return int(self.x.size(1))
+
+    def _map(self, fn):
+        out = GraphBatch(fn(self.x), fn(self.edge_index), None if self.y is None else fn(self.y),
+                         fn(self.batch), self.slices_x, self.slices_e)
+        return out
+
+    def to(self, device, non_blocking=False):
+        return self._map(lambda t: t.to(device, non_blocking=non_blocking))
+
+    def pin_memory(self):
+        return self._map(lambda t: t.pin_memory())
+
+    @staticmethod
+    def from_data_list(graphs):
+        """graphs: list of dicts / objects with x, edge_index, y (numpy arrays or tensors)."""
+        xs, eis, ys, ids, sx, se = [], [], [], [], [0], [0]
+        off = 0
+        for g, item in enumerate(graphs):
+            get = item.get if isinstance(item, dict) else (lambda k, it=item: getattr(it, k, None))
+            x = torch.as_tensor(get("x"))
+            ei = torch.as_tensor(get("edge_index")).long()
+            n = x.size(0)
+            xs.append(x)
+            eis.append(ei + off)
+            y = get("y")
+            if y is not None:
+                ys.append(torch.as_tensor(y).reshape(-1) if np.ndim(y) <= 1 else torch.as_tensor(y))
+            ids.append(torch.full((n,), g, dtype=torch.long))
+            off += n
+            sx.append(off)
+            se.append(se[-1] + ei.size(1))
+        y = torch.cat(ys) if ys else None
+        return GraphBatch(torch.cat(xs), torch.cat(eis, dim=1), y, torch.cat(ids), sx, se)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge preprocessing with the reference's ordering (data_procs/undirected.py:6-35, loop.py:13-17,
+# data_add_degree.py:45-65): symmetrise, sort-unique by (src,dst), append loops, out-degree
+# ------------------------------------------------------------------------------------------------
+def symmetrise_sorted_with_loops(src, dst, num_nodes):
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    key = np.concatenate([src * num_nodes + dst, dst * num_nodes + src])
+    key = np.unique(key)  # sorted: lexicographic (src, dst)
+    loop = np.arange(num_nodes, dtype=np.int64)
+    row = np.concatenate([key // num_nodes, loop])
+    col = np.concatenate([key % num_nodes, loop])
+    return np.stack([row, col])
+
+
+def synth_botnet_graph(seed=0, num_nodes=BOTNET_NODES, edge_entries=BOTNET_EDGE_ENTRIES,
+                       evil=BOTNET_EVIL):
+    """C1: power-law background traffic graph + planted ring-with-chords P2P botnet (y=1),
+    symmetrised, sort-unique, self-loops appended; x = [1, out-degree] as the botnet HDF5 stores it
+    (botnet_plot.ipynb:382: x = [[1.,313.],[1.,3.],...])."""
+    rng = np.random.default_rng(seed)
+    n = int(num_nodes)
+    evil = min(int(evil), n // 2)
+    # botnet overlay: ring + power-of-two chords (Chord-like fingers)
+    bots = rng.choice(n, size=evil, replace=False)
+    bs, bd = [], []
+    if evil >= 3:
+        idx = np.arange(evil)
+        for hop in (1, 2, 4, 8, 64, 512):
+            if hop < evil:
+                bs.append(bots[idx])
+                bd.append(bots[(idx + hop) % evil])
+    bs = np.concatenate(bs) if bs else np.zeros(0, np.int64)
+    bd = np.concatenate(bd) if bd else np.zeros(0, np.int64)
+    undirected_target = max((int(edge_entries) - n) // 2 - len(bs), 0)
+    # background: one endpoint by power-law popularity, partner uniform
+    pop = (np.arange(1, n + 1, dtype=np.float64)) ** -0.8
+    pop /= pop.sum()
+    ids = rng.permutation(n)
+    m = int(undirected_target * 1.035) + 16  # head-room for duplicates / loops removed below
+    a = ids[rng.choice(n, size=m, p=pop)]
+    b = rng.integers(0, n, size=m)
+    ok = a != b
+    a, b = a[ok], b[ok]
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    _, first = np.unique(lo * n + hi, return_index=True)
+    first = np.sort(first)[:undirected_target]
+    a, b = a[first], b[first]
+    ei = symmetrise_sorted_with_loops(np.concatenate([a, bs]), np.concatenate([b, bd]), n)
+    deg = np.bincount(ei[0], minlength=n).astype(np.float32)
+    x = np.stack([np.ones(n, dtype=np.float32), deg], axis=1)
+    y = np.zeros(n, dtype=np.uint8)
+    y[bots] = 1
+    return {"x": x, "edge_index": ei, "y": y}
+
+
+def synth_tu_graph(rng, f_in=3, num_classes=2):
+    """C3: PROTEINS/ENZYMES-like small graph: ~40 nodes (clipped normal), undirected avg degree
+    3.7, random-normal features (kernel/plot.ipynb:45,245 show x=[45,3]/[20,3])."""
+    n = int(np.clip(round(rng.normal(40, 25)), 4, 620))
+    m = max(int(round(n * 3.7 / 2)), 1)
+    a = rng.integers(0, n, size=m)
+    b = rng.integers(0, n, size=m)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    key = np.unique(np.concatenate([a * n + b, b * n + a]))
+    ei = np.stack([key // n, key % n]).astype(np.int64)
+    x = rng.normal(size=(n, f_in)).astype(np.float32)
+    return {"x": x, "edge_index": ei, "y": np.array([rng.integers(0, num_classes)], dtype=np.int64)}
+
+
+def synth_tu_batch(seed=0, num_graphs=128, f_in=3, num_classes=2):
+    rng = np.random.default_rng(seed)
+    return GraphBatch.from_data_list([synth_tu_graph(rng, f_in, num_classes) for _ in range(num_graphs)])
+
+
+def synth_powerlaw_graph(seed, num_nodes, num_edges, alpha=0.8, symmetric=False):
+    """C4/C5: directed power-law edge list (popular sources, uniform targets), unsorted order."""
+    rng = np.random.default_rng(seed)
+    n = int(num_nodes)
+    pop = (np.arange(1, n + 1, dtype=np.float64)) ** -alpha
+    pop /= pop.sum()
+    cdf = np.cumsum(pop)
+    ids = rng.permutation(n)
+    src = ids[np.minimum(np.searchsorted(cdf, rng.random(int(num_edges))), n - 1)]
+    dst = rng.integers(0, n, size=int(num_edges))
+    if symmetric:
+        src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
+    return np.stack([src, dst]).astype(np.int64)
+
+
+class _Meta:
+    """dataset stand-in for the kernel/ nets' constructor (dataset.num_features / num_classes)"""
+
+    def __init__(self, num_features, num_classes):
+        self.num_features = num_features
+        self.num_classes = num_classes
+
+
+def dataset_meta(num_features, num_classes):
+    return _Meta(num_features, num_classes)

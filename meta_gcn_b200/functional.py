@@ -1,0 +1,150 @@
+"""Differentiable wrappers over the mgcn kernels (what the model classes call).
+
+Each Function's forward/backward launches libmgcn kernels only; the backward of the aggregation is
+the same row-owned kernel on the structure grouped by the other endpoint (no atomics, so gradients
+are deterministic — the reference's CUDA autograd uses index_add_/atomicAdd).
+"""
+import torch
+
+from . import ops
+from .graph import GraphStructure, structure_of, structure_of_index
+
+_ACT = {None: 0, "none": 0, "relu": 1, 0: 0, 1: 1}
+_REDUCE = {"add": 0, "sum": 0, "mean": 1}
+
+
+class _Aggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd, reduce, act):
+        out = ops.spmm_impl(*graph.fwd_args(), x, False, ev_fwd, nbr_scale, row_scale, reduce, bias,
+                            residual, act)
+        ctx.graph = graph
+        ctx.cfg = (reduce, act, bias is not None, residual is not None)
+        ctx.save_for_backward(out if act else None, nbr_scale, row_scale, ev_bwd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, nbr_scale, row_scale, ev_bwd = ctx.saved_tensors
+        reduce, act, has_bias, has_res = ctx.cfg
+        graph = ctx.graph
+        g = g.contiguous()
+        if act:
+            g = ops.relu_backward_impl(g, out)
+        d_bias = g.sum(0) if (has_bias and ctx.needs_input_grad[1]) else None
+        d_res = g if (has_res and ctx.needs_input_grad[2]) else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            gg = g
+            if reduce == 1:
+                gg = g / graph.in_degree().clamp(min=1).unsqueeze(1)
+            # transpose: rows = sources; the per-target factor is now gathered, the per-source
+            # factor scales the row
+            dx = ops.spmm_impl(*graph.bwd_args(), gg, False, ev_bwd, row_scale, nbr_scale, 0, None,
+                               None, 0)
+        return dx, d_bias, d_res, None, None, None, None, None, None, None
+
+
+def aggregate(x, graph, nbr_scale=None, row_scale=None, edge_weight=None, reduce="add", bias=None,
+              residual=None, act=None, loop_value=1.0):
+    """out_i = act( reduce_{e: target(e)=i}  x[source(e)] * w_e  + bias + residual_i ),
+    w_e = nbr_scale[source] * edge_weight[e] * row_scale[target]   (gcn_base_models.py:138-139,
+    223-240).  ``graph`` is a GraphStructure; edge_weight is in edge_index order."""
+    ev_fwd = ev_bwd = None
+    if edge_weight is not None:
+        ev_fwd, ev_bwd = graph.edge_values(edge_weight, loop_value)
+    return _Aggregate.apply(x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd,
+                            _REDUCE[reduce], _ACT[act])
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, add, w_out_in, act):
+        y = ops.linear_impl(x, w, w_out_in, bias, add, act)
+        ctx.cfg = (w_out_in, act, bias is not None, add is not None)
+        ctx.save_for_backward(x, w, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        w_out_in, act, has_bias, has_add = ctx.cfg
+        g = g.contiguous()
+        if act:
+            g = ops.relu_backward_impl(g, y)
+        dx = dw = db = dadd = None
+        if ctx.needs_input_grad[0]:
+            # dX = G W^T: the same kernel with the weight read through swapped strides
+            dx = ops.linear_impl(g, w, not w_out_in, None, None, 0)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw, db_ = ops.linear_wgrad_impl(x, g, w_out_in, has_bias)
+            db = db_ if has_bias else None
+        if has_add and ctx.needs_input_grad[3]:
+            dadd = g
+        return dx, dw, db, dadd, None, None
+
+
+def linear(x, weight, bias=None, add=None, act=None, weight_layout="in_out"):
+    """y = act(x @ W + bias + add).  weight_layout 'in_out': weight_node [Hi,Ho]
+    (gcn_base_models.py:201); 'out_in': nn.Linear.weight [Ho,Hi] (gcn_model.py:64,73)."""
+    return _Linear.apply(x, weight, bias, add, weight_layout == "out_in", _ACT[act])
+
+
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, offsets, mode):
+        ctx.mode = mode
+        ctx.n = x.size(0)
+        ctx.save_for_backward(offsets)
+        return ops.segment_reduce_impl(x, offsets, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        (offsets,) = ctx.saved_tensors
+        return ops.segment_broadcast_impl(g.contiguous(), offsets, ctx.n, ctx.mode), None, None
+
+
+def segment_pool(x, offsets, reduce="mean"):
+    """per-graph sum/mean over contiguous node ranges (global_mean_pool, kernel/gcn.py:29)"""
+    return _SegmentReduce.apply(x, offsets, _REDUCE[reduce])
+
+
+def pool_by_batch(x, batch, size=None, reduce="mean"):
+    """global_{mean,add}_pool(x, batch, size): batch is sorted ascending (Batch.from_data_list)."""
+    if size is None:
+        size = int(batch.max().item()) + 1 if batch.numel() else 0  # same host sync as PyG
+    offsets = ops.batch_to_offsets_impl(batch, size)
+    return segment_pool(x, offsets, reduce)
+
+
+class _ScatterRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, graph, index, reduce):
+        out = ops.spmm_impl(*graph.fwd_args(), src, True, None, None, None, reduce, None, None, 0)
+        ctx.graph = graph
+        ctx.reduce = reduce
+        ctx.save_for_backward(index)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (index,) = ctx.saved_tensors
+        if ctx.reduce == 1:
+            g = g / ctx.graph.in_degree().clamp(min=1).unsqueeze(1)
+        return g.index_select(0, index), None, None, None
+
+
+def scatter_rows(src, index, dim_size=None, reduce="add"):
+    """Primitive seam: scatter_('add'|'mean', src[E,H], index[E], dim_size) (common.py:37-66) as a
+    deterministic row-owned gather-sum over a stable sort of ``index``."""
+    squeeze = src.dim() == 1
+    src2 = src.unsqueeze(1) if squeeze else src
+    if src2.dim() != 2:
+        src2 = src2.reshape(src2.size(0), -1)
+    if dim_size is None:
+        dim_size = int(index.max().item()) + 1 if index.numel() else 0
+    graph = structure_of_index(index, dim_size)
+    out = _ScatterRows.apply(src2, graph, index, _REDUCE[reduce])
+    if squeeze:
+        return out.squeeze(1)
+    return out.reshape(dim_size, *src.shape[1:])

@@ -1,0 +1,42 @@
+"""Mirror of src/gcn_meta/models/common.py for the hot path: the ``scatter_`` primitive seam
+(common.py:37-66) and the activation factory (common.py:27-34), backed by libmgcn kernels."""
+import torch.nn as nn
+
+from ... import functional as F_mgcn
+
+
+class Identity(nn.Module):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+    def forward(self, input):
+        return input
+
+
+_ACTIVATIONS = {
+    "lrelu": lambda slope: nn.LeakyReLU(slope),
+    "relu": lambda slope: nn.ReLU(),
+    "elu": lambda slope: nn.ELU(),
+    "none": lambda slope: Identity(),
+}
+
+
+def activation(act, negative_slope=0.2):
+    return _ACTIVATIONS[act](negative_slope)
+
+
+def scatter_(name, src, index, dim_size=None, out=None):
+    """Row-wise aggregation of ``src`` by ``index`` along dim 0 ('add' | 'mean').
+
+    Same call shape as the reference (common.py:37); computed by the row-owned gather-sum kernel
+    over a stable sort of ``index`` — deterministic, and for rows below the hub threshold the same
+    fp32 summation order as the reference's CPU scatter_add.  'max' belongs to the attention models
+    and is outside this hot path."""
+    if name == "max":
+        raise NotImplementedError("scatter_('max') (attention / hard-attention models) is out of scope")
+    if name not in ("add", "mean"):
+        raise AssertionError(name)
+    res = F_mgcn.scatter_rows(src, index, dim_size, name)
+    if out is not None:
+        res = out + res if name == "add" else res
+    return res

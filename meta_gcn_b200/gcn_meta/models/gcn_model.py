@@ -1,0 +1,130 @@
+"""Mirror of src/gcn_meta/models/gcn_model.py: ``GCNModel`` (stack of layers + residual Linear every
+``residual_hop`` + final projection + optional per-graph mean, gcn_model.py:8-125) and ``GCNLayer``
+(gcn_model.py:128-197), with the same constructor kwargs and parameter names
+(gcn_net.N.gcn.node_models.K.weight_node, residuals.N.weight/bias, final.weight/bias).
+
+What changes underneath: the edge_index -> row structure build and the degree factors are done once
+per forward and shared by all layers; ReLU after the aggregation is fused into its epilogue; the
+residual Linear, the add and the outer ReLU are one narrow-transform launch."""
+import torch
+import torch.nn as nn
+
+from ... import functional as F_mgcn
+from ...graph import structure_of
+from .common import activation
+from .gcn_base_models import NodeModelBase
+from .gcn_multi_kernel import GCNMultiKernel
+
+
+class GCNLayer(nn.Module):
+    def __init__(self, in_channels, out_channels, in_edgedim=None, deg_norm="sm", edge_gate=None,
+                 aggr="add", bias=True, num_kernel=1, nodemodel="additive", non_linear="relu", **kwargs):
+        super().__init__()
+        self.gcn = GCNMultiKernel(in_channels, out_channels, in_edgedim, deg_norm=deg_norm,
+                                  edge_gate=edge_gate, aggr=aggr, bias=bias, num_kernel=num_kernel,
+                                  nodemodel=nodemodel, **kwargs)
+        self.non_linear = activation(non_linear)
+        self._act_name = non_linear
+
+    def reset_parameters(self):
+        self.gcn.reset_parameters()
+
+    def forward(self, x, edge_index_K, edge_attr_K=None, deg_K=None, edge_weight_K=None, **kwargs):
+        if self._act_name == "relu":
+            return self.gcn(x, edge_index_K, edge_attr_K, deg_K, edge_weight_K, _act="relu", **kwargs)
+        xo = self.gcn(x, edge_index_K, edge_attr_K, deg_K, edge_weight_K, **kwargs)
+        return self.non_linear(xo)
+
+
+class GCNModel(nn.Module):
+    def __init__(self, in_channels, enc_sizes, num_classes, non_linear="relu",
+                 non_linear_layer_wise="relu", residual_hop=None, dropout=0.5, final_layer_config=None,
+                 final_type="none", pred_on="node", **kwargs):
+        assert final_type in ["none", "proj"]
+        assert pred_on in ["node", "graph"]
+        super().__init__()
+        self.in_channels = in_channels
+        self.enc_sizes = [in_channels, *enc_sizes]
+        self.num_layers = len(self.enc_sizes) - 1
+        self.num_classes = num_classes
+        self.residual_hop = residual_hop
+        self.non_linear_layer_wise = non_linear_layer_wise
+        self.final_type = final_type
+        self.pred_on = pred_on
+        nheads = kwargs.pop("nheads", 1)
+        self.nheads = [nheads] * self.num_layers if isinstance(nheads, int) else list(nheads)
+        assert len(self.nheads) == self.num_layers
+        # attention-only kwargs of the reference CLI are accepted and ignored by the additive model
+        pairs = list(zip(self.enc_sizes, self.enc_sizes[1:]))
+        layers = []
+        for i, (cin, cout) in enumerate(pairs):
+            kw = dict(kwargs)
+            if final_layer_config is not None and i == len(pairs) - 1:
+                assert isinstance(final_layer_config, dict)
+                kw.update(final_layer_config)
+            layers.append(GCNLayer(cin, cout, nheads=self.nheads[i], non_linear=non_linear_layer_wise, **kw))
+        self.gcn_net = nn.ModuleList(layers)
+        self.dropout = nn.Dropout(dropout)
+        if residual_hop is not None and residual_hop > 0:
+            srcs = range(0, len(self.enc_sizes), residual_hop)
+            dsts = range(residual_hop, len(self.enc_sizes), residual_hop)
+            self.residuals = nn.ModuleList(
+                [nn.Linear(self.enc_sizes[i], self.enc_sizes[j]) for i, j in zip(srcs, dsts)])
+            self.non_linear = activation(non_linear)
+            self._res_act = non_linear
+            self.num_residuals = len(self.residuals)
+        self.final = nn.Linear(self.enc_sizes[-1], num_classes) if final_type == "proj" else nn.Identity()
+
+    def reset_parameters(self):
+        for net in self.gcn_net:
+            net.reset_parameters()
+        if self.residual_hop is not None:
+            for net in self.residuals:
+                net.reset_parameters()
+        if self.final_type != "none":
+            self.final.reset_parameters()
+
+    def _shared_degree_factors(self, x, edge_index_K, deg_K, edge_weight_K):
+        """dis[N] once per forward when all layers see one edge set with one degree vector (the
+        reference recomputes norm[E] in every layer: gcn_base_models.py:215)."""
+        ei = edge_index_K if isinstance(edge_index_K, torch.Tensor) else (
+            edge_index_K[0] if len(edge_index_K) == 1 else None)
+        if ei is None:
+            return None
+        nm = self.gcn_net[0].gcn.node_models[0]
+        if nm.deg_norm is None:
+            return None
+        deg = deg_K if isinstance(deg_K, torch.Tensor) or deg_K is None else deg_K[0]
+        ew = edge_weight_K if isinstance(edge_weight_K, torch.Tensor) or edge_weight_K is None \
+            else edge_weight_K[0]
+        return NodeModelBase.degree_factors(ei, x.size(0), deg, ew, nm.deg_norm)
+
+    def forward(self, x, edge_index_K, edge_attr_K=None, deg_K=None, edge_weight_K=None, **kwargs):
+        dis = self._shared_degree_factors(x, edge_index_K, deg_K, edge_weight_K)
+        hop = self.residual_hop
+        xr_src, add_xr_at, res_idx = None, -1, -1
+        for n, net in enumerate(self.gcn_net):
+            xo = net(x, edge_index_K, edge_attr_K, deg_K, edge_weight_K, _dis=dis, **kwargs)
+            xo = self.dropout(xo)
+            if hop is not None and hop > 0:
+                if n % hop == 0 and (n // hop) < self.num_residuals:
+                    xr_src, res_idx = x, n // hop     # residual branch reads this layer's input
+                    add_xr_at = n + hop - 1
+                if n == add_xr_at:
+                    lin = self.residuals[res_idx]
+                    last = n == self.num_layers - 1
+                    fuse_relu = (not last) and self._res_act == "relu"
+                    # relu(xo + Linear(x)) in one launch (gcn_model.py:96-105)
+                    xo = F_mgcn.linear(xr_src, lin.weight, lin.bias, add=xo,
+                                       act="relu" if fuse_relu else None, weight_layout="out_in")
+                    if not last and not fuse_relu:
+                        xo = self.non_linear(xo)
+            x = xo
+        if self.final_type == "proj":
+            x = F_mgcn.linear(x, self.final.weight, self.final.bias, weight_layout="out_in")
+        if self.pred_on == "graph":
+            assert "batch_slices_x" in kwargs
+            sl = kwargs["batch_slices_x"]
+            offsets = torch.as_tensor(list(sl), dtype=torch.int32).to(x.device)
+            x = F_mgcn.segment_pool(x, offsets, "mean")
+        return x

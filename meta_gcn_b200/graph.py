@@ -1,0 +1,147 @@
+"""Row-owned adjacency structures of one ``edge_index`` and a small identity-keyed cache.
+
+The reference walks COO ``edge_index`` with index_select / scatter_add in every layer
+(gcn_base_models.py:223-237).  Here the COO list is turned ONCE per batch into two int32
+structures — grouped by target (forward aggregation) and grouped by source (backward, the
+transpose) — by ``mgcn_csr_build``; all layers of the model then share them.
+"""
+from collections import OrderedDict, namedtuple
+
+import torch
+
+from . import ops
+
+Csr = namedtuple("Csr", "rowptr nbr perm hub_rows hub_count bad hub_threshold")
+
+LOOPS_KEEP = 0      # edge_index used as given (gcn_meta: loops are already in the data, loop.py:13-17)
+LOOPS_REMOVE = 1    # PyG remove_self_loops (GINConv)
+LOOPS_ADD_REMAINING = 2  # PyG add_remaining_self_loops (GCNConv.norm, SAGEConv)
+
+
+def _csr_args(c):
+    return (c.rowptr, c.nbr, c.perm, c.hub_rows, c.hub_count, c.hub_threshold)
+
+
+class GraphStructure:
+    """Lazily built forward (by target) and backward (by source) structures of an edge_index."""
+
+    def __init__(self, edge_index, num_nodes, loop_mode=LOOPS_KEEP,
+                 hub_threshold=ops.DEFAULT_HUB_THRESHOLD):
+        if not edge_index.is_cuda:
+            raise RuntimeError("GraphStructure needs a CUDA edge_index (no CPU fallback)")
+        self.edge_index = edge_index
+        self.num_nodes = int(num_nodes)
+        self.num_edges = int(edge_index.size(1))
+        self.loop_mode = int(loop_mode)
+        self.hub_threshold = int(hub_threshold)
+        self._fwd = None
+        self._bwd = None
+        self._deg = {}
+
+    def _build(self, by):
+        out = ops.csr_build_impl(self.edge_index, self.num_nodes, by, self.loop_mode,
+                                 self.hub_threshold)
+        return Csr(*out, self.hub_threshold)
+
+    @property
+    def fwd(self):
+        """rows = targets (edge_index[1]), nbr = sources: out_i = sum over incoming edges"""
+        if self._fwd is None:
+            self._fwd = self._build(1)
+        return self._fwd
+
+    @property
+    def bwd(self):
+        """rows = sources (edge_index[0]), nbr = targets: the transpose, used by autograd"""
+        if self._bwd is None:
+            self._bwd = self._build(0)
+        return self._bwd
+
+    def fwd_args(self):
+        return _csr_args(self.fwd)
+
+    def bwd_args(self):
+        return _csr_args(self.bwd)
+
+    def out_degree(self):
+        """float degree over edge_index[0] (after loop handling): gcn_base_models.py:126"""
+        if "out" not in self._deg:
+            self._deg["out"] = ops.degree_impl(self.bwd.rowptr)
+        return self._deg["out"]
+
+    def in_degree(self):
+        if "in" not in self._deg:
+            self._deg["in"] = ops.degree_impl(self.fwd.rowptr)
+        return self._deg["in"]
+
+    def weighted_out_degree(self, edge_weight, loop_weight=1.0):
+        b = self.bwd
+        return ops.weighted_degree_impl(b.rowptr, b.nbr, b.perm, edge_weight, loop_weight)
+
+    def edge_values(self, edge_weight, loop_value=1.0):
+        """edge weights (input edge order) -> (forward row order, backward row order)"""
+        f, b = self.fwd, self.bwd
+        return (ops.permute_edge_values_impl(f.rowptr, f.nbr, f.perm, edge_weight, loop_value),
+                ops.permute_edge_values_impl(b.rowptr, b.nbr, b.perm, edge_weight, loop_value))
+
+    def check_indices(self):
+        """host-synchronising validation (debug entry point): raises on out-of-range endpoints"""
+        if int(self.fwd.bad.item()) != 0:
+            raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+
+
+class _StructureCache:
+    """Keeps the structures of the last few edge_index tensors (keyed on storage identity and
+    version counter), so that the L layers of a model and its backward build them once."""
+
+    def __init__(self, capacity=8):
+        self.capacity = capacity
+        self._items = OrderedDict()
+
+    def get(self, edge_index, num_nodes, loop_mode, hub_threshold=ops.DEFAULT_HUB_THRESHOLD):
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version,
+               int(num_nodes), int(loop_mode), int(hub_threshold), edge_index.device.index)
+        hit = self._items.get(key)
+        if hit is not None:
+            self._items.move_to_end(key)
+            return hit
+        gs = GraphStructure(edge_index, num_nodes, loop_mode, hub_threshold)
+        self._items[key] = gs  # holds edge_index alive, so the data_ptr cannot be recycled
+        while len(self._items) > self.capacity:
+            self._items.popitem(last=False)
+        return gs
+
+    def clear(self):
+        self._items.clear()
+
+
+_CACHE = _StructureCache()
+
+
+def structure_of(edge_index, num_nodes, loop_mode=LOOPS_KEEP,
+                 hub_threshold=ops.DEFAULT_HUB_THRESHOLD):
+    return _CACHE.get(edge_index, num_nodes, loop_mode, hub_threshold)
+
+
+_INDEX_CACHE = OrderedDict()
+
+
+def structure_of_index(index, dim_size, hub_threshold=ops.DEFAULT_HUB_THRESHOLD):
+    """Structure for the primitive seam scatter_(name, src, index): rows = values of ``index``,
+    perm = positions in ``index`` (a stable sort).  Cached on the identity of ``index``."""
+    key = (index.data_ptr(), index.numel(), index._version, int(dim_size), int(hub_threshold),
+           index.device.index)
+    hit = _INDEX_CACHE.get(key)
+    if hit is not None:
+        _INDEX_CACHE.move_to_end(key)
+        return hit[1]
+    gs = GraphStructure(torch.stack([index, index]), dim_size, LOOPS_KEEP, hub_threshold)
+    _INDEX_CACHE[key] = (index, gs)
+    while len(_INDEX_CACHE) > 8:
+        _INDEX_CACHE.popitem(last=False)
+    return gs
+
+
+def clear_structure_cache():
+    _CACHE.clear()
+    _INDEX_CACHE.clear()
