@@ -1,0 +1,106 @@
+"""Narrow dense transform, its gradients, relu backward and the segment reductions vs fp64 /
+the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from meta_gcn_b200 import functional as F_mgcn
+from meta_gcn_b200 import ops
+from oracle import port
+from util import assert_bitexact, assert_parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("N", [1, 127, 128, 129, 1000, 5001])
+@pytest.mark.parametrize("Hi,Ho", [(1, 32), (3, 64), (32, 32), (32, 2), (33, 47), (64, 64), (100, 256), (256, 256)])
+def test_linear_forward(N, Hi, Ho):
+    g = torch.Generator().manual_seed(N * 7 + Hi)
+    x = torch.randn(N, Hi, generator=g)
+    w = torch.randn(Hi, Ho, generator=g) / max(Hi, 1) ** 0.5
+    b = torch.randn(Ho, generator=g)
+    add = torch.randn(N, Ho, generator=g)
+    ref64 = x.double() @ w.double()
+    y = ops.linear_impl(x.to(DEV), w.to(DEV), False)
+    assert_parity(y, ref64, "x@W")
+    # nn.Linear layout + bias + add + relu
+    y2 = ops.linear_impl(x.to(DEV), w.t().contiguous().to(DEV), True, b.to(DEV), add.to(DEV), 1)
+    assert_parity(y2, torch.relu(ref64 + b.double() + add.double()), "relu(x@W^T + b + add)")
+    # fp32 CPU matmul (the reference's sgemm) is within the same tolerance of our result
+    assert_parity(y, x @ w, "vs torch CPU fp32")
+
+
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 4097, 20000])
+@pytest.mark.parametrize("Hi,Ho", [(1, 32), (3, 64), (32, 32), (32, 2), (33, 47), (100, 256)])
+@pytest.mark.parametrize("out_in", [False, True])
+def test_linear_weight_gradient(N, Hi, Ho, out_in):
+    g = torch.Generator().manual_seed(N + Hi * 3 + Ho)
+    x = torch.randn(N, Hi, generator=g)
+    gy = torch.randn(N, Ho, generator=g)
+    dw, db = ops.linear_wgrad_impl(x.to(DEV), gy.to(DEV), out_in, True)
+    ref = x.double().t() @ gy.double()
+    assert_parity(dw, ref.t() if out_in else ref, "dW")
+    assert_parity(db, gy.double().sum(0), "db")
+    dw2, _ = ops.linear_wgrad_impl(x.to(DEV), gy.to(DEV), out_in, True)
+    assert_bitexact(dw2, dw, "deterministic dW")
+
+
+def test_linear_autograd_matches_torch():
+    N, Hi, Ho = 3000, 32, 32
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, Hi, generator=g, requires_grad=True)
+    w = (torch.randn(Ho, Hi, generator=g) / Hi ** 0.5).requires_grad_(True)
+    b = torch.randn(Ho, generator=g, requires_grad=True)
+    add = torch.randn(N, Ho, generator=g, requires_grad=True)
+    wgt = torch.randn(N, Ho, generator=g)
+    ref = torch.relu(torch.nn.functional.linear(x, w, b) + add)
+    (ref * wgt).sum().backward()
+    xd, wd, bd, ad = (t.detach().to(DEV).requires_grad_(True) for t in (x, w, b, add))
+    out = F_mgcn.linear(xd, wd, bd, add=ad, act="relu", weight_layout="out_in")
+    (out * wgt.to(DEV)).sum().backward()
+    assert_parity(out, ref, "y")
+    assert_parity(xd.grad, x.grad, "dx")
+    assert_parity(wd.grad, w.grad, "dW")
+    assert_parity(bd.grad, b.grad, "db")
+    assert_parity(ad.grad, add.grad, "dadd")
+
+
+def test_relu_backward_exact():
+    y = torch.randn(1000, 33)
+    y[::7] = 0
+    g = torch.randn(1000, 33)
+    out = ops.relu_backward_impl(g.to(DEV), y.to(DEV))
+    assert_bitexact(out, torch.where(y > 0, g, torch.zeros_like(g)), "relu'")
+
+
+@pytest.mark.parametrize("H", [1, 3, 32, 64, 100, 300])
+@pytest.mark.parametrize("mode", ["add", "mean"])
+def test_segment_reduce_small_graphs_bitexact(H, mode):
+    sizes = [5, 0, 40, 1, 64, 17, 0, 33]
+    n = sum(sizes)
+    batch = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+    x = torch.randn(n, H)
+    out = F_mgcn.pool_by_batch(x.to(DEV), batch.to(DEV), len(sizes), mode)
+    assert_bitexact(out, port.scatter_rows(mode, x, batch, len(sizes)), f"pool {mode} H={H}")
+    # size inferred from batch (host sync, like PyG)
+    out2 = F_mgcn.pool_by_batch(x.to(DEV), batch[: n - 33].to(DEV), None, mode)
+    assert out2.shape[0] == 6
+
+
+@pytest.mark.parametrize("H", [2, 32, 256])
+def test_segment_reduce_large_graphs_and_backward(H):
+    sizes = [5000, 3, 12000, 700]
+    n = sum(sizes)
+    batch = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+    x = torch.randn(n, H, requires_grad=True)
+    wgt = torch.randn(len(sizes), H)
+    ref = port.scatter_rows("mean", x, batch, len(sizes))
+    (ref * wgt).sum().backward()
+    xd = x.detach().to(DEV).requires_grad_(True)
+    out = F_mgcn.pool_by_batch(xd, batch.to(DEV), len(sizes), "mean")
+    (out * wgt.to(DEV)).sum().backward()
+    assert_parity(out, ref, "mean pool")
+    assert_parity(xd.grad, x.grad, "mean pool backward")
+    out_b = F_mgcn.pool_by_batch(xd, batch.to(DEV), len(sizes), "mean")
+    assert_bitexact(out_b, out, "deterministic")

@@ -1,0 +1,177 @@
+"""Row-owned aggregation vs the oracle's index_select -> mul -> scatter_add (CPU, edge order)."""
+import numpy as np
+import pytest
+import torch
+
+from meta_gcn_b200 import functional as F_mgcn
+from meta_gcn_b200 import ops
+from meta_gcn_b200.graph import GraphStructure
+from oracle import port
+from util import assert_bitexact, assert_parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rand_graph(seed, n, e, hub=None):
+    rng = np.random.default_rng(seed)
+    ei = rng.integers(0, n, size=(2, e))
+    if hub:
+        ei[1, : hub] = 0          # node 0 receives `hub` messages
+        ei[0, hub: 2 * hub] = 1   # node 1 sends `hub` messages
+    return ei
+
+
+def oracle_aggregate(ei, n, x, w=None, reduce="add"):
+    ei_t = torch.from_numpy(ei)
+    msg = x[ei_t[0]]
+    if w is not None:
+        msg = msg * w.view(-1, 1)
+    return port.scatter_rows(reduce, msg, ei_t[1], n)
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 4, 8, 12, 16, 32, 33, 64, 100, 128, 256, 512])
+def test_plain_sum_is_bitexact_below_hub_threshold(H):
+    n, e = 700, 9000
+    ei = rand_graph(H, n, e)
+    x = torch.randn(n, H)
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=1 << 30)
+    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV))
+    assert_bitexact(out, oracle_aggregate(ei, n, x), f"sum H={H}")
+    outm = ops.spmm_impl(*g.fwd_args(), x.to(DEV), reduce=1)
+    assert_bitexact(outm, oracle_aggregate(ei, n, x, reduce="mean"), f"mean H={H}")
+
+
+@pytest.mark.parametrize("H", [1, 32, 64, 100, 256])
+def test_sym_norm_weights_follow_reference_rounding(H):
+    """w_e = dis[row]*dis[col] (gcn_base_models.py:138-139), msg = x_j * w_e, edge-order sum"""
+    n, e = 900, 12000
+    ei = rand_graph(100 + H, n, e)
+    x = torch.randn(n, H)
+    deg = torch.bincount(torch.from_numpy(ei[0]), minlength=n).float()
+    norm = port.degnorm_const(torch.from_numpy(ei), n, deg=deg, method="sm")
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=1 << 30)
+    dis = ops.gcn_norm_impl(deg.to(DEV), 0)
+    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV), nbr_scale=dis, row_scale=dis)
+    assert_bitexact(out, oracle_aggregate(ei, n, x, norm), f"sm H={H}")
+    # with edge weights: dis[row] * w * dis[col]
+    ew = torch.rand(e) + 0.5
+    normw = port.degnorm_const(torch.from_numpy(ei), n, edge_weight=ew, method="sm")
+    degw = g.weighted_out_degree(ew.to(DEV))
+    disw = ops.gcn_norm_impl(degw, 0)
+    ev_f, _ = g.edge_values(ew.to(DEV))
+    outw = ops.spmm_impl(*g.fwd_args(), x.to(DEV), edge_val=ev_f, nbr_scale=disw, row_scale=disw)
+    assert_bitexact(outw, oracle_aggregate(ei, n, x, normw), f"sm+w H={H}")
+    # rw: x * deg^-1 gathered (gcn_base_models.py:217-220)
+    dis_rw = ops.gcn_norm_impl(deg.to(DEV), 1)
+    out_rw = ops.spmm_impl(*g.fwd_args(), x.to(DEV), nbr_scale=dis_rw)
+    ref_rw = port.scatter_rows("add", (x * deg.pow(-1).nan_to_num(posinf=0).view(-1, 1))[torch.from_numpy(ei[0])],
+                               torch.from_numpy(ei[1]), n)
+    assert_bitexact(out_rw, ref_rw, f"rw H={H}")
+
+
+@pytest.mark.parametrize("H", [3, 32, 64, 256])
+@pytest.mark.parametrize("hub_t", [16, 256])
+def test_hub_rows_tree_sum_within_tolerance_and_deterministic(H, hub_t):
+    n, e = 500, 20000
+    ei = rand_graph(7 + H, n, e, hub=6000)
+    x = torch.randn(n, H)
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=hub_t)
+    assert int(g.fwd.hub_count.item()) >= 1
+    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV))
+    ref = oracle_aggregate(ei, n, x)
+    assert_parity(out, ref, f"hub sum H={H}")
+    # non-hub rows stay bit-exact
+    deg_in = np.bincount(ei[1], minlength=n)
+    small = torch.from_numpy(deg_in <= hub_t)
+    assert_bitexact(out.cpu()[small], ref[small], "non-hub rows")
+    again = ops.spmm_impl(*g.fwd_args(), x.to(DEV))
+    assert_bitexact(again, out, "run-to-run determinism")
+    outm = ops.spmm_impl(*g.fwd_args(), x.to(DEV), reduce=1)
+    assert_parity(outm, oracle_aggregate(ei, n, x, reduce="mean"), f"hub mean H={H}")
+
+
+@pytest.mark.parametrize("H", [5, 32])
+def test_fused_epilogue(H):
+    n, e = 300, 3000
+    ei = rand_graph(11, n, e)
+    x, res, bias = torch.randn(n, H), torch.randn(n, H), torch.randn(H)
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=1 << 30)
+    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV), bias=bias.to(DEV), residual=res.to(DEV), act=1)
+    ref = torch.relu(oracle_aggregate(ei, n, x) + bias + res)
+    assert_bitexact(out, ref, "relu(sum + bias + residual)")
+
+
+def test_rows_without_edges_and_empty_inputs():
+    n = 50
+    ei = np.array([[1, 2, 3], [4, 4, 9]])
+    x = torch.randn(n, 32)
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n)
+    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV), reduce=1, bias=torch.ones(32, device=DEV))
+    ref = oracle_aggregate(ei, n, x, reduce="mean") + 1
+    assert_bitexact(out, ref, "isolated rows")
+    g0 = GraphStructure(torch.zeros(2, 0, dtype=torch.long, device=DEV), n)
+    out0 = ops.spmm_impl(*g0.fwd_args(), x.to(DEV))
+    assert (out0 == 0).all()
+
+
+def test_scatter_rows_primitive_seam():
+    """scatter_('add'|'mean', src[E,H], index) — common.py:37-66 — incl. 1-D src and autograd"""
+    n, e = 400, 6000
+    rng = np.random.default_rng(3)
+    idx = torch.from_numpy(rng.integers(0, n, size=e))
+    for shape in ((e, 16), (e,), (e, 3)):
+        src = torch.randn(*shape)
+        for name in ("add", "mean"):
+            out = F_mgcn.scatter_rows(src.to(DEV), idx.to(DEV), n, name)
+            assert_bitexact(out, port.scatter_rows(name, src, idx, n), f"scatter_{name}{shape}")
+    src = torch.randn(e, 8, requires_grad=True)
+    src_d = src.detach().to(DEV).requires_grad_(True)
+    wgt = torch.randn(n, 8)
+    (F_mgcn.scatter_rows(src_d, idx.to(DEV), n, "mean") * wgt.to(DEV)).sum().backward()
+    (port.scatter_rows("mean", src, idx, n) * wgt).sum().backward()
+    assert_parity(src_d.grad, src.grad, "scatter_mean backward")
+
+
+@pytest.mark.parametrize("reduce", ["add", "mean"])
+@pytest.mark.parametrize("H", [32, 48])
+def test_aggregate_backward_matches_autograd_of_reference_path(reduce, H):
+    n, e = 600, 8000
+    ei = rand_graph(21, n, e, hub=700)
+    deg = torch.bincount(torch.from_numpy(ei[0]), minlength=n).float().clamp(min=1)
+    ew = torch.rand(e) + 0.5
+    x = torch.randn(n, H, requires_grad=True)
+    res = torch.randn(n, H, requires_grad=True)
+    bias = torch.randn(H, requires_grad=True)
+    wgt = torch.randn(n, H)
+    # reference path on CPU
+    ei_t = torch.from_numpy(ei)
+    dis = deg.pow(-0.5)
+    norm = dis[ei_t[0]] * ew * dis[ei_t[1]]
+    ref = torch.relu(port.scatter_rows(reduce, x[ei_t[0]] * norm.view(-1, 1), ei_t[1], n) + bias + res)
+    (ref * wgt).sum().backward()
+    # CUDA path
+    xd, rd, bd = (t.detach().to(DEV).requires_grad_(True) for t in (x, res, bias))
+    g = GraphStructure(ei_t.to(DEV), n, hub_threshold=64)
+    disd = ops.gcn_norm_impl(deg.to(DEV), 0)
+    out = F_mgcn.aggregate(xd, g, disd, disd, ew.to(DEV), reduce, bd, rd, "relu")
+    (out * wgt.to(DEV)).sum().backward()
+    assert_parity(out, ref, "forward")
+    assert_parity(xd.grad, x.grad, "dx")
+    assert_parity(rd.grad, res.grad, "dresidual")
+    assert_parity(bd.grad, bias.grad, "dbias")
+
+
+def test_backward_is_deterministic():
+    n, e, H = 2000, 60000, 32
+    ei = rand_graph(5, n, e, hub=3000)
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n)
+    x = torch.randn(n, H, device=DEV, requires_grad=True)
+    wgt = torch.randn(n, H, device=DEV)
+    grads = []
+    for _ in range(3):
+        x.grad = None
+        (F_mgcn.aggregate(x, g) * wgt).sum().backward()
+        grads.append(x.grad.clone())
+    assert_bitexact(grads[1], grads[0], "dx run 2")
+    assert_bitexact(grads[2], grads[0], "dx run 3")

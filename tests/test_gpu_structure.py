@@ -1,0 +1,133 @@
+"""edge_index -> row structure, degree and normalisation: BIT-EXACT against the integer oracle
+(oracle/port.py csr_oracle = stable argsort + bincount + cumsum) and torch CPU."""
+import numpy as np
+import pytest
+import torch
+
+from meta_gcn_b200 import ops
+from meta_gcn_b200.data import synth_botnet_graph
+from oracle import port
+from util import assert_bitexact
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build(ei_np, n, by, mode, hub_t=256):
+    ei = torch.from_numpy(np.ascontiguousarray(ei_np)).long().to(DEV)
+    out = ops.csr_build_impl(ei, n, by, mode, hub_t)
+    torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in out]
+
+
+def check_against_oracle(ei_np, n, by, mode, hub_t=256):
+    rowptr, nbr, perm, hubs, hcount, bad = build(ei_np, n, by, mode, hub_t)
+    o_rowptr, o_nbr, o_perm = port.csr_oracle(ei_np, n, by, mode)
+    assert bad[0] == 0
+    assert_bitexact(rowptr, o_rowptr, "rowptr")
+    nnz = int(o_rowptr[-1])
+    assert_bitexact(nbr[:nnz], o_nbr, "nbr")
+    assert_bitexact(perm[:nnz], o_perm, "perm")
+    assert (perm[nnz:] == -1).all()
+    deg = np.diff(o_rowptr)
+    want_hubs = np.nonzero(deg > hub_t)[0]
+    assert hcount[0] == len(want_hubs)
+    assert sorted(hubs[:hcount[0]].tolist()) == want_hubs.tolist()
+
+
+@pytest.mark.parametrize("n,e", [(1, 1), (5, 0), (7, 3), (100, 4095), (100, 4096), (100, 4097), (300, 8193),
+                                 (1000, 50000), (70000, 200000), (300000, 100000)])
+@pytest.mark.parametrize("by", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_csr_build_random(n, e, by, mode):
+    rng = np.random.default_rng(n * 31 + e)
+    ei = rng.integers(0, n, size=(2, e))
+    check_against_oracle(ei, n, by, mode)
+
+
+def test_csr_build_empty_graph():
+    rowptr, nbr, perm, hubs, hcount, bad = build(np.zeros((2, 0), np.int64), 0, 1, 0)
+    assert rowptr.tolist() == [0] and hcount[0] == 0
+    rowptr, nbr, perm, hubs, hcount, bad = build(np.zeros((2, 0), np.int64), 4, 1, 2)
+    assert rowptr.tolist() == [0, 1, 2, 3, 4] and nbr.tolist() == [0, 1, 2, 3]
+
+
+def test_csr_build_hubs_and_duplicates():
+    # star with duplicated spokes: one row of 5000 entries, stable order must keep duplicates apart
+    n = 600
+    spokes = np.tile(np.arange(1, 501), 10)
+    ei = np.stack([spokes, np.zeros_like(spokes)])
+    ei = np.concatenate([ei, ei[::-1]], axis=1)
+    for by in (0, 1):
+        check_against_oracle(ei, n, by, 0, hub_t=128)
+        check_against_oracle(ei, n, by, 2, hub_t=128)
+
+
+def test_csr_build_flags_out_of_range_indices():
+    ei = np.array([[0, 1, 9], [1, 0, 2]])
+    rowptr, nbr, perm, hubs, hcount, bad = build(ei, 3, 1, 0)
+    assert bad[0] == 1
+    assert rowptr[-1] == 2  # offending edge dropped
+    ei = np.array([[0, -1], [1, 0]])
+    assert build(ei, 3, 0, 0)[5][0] == 1
+
+
+def test_csr_build_botnet_graph_both_orders():
+    g = synth_botnet_graph(seed=1, num_nodes=20000, edge_entries=220000, evil=1500)
+    n = 20000
+    for by in (0, 1):
+        check_against_oracle(g["edge_index"], n, by, 0)
+    # grouped by source, the preprocessed file is already in row order apart from the appended
+    # loops: every row is its sorted prefix segment followed by its loop
+    rowptr, nbr, perm, *_ = build(g["edge_index"], n, 0, 0)
+    e = g["edge_index"].shape[1]
+    last = perm[rowptr[1:] - 1]
+    assert (last == e - n + np.arange(n)).all()
+
+
+def test_degree_and_norm_bitexact():
+    g = synth_botnet_graph(seed=2, num_nodes=5000, edge_entries=60000, evil=300)
+    n = 5000
+    ei = torch.from_numpy(g["edge_index"]).to(DEV)
+    rowptr = ops.csr_build_impl(ei, n, 0, 0, 256)[0]
+    deg = ops.degree_impl(rowptr)
+    assert_bitexact(deg, g["x"][:, 1], "out-degree")            # data_add_degree.py:60-63
+    for mode, p in ((0, -0.5), (1, -1.0)):
+        dis = ops.gcn_norm_impl(deg, mode)
+        ref = torch.from_numpy(g["x"][:, 1]).pow(p)             # gcn_base_models.py:128-131
+        ref[ref == float("inf")] = 0
+        assert_bitexact(dis, ref, f"dis mode {mode}")
+    # every degree value 0..100000 (0 -> inf -> 0)
+    d = torch.arange(0, 100001, dtype=torch.float32)
+    for mode, p in ((0, -0.5), (1, -1.0)):
+        ref = d.pow(p)
+        ref[ref == float("inf")] = 0
+        assert_bitexact(ops.gcn_norm_impl(d.to(DEV), mode), ref, f"all degrees mode {mode}")
+
+
+def test_weighted_degree_and_edge_value_permutation():
+    rng = np.random.default_rng(5)
+    n, e = 400, 5000
+    ei_np = rng.integers(0, n, size=(2, e))
+    ew = torch.rand(e) + 0.5
+    ei = torch.from_numpy(ei_np).to(DEV)
+    rowptr, nbr, perm, *_ = ops.csr_build_impl(ei, n, 0, 0, 256)
+    wd = ops.weighted_degree_impl(rowptr, nbr, perm, ew.to(DEV), 1.0)
+    ref = port.scatter_rows("add", ew, torch.from_numpy(ei_np[0]), n)   # gcn_base_models.py:126
+    assert_bitexact(wd, ref, "weighted degree")
+    pv = ops.permute_edge_values_impl(rowptr, nbr, perm, ew.to(DEV), 1.0)
+    assert_bitexact(pv, ew[perm.cpu().long()], "edge values in row order")
+    # with appended loops (GCNConv.norm: loop weight = fill value)
+    rowptr, nbr, perm, *_ = ops.csr_build_impl(ei, n, 0, 2, 256)
+    wd = ops.weighted_degree_impl(rowptr, nbr, perm, ew.to(DEV), 2.0)
+    keep = ei_np[0] != ei_np[1]
+    ei_l = np.concatenate([ei_np[:, keep], np.stack([np.arange(n)] * 2)], axis=1)
+    w_l = torch.cat([ew[torch.from_numpy(keep)], torch.full((n,), 2.0)])
+    assert_bitexact(wd, port.scatter_rows("add", w_l, torch.from_numpy(ei_l[0]), n), "weighted degree + loops")
+
+
+def test_batch_to_offsets():
+    sizes = [3, 0, 5, 1, 0, 0, 7]
+    batch = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)]).to(DEV)
+    off = ops.batch_to_offsets_impl(batch, len(sizes))
+    assert off.cpu().tolist() == np.concatenate([[0], np.cumsum(sizes)]).tolist()
