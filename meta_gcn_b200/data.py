@@ -22,8 +22,13 @@ class GraphBatch:
         self.x, self.edge_index, self.y = x, edge_index, y
         if batch is None:
             batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
+            if slices_x is None:
+                slices_x = [0, int(x.size(0))]
+        elif slices_x is None:  # boundaries from the (sorted) graph-id vector
+            counts = torch.bincount(batch.cpu()) if batch.numel() else torch.zeros(0, dtype=torch.long)
+            slices_x = [0] + torch.cumsum(counts, 0).tolist()
         self.batch = batch
-        self.slices_x = list(slices_x) if slices_x is not None else [0, int(x.size(0))]
+        self.slices_x = list(slices_x)
         self.slices_e = list(slices_e) if slices_e is not None else [0, int(edge_index.size(1))]
         self.__slices__ = {"x": self.slices_x, "edge_index": self.slices_e}
 
