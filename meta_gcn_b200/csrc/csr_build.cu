@@ -337,7 +337,8 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
     return MGCN_OK;
   }
   MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
-  MGCN_REQUIRE(rowptr && nbr && perm && hub_count && bad_index, MGCN_ERR_NULL);
+  MGCN_REQUIRE(rowptr && hub_count && bad_index, MGCN_ERR_NULL);
+  MGCN_REQUIRE(total == 0 || (nbr && perm), MGCN_ERR_NULL);
   MGCN_REQUIRE(E == 0 || edge_index != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(hub_cap == 0 || hub_rows != nullptr, MGCN_ERR_NULL);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
