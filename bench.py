@@ -263,13 +263,13 @@ def run_ours(args):
     dis = ops.gcn_norm_impl(batch.x[:, 1].contiguous(), 0)
     feat = torch.randn(n_nodes, HIDDEN, device=dev)
     for _ in range(3):
-        ops.spmm_impl(*gs.fwd_args(), feat, nbr_scale=dis, row_scale=dis, act=1)
+        ops.spmm_impl(gs.fwd, feat, nbr_scale=dis, row_scale=dis, act=1)
     torch.cuda.synchronize()
     reps = 20
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(reps):
-        ops.spmm_impl(*gs.fwd_args(), feat, nbr_scale=dis, row_scale=dis, act=1)
+        ops.spmm_impl(gs.fwd, feat, nbr_scale=dis, row_scale=dis, act=1)
     k1.record()
     torch.cuda.synchronize()
     agg_ms = k0.elapsed_time(k1) / reps

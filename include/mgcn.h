@@ -41,22 +41,33 @@ extern "C" {
 #define MGCN_ERR_ALIGN (-4)     /* pointer not aligned for 128-bit access             */
 #define MGCN_ERR_WORKSPACE (-5) /* workspace smaller than the queried size            */
 
-/* Degree above which a row is aggregated by a whole CTA (fixed-shape tree combine) instead of one
- * lane group (sequential, bit-identical to the reference's CPU edge-order sum). */
+/* Rows longer than this are "hubs": they are cut into segments of this many entries, each summed by
+ * one lane group like an ordinary row, and the partial sums are combined left to right.  Rows at or
+ * below it are summed by one lane group sequentially in edge_index order (bit-identical to the
+ * reference's CPU scatter_add). */
 #define MGCN_DEFAULT_HUB_THRESHOLD 256
 
-/* A row-owned adjacency (CSR when built by source, CSC when built by target).  All members are
- * device pointers written by mgcn_csr_build and owned by the caller. */
+/* A row-owned adjacency (CSR when built by source, CSC when built by target).  All pointer members
+ * are DEVICE buffers owned by the caller; mgcn_csr_build fills them.  Capacities come from
+ * mgcn_csr_capacities. */
 typedef struct mgcn_csr {
-  int64_t n_rows;          /* N                                                          */
-  int64_t nnz_cap;         /* allocated length of nbr/perm (E, or E+N when loops added)  */
-  const int32_t* rowptr;   /* [N+1]; rowptr[N] = number of kept edges                    */
-  const int32_t* nbr;      /* [nnz_cap] other endpoint of each kept edge, row-grouped    */
-  const int32_t* perm;     /* [nnz_cap] position in the input edge_index (E+i = loop i)  */
-  const int32_t* hub_rows; /* [hub_cap] rows with more than hub_threshold entries        */
-  const int32_t* hub_count;/* [1]                                                        */
-  int64_t hub_cap;
-  int32_t hub_threshold;
+  int64_t n_rows;           /* N                                                               */
+  int64_t nnz_cap;          /* length of nbr/perm: E, or E+N when loops are appended           */
+  int64_t hub_cap;          /* length of hub_rows/hub_seg0                                     */
+  int64_t seg_cap;          /* length of seg_row/seg_beg                                       */
+  int32_t hub_threshold;    /* hub limit = segment length                                      */
+  int32_t reserved;
+  const int32_t* rowptr;    /* [N+1]; rowptr[N] = number of kept edges                         */
+  const int32_t* nbr;       /* [nnz_cap] other endpoint of each kept edge, row-grouped         */
+  const int32_t* perm;      /* [nnz_cap] position in the input edge_index (E+i = loop of i)    */
+  const int32_t* order;     /* [N] rows sorted by (row / 16384, length): the work order that
+                               keeps the rows sharing a warp equally long; may be NULL         */
+  const int32_t* hub_rows;  /* [hub_cap] rows longer than hub_threshold                        */
+  const int32_t* hub_seg0;  /* [hub_cap] first segment of each hub row                         */
+  const int32_t* hub_count; /* [1]                                                             */
+  const int32_t* seg_row;   /* [seg_cap] row of each segment                                   */
+  const int32_t* seg_beg;   /* [seg_cap] first entry of each segment                           */
+  const int32_t* seg_count; /* [1]                                                             */
 } mgcn_csr_t;
 
 int mgcn_version(void);
@@ -77,14 +88,16 @@ void mgcn_reset_launch_count(void);
  *               (add_remaining_self_loops without weights) — nnz_cap must be E+N.
  * The order of edges inside a row is their order in edge_index (stable LSD radix sort), which is
  * the order the reference's CPU scatter_add sums them in.
- * Outputs: rowptr int32[N+1], nbr int32[nnz_cap], perm int32[nnz_cap] (unused tail = -1),
- *          hub_rows int32[hub_cap], hub_count int32[1], bad_index int32[1] (set to 1 if any
- *          endpoint is outside [0,N); such edges are dropped).
+ * out: every pointer member is a caller-allocated device buffer of the capacity given by
+ *      mgcn_csr_capacities; n_rows / capacities / hub_threshold are filled in by the caller.
+ * bad_index int32[1] is set to 1 if any endpoint is outside [0,N) (such edges are dropped).
+ * perm entries past rowptr[N] are -1.
  */
+int mgcn_csr_capacities(int64_t E, int64_t N, int loop_mode, int32_t hub_threshold,
+                        int64_t* nnz_cap, int64_t* hub_cap, int64_t* seg_cap);
 int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by, int loop_mode,
-                   int32_t hub_threshold, int32_t* rowptr, int32_t* nbr, int32_t* perm,
-                   int32_t* hub_rows, int64_t hub_cap, int32_t* hub_count, int32_t* bad_index,
-                   void* workspace, size_t* workspace_bytes, void* stream);
+                   const mgcn_csr_t* out, int32_t* bad_index, void* workspace,
+                   size_t* workspace_bytes, void* stream);
 
 /* deg[i] = float(rowptr[i+1]-rowptr[i]): the unweighted scatter_add(ones, row) of
  * gcn_base_models.py:126 and data_procs/data_add_degree.py:60-63. */
@@ -121,7 +134,18 @@ int mgcn_permute_edge_values(const mgcn_csr_t* g, const float* vals_in, int64_t 
  */
 int mgcn_spmm(const mgcn_csr_t* g, const float* x, int64_t n_in, int64_t H, int gather_perm,
               const float* edge_val, const float* nbr_scale, const float* row_scale, int reduce,
-              const float* bias, const float* residual, int act, float* out, void* stream);
+              const float* bias, const float* residual, int act, float* out, void* workspace,
+              size_t* workspace_bytes, void* stream);
+
+/* The same aggregation for inputs that already carry the per-source factor (x~ = nbr_scale * x,
+ * written by the producing transform): no per-edge weight at all,
+ *   out_i = act( post_scale[i] * sum_k x~[nbr[k], :] (/ len_i) + bias + residual_i ),
+ * rows visited in g->order.  Same summation order as mgcn_spmm; differs from it only in where the
+ * factors are rounded (x*(d_i d_j) vs (x d_j) summed, then * d_i).  H must be 16, 32, 64 or 128. */
+int mgcn_aggregate_prescaled(const mgcn_csr_t* g, const float* x, int64_t n_in, int64_t H,
+                             const float* post_scale, int reduce, const float* bias,
+                             const float* residual, int act, float* out, void* workspace,
+                             size_t* workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense transform on the FMA pipes (narrow widths) — torch.matmul(x, weight_node)

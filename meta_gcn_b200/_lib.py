@@ -22,13 +22,20 @@ class MgcnCsr(ctypes.Structure):
     _fields_ = [
         ("n_rows", c_i64),
         ("nnz_cap", c_i64),
+        ("hub_cap", c_i64),
+        ("seg_cap", c_i64),
+        ("hub_threshold", c_i32),
+        ("reserved", c_i32),
         ("rowptr", c_ptr),
         ("nbr", c_ptr),
         ("perm", c_ptr),
+        ("order", c_ptr),
         ("hub_rows", c_ptr),
+        ("hub_seg0", c_ptr),
         ("hub_count", c_ptr),
-        ("hub_cap", c_i64),
-        ("hub_threshold", c_i32),
+        ("seg_row", c_ptr),
+        ("seg_beg", c_ptr),
+        ("seg_count", c_ptr),
     ]
 
 
@@ -40,14 +47,17 @@ SIGNATURES = {
     "mgcn_error_string": (ctypes.c_char_p, [c_int]),
     "mgcn_launch_count": (c_i64, []),
     "mgcn_reset_launch_count": (None, []),
-    "mgcn_csr_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i32, c_ptr, c_ptr, c_ptr, c_ptr,
-                               c_i64, c_ptr, c_ptr, c_ptr, c_size_p, c_ptr]),
+    "mgcn_csr_capacities": (c_int, [c_i64, c_i64, c_int, c_i32, ctypes.POINTER(c_i64),
+                                    ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "mgcn_csr_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, CSR_P, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_degree_from_rowptr": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "mgcn_weighted_degree": (c_int, [CSR_P, c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
     "mgcn_gcn_norm": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "mgcn_permute_edge_values": (c_int, [CSR_P, c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
     "mgcn_spmm": (c_int, [CSR_P, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
-                          c_ptr, c_int, c_ptr, c_ptr]),
+                          c_ptr, c_int, c_ptr, c_ptr, c_size_p, c_ptr]),
+    "mgcn_aggregate_prescaled": (c_int, [CSR_P, c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_ptr,
+                                         c_int, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_linear": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int,
                             c_ptr, c_ptr]),
     "mgcn_linear_wgrad": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr,

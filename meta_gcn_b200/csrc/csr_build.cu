@@ -234,15 +234,50 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Hub rows (longer than `threshold`) are cut into segments of `threshold` entries.  The order in
+// which hubs claim table slots is arbitrary (atomic counters) but never reaches the results: each
+// hub's segments are contiguous and combined in segment order.
 __global__ void __launch_bounds__(256)
     k_find_hubs(const int32_t* __restrict__ rowptr, int64_t N, int32_t threshold,
-                int32_t* __restrict__ hub_rows, int64_t hub_cap, int32_t* __restrict__ hub_count) {
+                int32_t* __restrict__ hub_rows, int32_t* __restrict__ hub_seg0, int64_t hub_cap,
+                int32_t* __restrict__ hub_count, int32_t* __restrict__ seg_row,
+                int32_t* __restrict__ seg_beg, int64_t seg_cap, int32_t* __restrict__ seg_count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  if (rowptr[i + 1] - rowptr[i] > threshold) {
+  const int32_t beg = rowptr[i];
+  const int32_t len = rowptr[i + 1] - beg;
+  if (len > threshold) {
+    const int32_t nseg = (len + threshold - 1) / threshold;
     const int32_t k = atomicAdd(hub_count, 1);
-    if (k < hub_cap) hub_rows[k] = (int32_t)i;
+    const int32_t s0 = atomicAdd(seg_count, nseg);
+    if (k < hub_cap && (int64_t)s0 + nseg <= seg_cap) {
+      hub_rows[k] = (int32_t)i;
+      hub_seg0[k] = s0;
+      for (int32_t q = 0; q < nseg; ++q) {
+        seg_row[s0 + q] = (int32_t)i;
+        seg_beg[s0 + q] = beg + q * threshold;
+      }
+    }
   }
+}
+
+// work-order key: (locality window, row length clipped to 1023)
+constexpr int kOrderWindowShift = 14;  // 16384 rows: 2 MB of H=32 features stay L2/L1-local
+constexpr int kOrderLenBits = 10;
+
+__global__ void __launch_bounds__(256) k_order_keys(const int32_t* __restrict__ rowptr, int64_t N,
+                                                    uint32_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int32_t len = rowptr[i + 1] - rowptr[i];
+  if (len > (1 << kOrderLenBits) - 1) len = (1 << kOrderLenBits) - 1;
+  keys[i] = ((uint32_t)(i >> kOrderWindowShift) << kOrderLenBits) | (uint32_t)len;
+}
+
+__global__ void __launch_bounds__(256) k_copy_i32(const int32_t* __restrict__ in, int64_t n,
+                                                  int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
 }
 
 __global__ void __launch_bounds__(256) k_degree(const int32_t* __restrict__ rowptr, int64_t N,
@@ -300,21 +335,60 @@ static int grid_for(int64_t n, int block, int max_blocks = kNumSMs * 32) {
   return (int)g;
 }
 
-static int radix_passes(int64_t N) {
+static int radix_passes_for(uint64_t max_key) {
   int bits = 1;
-  while ((int64_t(1) << bits) <= N) ++bits;  // values 0..N inclusive
+  while ((uint64_t(1) << bits) <= max_key) ++bits;
   return (bits + 7) / 8;
+}
+
+// stable sort of (keys, position) by key; keys_a holds the input keys, initial values are the
+// positions 0..n-1.  *sorted_vals points at the buffer holding the sorted positions.
+static int radix_sort_positions(uint32_t* keys_a, uint32_t* keys_b, int32_t* vals_a, int32_t* vals_b,
+                                int64_t n, uint64_t max_key, int32_t* block_hist,
+                                int32_t* tile_sums, const int32_t** sorted_vals, void* stream) {
+  const int num_blocks = (int)ceil_div(n > 0 ? n : 1, kRsTile);
+  const int64_t hist_len = (int64_t)256 * num_blocks;
+  const int passes = radix_passes_for(max_key);
+  const uint32_t* kin = keys_a;
+  uint32_t* kout = keys_b;
+  const int32_t* vin = nullptr;  // identity on the first pass
+  int32_t* vout = vals_a;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    MGCN_LAUNCH(k_radix_hist, num_blocks, 256, 0, stream, kin, n, shift, block_hist, num_blocks);
+    int rc = exclusive_scan_i32(block_hist, block_hist, hist_len, tile_sums, stream);
+    if (rc != MGCN_OK) return rc;
+    MGCN_LAUNCH(k_radix_scatter, num_blocks, 256, 0, stream, kin, vin, kout, vout, n, shift,
+                block_hist, num_blocks);
+    uint32_t* old_in = const_cast<uint32_t*>(kin);
+    kin = kout;
+    kout = old_in;
+    vin = vout;
+    vout = (vout == vals_a) ? vals_b : vals_a;
+  }
+  *sorted_vals = vin;
+  return MGCN_OK;
 }
 
 }  // namespace mgcn
 
 using namespace mgcn;
 
+extern "C" int mgcn_csr_capacities(int64_t E, int64_t N, int loop_mode, int32_t hub_threshold,
+                                   int64_t* nnz_cap, int64_t* hub_cap, int64_t* seg_cap) {
+  MGCN_REQUIRE(nnz_cap && hub_cap && seg_cap, MGCN_ERR_NULL);
+  MGCN_REQUIRE(E >= 0 && N >= 0 && hub_threshold >= 1, MGCN_ERR_RANGE);
+  MGCN_REQUIRE(loop_mode >= 0 && loop_mode <= 2, MGCN_ERR_SHAPE);
+  const int64_t total = E + (loop_mode == 2 ? N : 0);
+  *nnz_cap = total;
+  *hub_cap = total / hub_threshold + 1;              // every hub owns > hub_threshold entries
+  *seg_cap = total / hub_threshold + *hub_cap + 1;   // sum ceil(len/T) <= nnz/T + hubs
+  return MGCN_OK;
+}
+
 extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by,
-                              int loop_mode, int32_t hub_threshold, int32_t* rowptr, int32_t* nbr,
-                              int32_t* perm, int32_t* hub_rows, int64_t hub_cap,
-                              int32_t* hub_count, int32_t* bad_index, void* workspace,
-                              size_t* workspace_bytes, void* stream) {
+                              int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
+                              void* workspace, size_t* workspace_bytes, void* stream) {
   MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(by == 0 || by == 1, MGCN_ERR_SHAPE);
   MGCN_REQUIRE(loop_mode >= 0 && loop_mode <= 2, MGCN_ERR_SHAPE);
@@ -323,13 +397,14 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
   const int64_t total = E + (loop_mode == 2 ? N : 0);
   MGCN_REQUIRE(total < kMax, MGCN_ERR_RANGE);
 
-  const int num_blocks = (int)ceil_div(total > 0 ? total : 1, kRsTile);
+  const int64_t items = total > N ? total : N;  // the sort buffers also serve the row-order sort
+  const int num_blocks = (int)ceil_div(items > 0 ? items : 1, kRsTile);
   const int64_t hist_len = (int64_t)256 * num_blocks;
   WorkspaceCarver ws(workspace);
-  uint32_t* keys_a = ws.take<uint32_t>(total);
-  uint32_t* keys_b = ws.take<uint32_t>(total);
-  int32_t* vals_a = ws.take<int32_t>(total);
-  int32_t* vals_b = ws.take<int32_t>(total);
+  uint32_t* keys_a = ws.take<uint32_t>(items);
+  uint32_t* keys_b = ws.take<uint32_t>(items);
+  int32_t* vals_a = ws.take<int32_t>(items);
+  int32_t* vals_b = ws.take<int32_t>(items);
   int32_t* block_hist = ws.take<int32_t>(hist_len);
   int32_t* tile_sums = ws.take<int32_t>(scan_tiles(hist_len > N + 1 ? hist_len : N + 1));
   if (workspace == nullptr) {
@@ -337,14 +412,28 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
     return MGCN_OK;
   }
   MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
-  MGCN_REQUIRE(rowptr && hub_count && bad_index, MGCN_ERR_NULL);
+  MGCN_REQUIRE(out != nullptr && bad_index != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(out->n_rows == N && out->nnz_cap >= total && out->hub_threshold >= 1, MGCN_ERR_SHAPE);
+  int32_t* rowptr = const_cast<int32_t*>(out->rowptr);
+  int32_t* nbr = const_cast<int32_t*>(out->nbr);
+  int32_t* perm = const_cast<int32_t*>(out->perm);
+  int32_t* order = const_cast<int32_t*>(out->order);
+  int32_t* hub_rows = const_cast<int32_t*>(out->hub_rows);
+  int32_t* hub_seg0 = const_cast<int32_t*>(out->hub_seg0);
+  int32_t* hub_count = const_cast<int32_t*>(out->hub_count);
+  int32_t* seg_row = const_cast<int32_t*>(out->seg_row);
+  int32_t* seg_beg = const_cast<int32_t*>(out->seg_beg);
+  int32_t* seg_count = const_cast<int32_t*>(out->seg_count);
+  MGCN_REQUIRE(rowptr && hub_count && seg_count, MGCN_ERR_NULL);
   MGCN_REQUIRE(total == 0 || (nbr && perm), MGCN_ERR_NULL);
   MGCN_REQUIRE(E == 0 || edge_index != nullptr, MGCN_ERR_NULL);
-  MGCN_REQUIRE(hub_cap == 0 || hub_rows != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(out->hub_cap == 0 || (hub_rows && hub_seg0), MGCN_ERR_NULL);
+  MGCN_REQUIRE(out->seg_cap == 0 || (seg_row && seg_beg), MGCN_ERR_NULL);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   MGCN_CHECK_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (N + 1), st));
   MGCN_CHECK_CUDA(cudaMemsetAsync(hub_count, 0, sizeof(int32_t), st));
+  MGCN_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, sizeof(int32_t), st));
   MGCN_CHECK_CUDA(cudaMemsetAsync(bad_index, 0, sizeof(int32_t), st));
   if (total > 0) {
     MGCN_LAUNCH(k_make_keys, grid_for(total, 256), 256, 0, stream, edge_index, E, N, by,
@@ -353,35 +442,28 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
   int rc = exclusive_scan_i32(rowptr, rowptr, N + 1, tile_sums, stream);
   if (rc != MGCN_OK) return rc;
 
-  const int32_t* sorted_vals = nullptr;
   if (total > 0) {
-    const int passes = radix_passes(N);
-    const uint32_t* kin = keys_a;
-    uint32_t* kout = keys_b;
-    const int32_t* vin = nullptr;  // identity on the first pass
-    int32_t* vout = vals_a;
-    for (int p = 0; p < passes; ++p) {
-      const int shift = 8 * p;
-      MGCN_LAUNCH(k_radix_hist, num_blocks, 256, 0, stream, kin, total, shift, block_hist,
-                  num_blocks);
-      rc = exclusive_scan_i32(block_hist, block_hist, hist_len, tile_sums, stream);
-      if (rc != MGCN_OK) return rc;
-      MGCN_LAUNCH(k_radix_scatter, num_blocks, 256, 0, stream, kin, vin, kout, vout, total, shift,
-                  block_hist, num_blocks);
-      // ping-pong
-      const uint32_t* nk = kout;
-      kout = const_cast<uint32_t*>(kin == keys_a ? keys_a : keys_b);
-      kin = nk;
-      vin = vout;
-      vout = (vout == vals_a) ? vals_b : vals_a;
-    }
-    sorted_vals = vin;
+    const int32_t* sorted_pos = nullptr;
+    rc = radix_sort_positions(keys_a, keys_b, vals_a, vals_b, total, (uint64_t)N, block_hist,
+                              tile_sums, &sorted_pos, stream);
+    if (rc != MGCN_OK) return rc;
     MGCN_LAUNCH(k_finalize, grid_for(total, 256), 256, 0, stream, edge_index, E, by, total,
-                sorted_vals, rowptr, N, nbr, perm);
+                sorted_pos, rowptr, N, nbr, perm);
   }
-  if (N > 0 && hub_cap > 0) {
-    MGCN_LAUNCH(k_find_hubs, (int)ceil_div(N, 256), 256, 0, stream, rowptr, N, hub_threshold,
-                hub_rows, hub_cap, hub_count);
+  if (N > 0 && out->hub_cap > 0 && out->seg_cap > 0) {
+    MGCN_LAUNCH(k_find_hubs, (int)ceil_div(N, 256), 256, 0, stream, rowptr, N, out->hub_threshold,
+                hub_rows, hub_seg0, out->hub_cap, hub_count, seg_row, seg_beg, out->seg_cap,
+                seg_count);
+  }
+  if (N > 0 && order != nullptr) {
+    MGCN_LAUNCH(k_order_keys, (int)ceil_div(N, 256), 256, 0, stream, rowptr, N, keys_a);
+    const uint64_t max_key =
+        ((uint64_t)((N - 1) >> kOrderWindowShift) << kOrderLenBits) | ((1u << kOrderLenBits) - 1);
+    const int32_t* sorted_rows = nullptr;
+    rc = radix_sort_positions(keys_a, keys_b, vals_a, vals_b, N, max_key, block_hist, tile_sums,
+                              &sorted_rows, stream);
+    if (rc != MGCN_OK) return rc;
+    MGCN_LAUNCH(k_copy_i32, (int)ceil_div(N, 256), 256, 0, stream, sorted_rows, N, order);
   }
   return MGCN_OK;
 }

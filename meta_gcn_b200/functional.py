@@ -16,7 +16,7 @@ _REDUCE = {"add": 0, "sum": 0, "mean": 1}
 class _Aggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd, reduce, act):
-        out = ops.spmm_impl(*graph.fwd_args(), x, False, ev_fwd, nbr_scale, row_scale, reduce, bias,
+        out = ops.spmm_impl(graph.fwd, x, False, ev_fwd, nbr_scale, row_scale, reduce, bias,
                             residual, act)
         ctx.graph = graph
         ctx.cfg = (reduce, act, bias is not None, residual is not None)
@@ -40,7 +40,7 @@ class _Aggregate(torch.autograd.Function):
                 gg = g / graph.in_degree().clamp(min=1).unsqueeze(1)
             # transpose: rows = sources; the per-target factor is now gathered, the per-source
             # factor scales the row
-            dx = ops.spmm_impl(*graph.bwd_args(), gg, False, ev_bwd, row_scale, nbr_scale, 0, None,
+            dx = ops.spmm_impl(graph.bwd, gg, False, ev_bwd, row_scale, nbr_scale, 0, None,
                                None, 0)
         return dx, d_bias, d_res, None, None, None, None, None, None, None
 
@@ -120,7 +120,7 @@ def pool_by_batch(x, batch, size=None, reduce="mean"):
 class _ScatterRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, graph, index, reduce):
-        out = ops.spmm_impl(*graph.fwd_args(), src, True, None, None, None, reduce, None, None, 0)
+        out = ops.spmm_impl(graph.fwd, src, True, None, None, None, reduce, None, None, 0)
         ctx.graph = graph
         ctx.reduce = reduce
         ctx.save_for_backward(index)

@@ -5,21 +5,17 @@ The reference walks COO ``edge_index`` with index_select / scatter_add in every 
 structures — grouped by target (forward aggregation) and grouped by source (backward, the
 transpose) — by ``mgcn_csr_build``; all layers of the model then share them.
 """
-from collections import OrderedDict, namedtuple
+from collections import OrderedDict
 
 import torch
 
 from . import ops
 
-Csr = namedtuple("Csr", "rowptr nbr perm hub_rows hub_count bad hub_threshold")
+Csr = ops.Csr
 
 LOOPS_KEEP = 0      # edge_index used as given (gcn_meta: loops are already in the data, loop.py:13-17)
 LOOPS_REMOVE = 1    # PyG remove_self_loops (GINConv)
 LOOPS_ADD_REMAINING = 2  # PyG add_remaining_self_loops (GCNConv.norm, SAGEConv)
-
-
-def _csr_args(c):
-    return (c.rowptr, c.nbr, c.perm, c.hub_rows, c.hub_count, c.hub_threshold)
 
 
 class GraphStructure:
@@ -39,9 +35,8 @@ class GraphStructure:
         self._deg = {}
 
     def _build(self, by):
-        out = ops.csr_build_impl(self.edge_index, self.num_nodes, by, self.loop_mode,
-                                 self.hub_threshold)
-        return Csr(*out, self.hub_threshold)
+        return ops.csr_build_impl(self.edge_index, self.num_nodes, by, self.loop_mode,
+                                  self.hub_threshold)
 
     @property
     def fwd(self):
@@ -57,12 +52,6 @@ class GraphStructure:
             self._bwd = self._build(0)
         return self._bwd
 
-    def fwd_args(self):
-        return _csr_args(self.fwd)
-
-    def bwd_args(self):
-        return _csr_args(self.bwd)
-
     def out_degree(self):
         """float degree over edge_index[0] (after loop handling): gcn_base_models.py:126"""
         if "out" not in self._deg:
@@ -75,14 +64,12 @@ class GraphStructure:
         return self._deg["in"]
 
     def weighted_out_degree(self, edge_weight, loop_weight=1.0):
-        b = self.bwd
-        return ops.weighted_degree_impl(b.rowptr, b.nbr, b.perm, edge_weight, loop_weight)
+        return ops.weighted_degree_impl(self.bwd, edge_weight, loop_weight)
 
     def edge_values(self, edge_weight, loop_value=1.0):
         """edge weights (input edge order) -> (forward row order, backward row order)"""
-        f, b = self.fwd, self.bwd
-        return (ops.permute_edge_values_impl(f.rowptr, f.nbr, f.perm, edge_weight, loop_value),
-                ops.permute_edge_values_impl(b.rowptr, b.nbr, b.perm, edge_weight, loop_value))
+        return (ops.permute_edge_values_impl(self.fwd, edge_weight, loop_value),
+                ops.permute_edge_values_impl(self.bwd, edge_weight, loop_value))
 
     def check_indices(self):
         """host-synchronising validation (debug entry point): raises on out-of-range endpoints"""

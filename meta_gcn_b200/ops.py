@@ -40,29 +40,54 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-def _csr_struct(rowptr, nbr, perm, hub_rows, hub_count, hub_threshold):
-    s = MgcnCsr()
-    s.n_rows = rowptr.numel() - 1
-    s.nnz_cap = nbr.numel()
-    s.rowptr = rowptr.data_ptr()
-    s.nbr = nbr.data_ptr() if nbr.numel() else None
-    s.perm = perm.data_ptr() if perm is not None and perm.numel() else None
-    if hub_rows is not None and hub_rows.numel() > 0:
-        s.hub_rows = hub_rows.data_ptr()
-        s.hub_count = hub_count.data_ptr()
-        s.hub_cap = hub_rows.numel()
-    else:
-        s.hub_rows = None
-        s.hub_count = None
-        s.hub_cap = 0
-    s.hub_threshold = int(hub_threshold)
-    return s
+CSR_FIELDS = ("rowptr", "nbr", "perm", "order", "hub_rows", "hub_seg0", "hub_count", "seg_row",
+              "seg_beg", "seg_count")
+
+
+class Csr:
+    """Device buffers of one mgcn_csr_t (include/mgcn.h) plus the ctypes view handed to the library."""
+
+    __slots__ = CSR_FIELDS + ("bad", "hub_threshold", "_struct")
+
+    def __init__(self, tensors, hub_threshold, bad=None):
+        for name, t in zip(CSR_FIELDS, tensors):
+            setattr(self, name, t)
+        self.bad = bad
+        self.hub_threshold = int(hub_threshold)
+        self._struct = None
+
+    def tensors(self):
+        return [getattr(self, n) for n in CSR_FIELDS]
+
+    @property
+    def n_rows(self):
+        return self.rowptr.numel() - 1
+
+    def struct(self):
+        if self._struct is None:
+            s = MgcnCsr()
+            s.n_rows = self.rowptr.numel() - 1
+            s.nnz_cap = self.nbr.numel()
+            s.hub_cap = self.hub_rows.numel()
+            s.seg_cap = self.seg_row.numel()
+            s.hub_threshold = self.hub_threshold
+            for name in CSR_FIELDS:
+                t = getattr(self, name)
+                setattr(s, name, t.data_ptr() if t is not None and t.numel() else None)
+            self._struct = s
+        return self._struct
+
+
+def _as_csr(csr, hub_threshold=None):
+    if isinstance(csr, Csr):
+        return csr
+    return Csr(list(csr), hub_threshold)
 
 
 # ------------------------------------------------------------------------------------------------
 # implementations (plain functions; also what meta_gcn_b200.functional calls directly)
 # ------------------------------------------------------------------------------------------------
-def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold):
+def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRESHOLD):
     _need_cuda(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise TypeError("edge_index must be int64 [2,E]")
@@ -70,22 +95,24 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold):
     E = ei.size(1)
     N = int(N)
     dev = ei.device
-    nnz_cap = E + (N if loop_mode == 2 else 0)
-    hub_cap = nnz_cap // max(int(hub_threshold), 1) + 1
-    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
-    nbr = torch.empty(nnz_cap, dtype=torch.int32, device=dev)
-    perm = torch.empty(nnz_cap, dtype=torch.int32, device=dev)
-    hub_rows = torch.empty(hub_cap, dtype=torch.int32, device=dev)
-    hub_count = torch.empty(1, dtype=torch.int32, device=dev)
-    bad = torch.empty(1, dtype=torch.int32, device=dev)
     lib = _lib.load()
+    caps = [ctypes.c_int64(0) for _ in range(3)]
+    _lib.check(lib.mgcn_csr_capacities(E, N, int(loop_mode), int(hub_threshold),
+                                       *[ctypes.byref(c) for c in caps]))
+    nnz_cap, hub_cap, seg_cap = (c.value for c in caps)
+    i32 = dict(dtype=torch.int32, device=dev)
+    sizes = dict(rowptr=N + 1, nbr=nnz_cap, perm=nnz_cap, order=N, hub_rows=hub_cap, hub_seg0=hub_cap,
+                 hub_count=1, seg_row=seg_cap, seg_beg=seg_cap, seg_count=1)
+    csr = Csr([torch.empty(sizes[n], **i32) for n in CSR_FIELDS], hub_threshold,
+              torch.empty(1, **i32))
     nbytes = ctypes.c_size_t(0)
-    args = (_ptr(ei), E, N, int(by), int(loop_mode), int(hub_threshold), _ptr(rowptr), _ptr(nbr),
-            _ptr(perm), _ptr(hub_rows), hub_cap, _ptr(hub_count), _ptr(bad))
-    _lib.check(lib.mgcn_csr_build(*args, None, ctypes.byref(nbytes), None))
+    st = csr.struct()
+    _lib.check(lib.mgcn_csr_build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
+                                  _ptr(csr.bad), None, ctypes.byref(nbytes), None))
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-    _lib.check(lib.mgcn_csr_build(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
-    return rowptr, nbr, perm, hub_rows, hub_count, bad
+    _lib.check(lib.mgcn_csr_build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
+                                  _ptr(csr.bad), _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return csr
 
 
 def degree_impl(rowptr):
@@ -96,12 +123,11 @@ def degree_impl(rowptr):
     return deg
 
 
-def weighted_degree_impl(rowptr, nbr, perm, edge_weight, loop_weight):
-    _need_cuda(rowptr, edge_weight)
+def weighted_degree_impl(csr, edge_weight, loop_weight):
+    _need_cuda(csr.rowptr, edge_weight)
     ew = _f32c(edge_weight, "edge_weight")
-    s = _csr_struct(rowptr, nbr, perm, None, None, 0)
-    deg = torch.empty(rowptr.numel() - 1, dtype=torch.float32, device=rowptr.device)
-    _lib.check(_lib.load().mgcn_weighted_degree(ctypes.byref(s), _ptr(ew), ew.numel(),
+    deg = torch.empty(csr.n_rows, dtype=torch.float32, device=csr.rowptr.device)
+    _lib.check(_lib.load().mgcn_weighted_degree(ctypes.byref(csr.struct()), _ptr(ew), ew.numel(),
                                                 float(loop_weight), _ptr(deg), _stream()))
     return deg
 
@@ -114,20 +140,26 @@ def gcn_norm_impl(deg, mode):
     return dis
 
 
-def permute_edge_values_impl(rowptr, nbr, perm, vals, loop_value):
-    _need_cuda(rowptr, vals)
+def permute_edge_values_impl(csr, vals, loop_value):
+    _need_cuda(csr.rowptr, vals)
     v = _f32c(vals, "vals")
-    s = _csr_struct(rowptr, nbr, perm, None, None, 0)
-    out = torch.empty(nbr.numel(), dtype=torch.float32, device=rowptr.device)
-    _lib.check(_lib.load().mgcn_permute_edge_values(ctypes.byref(s), _ptr(v), v.numel(),
+    out = torch.empty(csr.nbr.numel(), dtype=torch.float32, device=csr.rowptr.device)
+    _lib.check(_lib.load().mgcn_permute_edge_values(ctypes.byref(csr.struct()), _ptr(v), v.numel(),
                                                     float(loop_value), _ptr(out), _stream()))
     return out
 
 
-def spmm_impl(rowptr, nbr, perm, hub_rows, hub_count, hub_threshold, x, gather_perm=False,
-              edge_val=None, nbr_scale=None, row_scale=None, reduce=0, bias=None, residual=None,
-              act=0):
-    _need_cuda(rowptr, x, edge_val, nbr_scale, row_scale, bias, residual)
+def _workspace(fn, dev):
+    """two-phase workspace protocol: fn(ws_ptr, byref(nbytes)) -> rc"""
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(fn(None, ctypes.byref(nbytes), None))
+    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
+    return ws, nbytes
+
+
+def spmm_impl(csr, x, gather_perm=False, edge_val=None, nbr_scale=None, row_scale=None, reduce=0,
+              bias=None, residual=None, act=0):
+    _need_cuda(csr.rowptr, x, edge_val, nbr_scale, row_scale, bias, residual)
     if x.dim() != 2:
         raise ValueError("x must be [n_in, H]")
     x = _f32c(x, "x")
@@ -136,9 +168,9 @@ def spmm_impl(rowptr, nbr, perm, hub_rows, hub_count, hub_threshold, x, gather_p
     row_scale = _f32c(row_scale, "row_scale")
     bias = _f32c(bias, "bias")
     residual = _f32c(residual, "residual")
-    n_rows = rowptr.numel() - 1
+    n_rows = csr.n_rows
     H = x.size(1)
-    if edge_val is not None and edge_val.numel() != nbr.numel():
+    if edge_val is not None and edge_val.numel() != csr.nbr.numel():
         raise ValueError("edge_val must be in row order with nnz_cap entries")
     if row_scale is not None and row_scale.numel() != n_rows:
         raise ValueError("row_scale must have one entry per row")
@@ -147,10 +179,30 @@ def spmm_impl(rowptr, nbr, perm, hub_rows, hub_count, hub_threshold, x, gather_p
     if bias is not None and bias.numel() != H:
         raise ValueError("bias must have H entries")
     out = torch.empty(n_rows, H, dtype=torch.float32, device=x.device)
-    s = _csr_struct(rowptr, nbr, perm, hub_rows, hub_count, hub_threshold)
-    _lib.check(_lib.load().mgcn_spmm(ctypes.byref(s), _ptr(x), x.size(0), H, int(bool(gather_perm)),
-                                     _ptr(edge_val), _ptr(nbr_scale), _ptr(row_scale), int(reduce),
-                                     _ptr(bias), _ptr(residual), int(act), _ptr(out), _stream()))
+    lib = _lib.load()
+    st = ctypes.byref(csr.struct())
+    args = (st, _ptr(x), x.size(0), H, int(bool(gather_perm)), _ptr(edge_val), _ptr(nbr_scale),
+            _ptr(row_scale), int(reduce), _ptr(bias), _ptr(residual), int(act), _ptr(out))
+    ws, nbytes = _workspace(lambda w, nb, stm: lib.mgcn_spmm(*args, w, nb, stm), x.device)
+    _lib.check(lib.mgcn_spmm(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return out
+
+
+def aggregate_prescaled_impl(csr, x, post_scale=None, reduce=0, bias=None, residual=None, act=0):
+    """out_i = act(post_scale[i] * sum_k x[nbr_k] (/len) + bias + residual_i) for x that already
+    carries the per-source factor; H in {16, 32, 64, 128}."""
+    _need_cuda(csr.rowptr, x, post_scale, bias, residual)
+    x = _f32c(x, "x")
+    post_scale = _f32c(post_scale, "post_scale")
+    bias = _f32c(bias, "bias")
+    residual = _f32c(residual, "residual")
+    n_rows, H = csr.n_rows, x.size(1)
+    out = torch.empty(n_rows, H, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    args = (ctypes.byref(csr.struct()), _ptr(x), x.size(0), H, _ptr(post_scale), int(reduce),
+            _ptr(bias), _ptr(residual), int(act), _ptr(out))
+    ws, nbytes = _workspace(lambda w, nb, stm: lib.mgcn_aggregate_prescaled(*args, w, nb, stm), x.device)
+    _lib.check(lib.mgcn_aggregate_prescaled(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
     return out
 
 
@@ -242,17 +294,17 @@ def segment_broadcast_impl(gout, offsets, N, mode):
 # torch.library registration
 # ------------------------------------------------------------------------------------------------
 _LIBDEF = torch.library.Library("mgcn", "DEF")
-_LIBDEF.define("csr_build(Tensor edge_index, int N, int by, int loop_mode, int hub_threshold) -> "
-               "(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)")
+# `csr` is the list of the ten int32 tensors of a row structure, in CSR_FIELDS order
+_LIBDEF.define("csr_build(Tensor edge_index, int N, int by, int loop_mode, int hub_threshold) -> Tensor[]")
 _LIBDEF.define("degree(Tensor rowptr) -> Tensor")
-_LIBDEF.define("weighted_degree(Tensor rowptr, Tensor nbr, Tensor perm, Tensor edge_weight, "
-               "float loop_weight) -> Tensor")
+_LIBDEF.define("weighted_degree(Tensor[] csr, Tensor edge_weight, float loop_weight) -> Tensor")
 _LIBDEF.define("gcn_norm(Tensor deg, int mode) -> Tensor")
-_LIBDEF.define("permute_edge_values(Tensor rowptr, Tensor nbr, Tensor perm, Tensor vals, "
-               "float loop_value) -> Tensor")
-_LIBDEF.define("spmm(Tensor rowptr, Tensor nbr, Tensor perm, Tensor hub_rows, Tensor hub_count, "
-               "int hub_threshold, Tensor x, bool gather_perm, Tensor? edge_val, Tensor? nbr_scale, "
-               "Tensor? row_scale, int reduce, Tensor? bias, Tensor? residual, int act) -> Tensor")
+_LIBDEF.define("permute_edge_values(Tensor[] csr, Tensor vals, float loop_value) -> Tensor")
+_LIBDEF.define("spmm(Tensor[] csr, int hub_threshold, Tensor x, bool gather_perm, Tensor? edge_val, "
+               "Tensor? nbr_scale, Tensor? row_scale, int reduce, Tensor? bias, Tensor? residual, "
+               "int act) -> Tensor")
+_LIBDEF.define("aggregate_prescaled(Tensor[] csr, int hub_threshold, Tensor x, Tensor? post_scale, "
+               "int reduce, Tensor? bias, Tensor? residual, int act) -> Tensor")
 _LIBDEF.define("linear(Tensor x, Tensor w, bool w_out_in, Tensor? bias, Tensor? add, int act) -> Tensor")
 _LIBDEF.define("linear_wgrad(Tensor x, Tensor g, bool w_out_in, bool want_bias) -> (Tensor, Tensor)")
 _LIBDEF.define("relu_backward(Tensor g, Tensor y) -> Tensor")
@@ -260,13 +312,38 @@ _LIBDEF.define("batch_to_offsets(Tensor batch, int G) -> Tensor")
 _LIBDEF.define("segment_reduce(Tensor x, Tensor offsets, int mode) -> Tensor")
 _LIBDEF.define("segment_broadcast(Tensor gout, Tensor offsets, int N, int mode) -> Tensor")
 
+
+def _op_csr_build(edge_index, N, by, loop_mode, hub_threshold):
+    return csr_build_impl(edge_index, N, by, loop_mode, hub_threshold).tensors()
+
+
+def _op_weighted_degree(csr, edge_weight, loop_weight):
+    return weighted_degree_impl(_as_csr(csr, DEFAULT_HUB_THRESHOLD), edge_weight, loop_weight)
+
+
+def _op_permute_edge_values(csr, vals, loop_value):
+    return permute_edge_values_impl(_as_csr(csr, DEFAULT_HUB_THRESHOLD), vals, loop_value)
+
+
+def _op_spmm(csr, hub_threshold, x, gather_perm, edge_val, nbr_scale, row_scale, reduce, bias,
+             residual, act):
+    return spmm_impl(_as_csr(csr, hub_threshold), x, gather_perm, edge_val, nbr_scale, row_scale,
+                     reduce, bias, residual, act)
+
+
+def _op_aggregate_prescaled(csr, hub_threshold, x, post_scale, reduce, bias, residual, act):
+    return aggregate_prescaled_impl(_as_csr(csr, hub_threshold), x, post_scale, reduce, bias,
+                                    residual, act)
+
+
 _IMPLS = {
-    "csr_build": csr_build_impl,
+    "csr_build": _op_csr_build,
     "degree": degree_impl,
-    "weighted_degree": weighted_degree_impl,
+    "weighted_degree": _op_weighted_degree,
     "gcn_norm": gcn_norm_impl,
-    "permute_edge_values": permute_edge_values_impl,
-    "spmm": spmm_impl,
+    "permute_edge_values": _op_permute_edge_values,
+    "spmm": _op_spmm,
+    "aggregate_prescaled": _op_aggregate_prescaled,
     "linear": linear_impl,
     "linear_wgrad": linear_wgrad_impl,
     "relu_backward": relu_backward_impl,
@@ -293,10 +370,11 @@ for _name in _IMPLS:
 def _(edge_index, N, by, loop_mode, hub_threshold):
     E = edge_index.size(1)
     cap = E + (N if loop_mode == 2 else 0)
+    hub_cap = cap // max(hub_threshold, 1) + 1
+    seg_cap = cap // max(hub_threshold, 1) + hub_cap + 1
     i32 = dict(dtype=torch.int32, device=edge_index.device)
-    return (torch.empty(N + 1, **i32), torch.empty(cap, **i32), torch.empty(cap, **i32),
-            torch.empty(cap // max(hub_threshold, 1) + 1, **i32), torch.empty(1, **i32),
-            torch.empty(1, **i32))
+    sizes = (N + 1, cap, cap, N, hub_cap, hub_cap, 1, seg_cap, seg_cap, 1)
+    return [torch.empty(n, **i32) for n in sizes]
 
 
 @torch.library.register_fake("mgcn::degree")
@@ -305,8 +383,8 @@ def _(rowptr):
 
 
 @torch.library.register_fake("mgcn::weighted_degree")
-def _(rowptr, nbr, perm, edge_weight, loop_weight):
-    return torch.empty(rowptr.numel() - 1, dtype=torch.float32, device=rowptr.device)
+def _(csr, edge_weight, loop_weight):
+    return torch.empty(csr[0].numel() - 1, dtype=torch.float32, device=csr[0].device)
 
 
 @torch.library.register_fake("mgcn::gcn_norm")
@@ -315,14 +393,18 @@ def _(deg, mode):
 
 
 @torch.library.register_fake("mgcn::permute_edge_values")
-def _(rowptr, nbr, perm, vals, loop_value):
-    return torch.empty(nbr.numel(), dtype=torch.float32, device=rowptr.device)
+def _(csr, vals, loop_value):
+    return torch.empty(csr[1].numel(), dtype=torch.float32, device=csr[0].device)
 
 
 @torch.library.register_fake("mgcn::spmm")
-def _(rowptr, nbr, perm, hub_rows, hub_count, hub_threshold, x, gather_perm, edge_val, nbr_scale,
-      row_scale, reduce, bias, residual, act):
-    return torch.empty(rowptr.numel() - 1, x.size(1), dtype=torch.float32, device=x.device)
+def _(csr, hub_threshold, x, gather_perm, edge_val, nbr_scale, row_scale, reduce, bias, residual, act):
+    return torch.empty(csr[0].numel() - 1, x.size(1), dtype=torch.float32, device=x.device)
+
+
+@torch.library.register_fake("mgcn::aggregate_prescaled")
+def _(csr, hub_threshold, x, post_scale, reduce, bias, residual, act):
+    return torch.empty(csr[0].numel() - 1, x.size(1), dtype=torch.float32, device=x.device)
 
 
 @torch.library.register_fake("mgcn::linear")

@@ -43,19 +43,22 @@ def test_version_and_error_strings():
 def test_argument_errors_without_device():
     lib = _lib.load()
     n = ctypes.c_size_t(0)
+    caps = [ctypes.c_int64(0) for _ in range(3)]
+    assert lib.mgcn_csr_capacities(1000, 100, 2, 256, *[ctypes.byref(c) for c in caps]) == 0
+    assert caps[0].value == 1100 and caps[1].value == 1100 // 256 + 1
     # workspace query never launches
-    rc = lib.mgcn_csr_build(None, 1000, 100, 1, 0, 256, None, None, None, None, 0, None, None, None,
-                            ctypes.byref(n), None)
+    rc = lib.mgcn_csr_build(None, 1000, 100, 1, 0, None, None, None, ctypes.byref(n), None)
     assert rc == 0 and n.value > 4 * 1000 * 4
-    assert lib.mgcn_csr_build(None, 10, 10, 7, 0, 256, None, None, None, None, 0, None, None, None,
-                              ctypes.byref(n), None) == -3          # bad `by`
-    assert lib.mgcn_csr_build(None, 1 << 31, 10, 0, 0, 256, None, None, None, None, 0, None, None,
-                              None, ctypes.byref(n), None) == -2    # E out of int32 range
-    assert lib.mgcn_spmm(None, None, 0, 32, 0, None, None, None, 0, None, None, 0, None, None) == -1
+    assert lib.mgcn_csr_build(None, 10, 10, 7, 0, None, None, None, ctypes.byref(n), None) == -3
+    assert lib.mgcn_csr_build(None, 1 << 31, 10, 0, 0, None, None, None, ctypes.byref(n), None) == -2
+    assert lib.mgcn_spmm(None, None, 0, 32, 0, None, None, None, 0, None, None, 0, None, None,
+                         ctypes.byref(n), None) == -1
     s = _lib.MgcnCsr()
     s.n_rows = 4
     assert lib.mgcn_spmm(ctypes.byref(s), None, 4, 0, 0, None, None, None, 0, None, None, 0, None,
-                         None) == -3                                # H = 0
+                         None, ctypes.byref(n), None) == -3         # H = 0
+    assert lib.mgcn_aggregate_prescaled(ctypes.byref(s), None, 4, 48, None, 0, None, None, 0, None,
+                                        None, ctypes.byref(n), None) == -3   # H not in {16,32,64,128}
     assert lib.mgcn_linear(None, 5, 0, None, 1, 1, 4, None, None, 0, None, None) == -3
     assert lib.mgcn_linear(None, 5, 4, None, 1, 1, 4, None, None, 0, None, None) == -1
     assert lib.mgcn_gcn_norm(None, 5, 3, None, None) == -3

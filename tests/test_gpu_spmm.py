@@ -36,9 +36,9 @@ def test_plain_sum_is_bitexact_below_hub_threshold(H):
     ei = rand_graph(H, n, e)
     x = torch.randn(n, H)
     g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=1 << 30)
-    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV))
+    out = ops.spmm_impl(g.fwd, x.to(DEV))
     assert_bitexact(out, oracle_aggregate(ei, n, x), f"sum H={H}")
-    outm = ops.spmm_impl(*g.fwd_args(), x.to(DEV), reduce=1)
+    outm = ops.spmm_impl(g.fwd, x.to(DEV), reduce=1)
     assert_bitexact(outm, oracle_aggregate(ei, n, x, reduce="mean"), f"mean H={H}")
 
 
@@ -52,7 +52,7 @@ def test_sym_norm_weights_follow_reference_rounding(H):
     norm = port.degnorm_const(torch.from_numpy(ei), n, deg=deg, method="sm")
     g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=1 << 30)
     dis = ops.gcn_norm_impl(deg.to(DEV), 0)
-    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV), nbr_scale=dis, row_scale=dis)
+    out = ops.spmm_impl(g.fwd, x.to(DEV), nbr_scale=dis, row_scale=dis)
     assert_bitexact(out, oracle_aggregate(ei, n, x, norm), f"sm H={H}")
     # with edge weights: dis[row] * w * dis[col]
     ew = torch.rand(e) + 0.5
@@ -60,11 +60,11 @@ def test_sym_norm_weights_follow_reference_rounding(H):
     degw = g.weighted_out_degree(ew.to(DEV))
     disw = ops.gcn_norm_impl(degw, 0)
     ev_f, _ = g.edge_values(ew.to(DEV))
-    outw = ops.spmm_impl(*g.fwd_args(), x.to(DEV), edge_val=ev_f, nbr_scale=disw, row_scale=disw)
+    outw = ops.spmm_impl(g.fwd, x.to(DEV), edge_val=ev_f, nbr_scale=disw, row_scale=disw)
     assert_bitexact(outw, oracle_aggregate(ei, n, x, normw), f"sm+w H={H}")
     # rw: x * deg^-1 gathered (gcn_base_models.py:217-220)
     dis_rw = ops.gcn_norm_impl(deg.to(DEV), 1)
-    out_rw = ops.spmm_impl(*g.fwd_args(), x.to(DEV), nbr_scale=dis_rw)
+    out_rw = ops.spmm_impl(g.fwd, x.to(DEV), nbr_scale=dis_rw)
     ref_rw = port.scatter_rows("add", (x * deg.pow(-1).nan_to_num(posinf=0).view(-1, 1))[torch.from_numpy(ei[0])],
                                torch.from_numpy(ei[1]), n)
     assert_bitexact(out_rw, ref_rw, f"rw H={H}")
@@ -78,16 +78,16 @@ def test_hub_rows_tree_sum_within_tolerance_and_deterministic(H, hub_t):
     x = torch.randn(n, H)
     g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=hub_t)
     assert int(g.fwd.hub_count.item()) >= 1
-    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV))
+    out = ops.spmm_impl(g.fwd, x.to(DEV))
     ref = oracle_aggregate(ei, n, x)
     assert_parity(out, ref, f"hub sum H={H}")
     # non-hub rows stay bit-exact
     deg_in = np.bincount(ei[1], minlength=n)
     small = torch.from_numpy(deg_in <= hub_t)
     assert_bitexact(out.cpu()[small], ref[small], "non-hub rows")
-    again = ops.spmm_impl(*g.fwd_args(), x.to(DEV))
+    again = ops.spmm_impl(g.fwd, x.to(DEV))
     assert_bitexact(again, out, "run-to-run determinism")
-    outm = ops.spmm_impl(*g.fwd_args(), x.to(DEV), reduce=1)
+    outm = ops.spmm_impl(g.fwd, x.to(DEV), reduce=1)
     assert_parity(outm, oracle_aggregate(ei, n, x, reduce="mean"), f"hub mean H={H}")
 
 
@@ -97,7 +97,7 @@ def test_fused_epilogue(H):
     ei = rand_graph(11, n, e)
     x, res, bias = torch.randn(n, H), torch.randn(n, H), torch.randn(H)
     g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=1 << 30)
-    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV), bias=bias.to(DEV), residual=res.to(DEV), act=1)
+    out = ops.spmm_impl(g.fwd, x.to(DEV), bias=bias.to(DEV), residual=res.to(DEV), act=1)
     ref = torch.relu(oracle_aggregate(ei, n, x) + bias + res)
     assert_bitexact(out, ref, "relu(sum + bias + residual)")
 
@@ -107,11 +107,11 @@ def test_rows_without_edges_and_empty_inputs():
     ei = np.array([[1, 2, 3], [4, 4, 9]])
     x = torch.randn(n, 32)
     g = GraphStructure(torch.from_numpy(ei).to(DEV), n)
-    out = ops.spmm_impl(*g.fwd_args(), x.to(DEV), reduce=1, bias=torch.ones(32, device=DEV))
+    out = ops.spmm_impl(g.fwd, x.to(DEV), reduce=1, bias=torch.ones(32, device=DEV))
     ref = oracle_aggregate(ei, n, x, reduce="mean") + 1
     assert_bitexact(out, ref, "isolated rows")
     g0 = GraphStructure(torch.zeros(2, 0, dtype=torch.long, device=DEV), n)
-    out0 = ops.spmm_impl(*g0.fwd_args(), x.to(DEV))
+    out0 = ops.spmm_impl(g0.fwd, x.to(DEV))
     assert (out0 == 0).all()
 
 
@@ -175,3 +175,44 @@ def test_backward_is_deterministic():
         grads.append(x.grad.clone())
     assert_bitexact(grads[1], grads[0], "dx run 2")
     assert_bitexact(grads[2], grads[0], "dx run 3")
+
+
+@pytest.mark.parametrize("H", [16, 32, 64, 128])
+@pytest.mark.parametrize("reduce", [0, 1])
+def test_prescaled_aggregation(H, reduce):
+    """inputs carrying the per-source factor: out = post * sum x~[nbr]  — same summation order as
+    the exact kernel, different placement of the two roundings of the degree factors"""
+    n, e = 3000, 40000
+    ei = rand_graph(50 + H, n, e, hub=2500)
+    deg = torch.bincount(torch.from_numpy(ei[0]), minlength=n).float().clamp(min=1)
+    dis = deg.pow(-0.5)
+    x = torch.randn(n, H)
+    bias, res = torch.randn(H), torch.randn(n, H)
+    g = GraphStructure(torch.from_numpy(ei).to(DEV), n, hub_threshold=64)
+    xs = (x * dis.view(-1, 1)).to(DEV)
+    out = ops.aggregate_prescaled_impl(g.fwd, xs, dis.to(DEV), reduce, bias.to(DEV), res.to(DEV), 1)
+    norm = dis[torch.from_numpy(ei[0])] * dis[torch.from_numpy(ei[1])]
+    ref = torch.relu(oracle_aggregate(ei, n, x, norm, "mean" if reduce else "add") + bias + res)
+    assert_parity(out, ref, f"prescaled H={H}")
+    # unweighted, non-hub rows: exactly the reference's edge-order sum
+    plain = ops.aggregate_prescaled_impl(g.fwd, x.to(DEV), None, reduce, None, None, 0)
+    refp = oracle_aggregate(ei, n, x, None, "mean" if reduce else "add")
+    small = torch.from_numpy(np.bincount(ei[1], minlength=n) <= 64)
+    assert_bitexact(plain.cpu()[small], refp[small], "plain non-hub rows")
+    assert_parity(plain, refp, "plain all rows")
+    assert_bitexact(ops.aggregate_prescaled_impl(g.fwd, xs, dis.to(DEV), reduce, bias.to(DEV), res.to(DEV), 1),
+                    out, "deterministic")
+
+
+def test_torch_library_ops_roundtrip():
+    """the registered torch.ops.mgcn.* surface (list-of-tensors structure) matches the direct calls"""
+    n, e = 500, 6000
+    ei = torch.from_numpy(rand_graph(1, n, e)).to(DEV)
+    csr = torch.ops.mgcn.csr_build(ei, n, 1, 0, 256)
+    assert len(csr) == len(ops.CSR_FIELDS)
+    x = torch.randn(n, 32, device=DEV)
+    a = torch.ops.mgcn.spmm(csr, 256, x, False, None, None, None, 0, None, None, 0)
+    b = ops.spmm_impl(GraphStructure(ei, n).fwd, x)
+    assert_bitexact(a, b, "torch.ops.mgcn.spmm")
+    c = torch.ops.mgcn.aggregate_prescaled(csr, 256, x, None, 0, None, None, 0)
+    assert_bitexact(c, b, "torch.ops.mgcn.aggregate_prescaled")

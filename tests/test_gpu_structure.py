@@ -13,26 +13,50 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+class _Built:
+    pass
+
+
 def build(ei_np, n, by, mode, hub_t=256):
     ei = torch.from_numpy(np.ascontiguousarray(ei_np)).long().to(DEV)
-    out = ops.csr_build_impl(ei, n, by, mode, hub_t)
+    csr = ops.csr_build_impl(ei, n, by, mode, hub_t)
     torch.cuda.synchronize()
-    return [t.cpu().numpy() for t in out]
+    b = _Built()
+    for name in ops.CSR_FIELDS:
+        setattr(b, name, getattr(csr, name).cpu().numpy())
+    b.bad = csr.bad.cpu().numpy()
+    return b
 
 
 def check_against_oracle(ei_np, n, by, mode, hub_t=256):
-    rowptr, nbr, perm, hubs, hcount, bad = build(ei_np, n, by, mode, hub_t)
+    b = build(ei_np, n, by, mode, hub_t)
     o_rowptr, o_nbr, o_perm = port.csr_oracle(ei_np, n, by, mode)
-    assert bad[0] == 0
-    assert_bitexact(rowptr, o_rowptr, "rowptr")
+    assert b.bad[0] == 0
+    assert_bitexact(b.rowptr, o_rowptr, "rowptr")
     nnz = int(o_rowptr[-1])
-    assert_bitexact(nbr[:nnz], o_nbr, "nbr")
-    assert_bitexact(perm[:nnz], o_perm, "perm")
-    assert (perm[nnz:] == -1).all()
+    assert_bitexact(b.nbr[:nnz], o_nbr, "nbr")
+    assert_bitexact(b.perm[:nnz], o_perm, "perm")
+    assert (b.perm[nnz:] == -1).all()
     deg = np.diff(o_rowptr)
+    # hubs and their segments: every hub once, segments contiguous, covering the row in order
     want_hubs = np.nonzero(deg > hub_t)[0]
-    assert hcount[0] == len(want_hubs)
-    assert sorted(hubs[:hcount[0]].tolist()) == want_hubs.tolist()
+    nh = int(b.hub_count[0])
+    assert nh == len(want_hubs)
+    assert sorted(b.hub_rows[:nh].tolist()) == want_hubs.tolist()
+    total_segs = 0
+    for k in range(nh):
+        row, s0 = int(b.hub_rows[k]), int(b.hub_seg0[k])
+        nseg = -(-int(deg[row]) // hub_t)
+        total_segs += nseg
+        assert (b.seg_row[s0:s0 + nseg] == row).all()
+        assert b.seg_beg[s0:s0 + nseg].tolist() == [int(o_rowptr[row]) + q * hub_t for q in range(nseg)]
+    assert int(b.seg_count[0]) == total_segs
+    # work order: a permutation of the rows, sorted by (row // 16384, min(len, 1023)), stable
+    assert sorted(b.order.tolist()) == list(range(n))
+    key = (b.order.astype(np.int64) >> 14) * 1024 + np.minimum(deg[b.order], 1023)
+    assert (np.diff(key) >= 0).all()
+    same = np.diff(key) == 0
+    assert (np.diff(b.order)[same] > 0).all()
 
 
 @pytest.mark.parametrize("n,e", [(1, 1), (5, 0), (7, 3), (100, 4095), (100, 4096), (100, 4097), (300, 8193),
@@ -46,10 +70,11 @@ def test_csr_build_random(n, e, by, mode):
 
 
 def test_csr_build_empty_graph():
-    rowptr, nbr, perm, hubs, hcount, bad = build(np.zeros((2, 0), np.int64), 0, 1, 0)
-    assert rowptr.tolist() == [0] and hcount[0] == 0
-    rowptr, nbr, perm, hubs, hcount, bad = build(np.zeros((2, 0), np.int64), 4, 1, 2)
-    assert rowptr.tolist() == [0, 1, 2, 3, 4] and nbr.tolist() == [0, 1, 2, 3]
+    b = build(np.zeros((2, 0), np.int64), 0, 1, 0)
+    assert b.rowptr.tolist() == [0] and b.hub_count[0] == 0
+    b = build(np.zeros((2, 0), np.int64), 4, 1, 2)
+    assert b.rowptr.tolist() == [0, 1, 2, 3, 4] and b.nbr.tolist() == [0, 1, 2, 3]
+    assert b.order.tolist() == [0, 1, 2, 3]
 
 
 def test_csr_build_hubs_and_duplicates():
@@ -65,11 +90,11 @@ def test_csr_build_hubs_and_duplicates():
 
 def test_csr_build_flags_out_of_range_indices():
     ei = np.array([[0, 1, 9], [1, 0, 2]])
-    rowptr, nbr, perm, hubs, hcount, bad = build(ei, 3, 1, 0)
-    assert bad[0] == 1
-    assert rowptr[-1] == 2  # offending edge dropped
+    b = build(ei, 3, 1, 0)
+    assert b.bad[0] == 1
+    assert b.rowptr[-1] == 2  # offending edge dropped
     ei = np.array([[0, -1], [1, 0]])
-    assert build(ei, 3, 0, 0)[5][0] == 1
+    assert build(ei, 3, 0, 0).bad[0] == 1
 
 
 def test_csr_build_botnet_graph_both_orders():
@@ -79,9 +104,9 @@ def test_csr_build_botnet_graph_both_orders():
         check_against_oracle(g["edge_index"], n, by, 0)
     # grouped by source, the preprocessed file is already in row order apart from the appended
     # loops: every row is its sorted prefix segment followed by its loop
-    rowptr, nbr, perm, *_ = build(g["edge_index"], n, 0, 0)
+    b = build(g["edge_index"], n, 0, 0)
     e = g["edge_index"].shape[1]
-    last = perm[rowptr[1:] - 1]
+    last = b.perm[b.rowptr[1:] - 1]
     assert (last == e - n + np.arange(n)).all()
 
 
@@ -89,7 +114,7 @@ def test_degree_and_norm_bitexact():
     g = synth_botnet_graph(seed=2, num_nodes=5000, edge_entries=60000, evil=300)
     n = 5000
     ei = torch.from_numpy(g["edge_index"]).to(DEV)
-    rowptr = ops.csr_build_impl(ei, n, 0, 0, 256)[0]
+    rowptr = ops.csr_build_impl(ei, n, 0, 0, 256).rowptr
     deg = ops.degree_impl(rowptr)
     assert_bitexact(deg, g["x"][:, 1], "out-degree")            # data_add_degree.py:60-63
     for mode, p in ((0, -0.5), (1, -1.0)):
@@ -111,15 +136,15 @@ def test_weighted_degree_and_edge_value_permutation():
     ei_np = rng.integers(0, n, size=(2, e))
     ew = torch.rand(e) + 0.5
     ei = torch.from_numpy(ei_np).to(DEV)
-    rowptr, nbr, perm, *_ = ops.csr_build_impl(ei, n, 0, 0, 256)
-    wd = ops.weighted_degree_impl(rowptr, nbr, perm, ew.to(DEV), 1.0)
+    csr = ops.csr_build_impl(ei, n, 0, 0, 256)
+    wd = ops.weighted_degree_impl(csr, ew.to(DEV), 1.0)
     ref = port.scatter_rows("add", ew, torch.from_numpy(ei_np[0]), n)   # gcn_base_models.py:126
     assert_bitexact(wd, ref, "weighted degree")
-    pv = ops.permute_edge_values_impl(rowptr, nbr, perm, ew.to(DEV), 1.0)
-    assert_bitexact(pv, ew[perm.cpu().long()], "edge values in row order")
+    pv = ops.permute_edge_values_impl(csr, ew.to(DEV), 1.0)
+    assert_bitexact(pv, ew[csr.perm.cpu().long()], "edge values in row order")
     # with appended loops (GCNConv.norm: loop weight = fill value)
-    rowptr, nbr, perm, *_ = ops.csr_build_impl(ei, n, 0, 2, 256)
-    wd = ops.weighted_degree_impl(rowptr, nbr, perm, ew.to(DEV), 2.0)
+    csr = ops.csr_build_impl(ei, n, 0, 2, 256)
+    wd = ops.weighted_degree_impl(csr, ew.to(DEV), 2.0)
     keep = ei_np[0] != ei_np[1]
     ei_l = np.concatenate([ei_np[:, keep], np.stack([np.arange(n)] * 2)], axis=1)
     w_l = torch.cat([ew[torch.from_numpy(keep)], torch.full((n,), 2.0)])

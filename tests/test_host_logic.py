@@ -114,11 +114,10 @@ def test_ops_trace_with_fake_tensors():
     from torch._subclasses.fake_tensor import FakeTensorMode
     with FakeTensorMode():
         ei = torch.empty(2, 100, dtype=torch.int64, device="cuda")
-        rowptr, nbr, perm, hubs, hcount, bad = torch.ops.mgcn.csr_build(ei, 10, 1, 2, 256)
-        assert rowptr.shape == (11,) and nbr.shape == (110,) and perm.dtype == torch.int32
+        csr = torch.ops.mgcn.csr_build(ei, 10, 1, 2, 256)
+        assert csr[0].shape == (11,) and csr[1].shape == (110,) and csr[2].dtype == torch.int32
         x = torch.empty(10, 32, device="cuda")
-        y = torch.ops.mgcn.spmm(rowptr, nbr, perm, hubs, hcount, 256, x, False, None, None, None, 0,
-                                None, None, 1)
+        y = torch.ops.mgcn.spmm(csr, 256, x, False, None, None, None, 0, None, None, 1)
         assert y.shape == (10, 32) and y.device.type == "cuda"
         w = torch.empty(32, 16, device="cuda")
         z = torch.ops.mgcn.linear(y, w, False, None, None, 0)
