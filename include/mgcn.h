@@ -68,6 +68,11 @@ typedef struct mgcn_csr {
   const int32_t* seg_row;   /* [seg_cap] row of each segment                                   */
   const int32_t* seg_beg;   /* [seg_cap] first entry of each segment                           */
   const int32_t* seg_count; /* [1]                                                             */
+  const int32_t* tasks;     /* [(N + seg_cap) * 4] work descriptors {row, beg, end, partial_slot}:
+                               entries [0,N) are the rows in `order` (row = -1 for a hub row, which
+                               is covered by its segments), entries [N, N+seg_count) are the hub
+                               segments (partial_slot = segment index + 1); 16-byte aligned; may be
+                               NULL (then mgcn_aggregate_prescaled is unavailable)              */
 } mgcn_csr_t;
 
 int mgcn_version(void);

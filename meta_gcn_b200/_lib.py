@@ -36,6 +36,7 @@ class MgcnCsr(ctypes.Structure):
         ("seg_row", c_ptr),
         ("seg_beg", c_ptr),
         ("seg_count", c_ptr),
+        ("tasks", c_ptr),
     ]
 
 

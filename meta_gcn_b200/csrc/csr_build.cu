@@ -274,6 +274,35 @@ __global__ void __launch_bounds__(256) k_order_keys(const int32_t* __restrict__ 
   keys[i] = ((uint32_t)(i >> kOrderWindowShift) << kOrderLenBits) | (uint32_t)len;
 }
 
+// work descriptors {row, beg, end, partial_slot} in work order (see mgcn_csr_t::tasks)
+__global__ void __launch_bounds__(256)
+    k_make_row_tasks(const int32_t* __restrict__ order, const int32_t* __restrict__ rowptr, int64_t N,
+                     int32_t threshold, int4* __restrict__ tasks) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  const int32_t row = order[s];
+  const int32_t beg = rowptr[row], end = rowptr[row + 1];
+  tasks[s] = (end - beg > threshold) ? make_int4(-1, 0, 0, 0) : make_int4(row, beg, end, 0);
+}
+
+__global__ void __launch_bounds__(256)
+    k_make_seg_tasks(const int32_t* __restrict__ seg_row, const int32_t* __restrict__ seg_beg,
+                     const int32_t* __restrict__ seg_count, int64_t seg_cap,
+                     const int32_t* __restrict__ rowptr, int32_t threshold,
+                     int4* __restrict__ tasks) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= seg_cap) return;
+  int64_t ns = *seg_count;
+  if (ns > seg_cap) ns = seg_cap;
+  if (s < ns) {
+    const int32_t row = seg_row[s], beg = seg_beg[s];
+    const int32_t row_end = rowptr[row + 1];
+    tasks[s] = make_int4(row, beg, min(beg + threshold, row_end), (int32_t)s + 1);
+  } else {
+    tasks[s] = make_int4(-1, 0, 0, 0);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_copy_i32(const int32_t* __restrict__ in, int64_t n,
                                                   int32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,7 +453,9 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
   int32_t* seg_row = const_cast<int32_t*>(out->seg_row);
   int32_t* seg_beg = const_cast<int32_t*>(out->seg_beg);
   int32_t* seg_count = const_cast<int32_t*>(out->seg_count);
+  int4* tasks = reinterpret_cast<int4*>(const_cast<int32_t*>(out->tasks));
   MGCN_REQUIRE(rowptr && hub_count && seg_count, MGCN_ERR_NULL);
+  MGCN_REQUIRE(tasks == nullptr || (aligned16(tasks) && order != nullptr), MGCN_ERR_ALIGN);
   MGCN_REQUIRE(total == 0 || (nbr && perm), MGCN_ERR_NULL);
   MGCN_REQUIRE(E == 0 || edge_index != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(out->hub_cap == 0 || (hub_rows && hub_seg0), MGCN_ERR_NULL);
@@ -464,6 +495,14 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
                               &sorted_rows, stream);
     if (rc != MGCN_OK) return rc;
     MGCN_LAUNCH(k_copy_i32, (int)ceil_div(N, 256), 256, 0, stream, sorted_rows, N, order);
+    if (tasks != nullptr) {
+      MGCN_LAUNCH(k_make_row_tasks, (int)ceil_div(N, 256), 256, 0, stream, order, rowptr, N,
+                  out->hub_cap > 0 && out->seg_cap > 0 ? out->hub_threshold : 0x7fffffff, tasks);
+      if (out->hub_cap > 0 && out->seg_cap > 0) {
+        MGCN_LAUNCH(k_make_seg_tasks, (int)ceil_div(out->seg_cap, 256), 256, 0, stream, seg_row,
+                    seg_beg, seg_count, out->seg_cap, rowptr, out->hub_threshold, tasks + N);
+      }
+    }
   }
   return MGCN_OK;
 }

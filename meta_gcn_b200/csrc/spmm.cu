@@ -379,27 +379,3 @@ extern "C" int mgcn_spmm(const mgcn_csr_t* g, const float* x, int64_t n_in, int6
   if (!edge_val && !nbr_scale && !row_scale) return dispatch_spmm<kPlain>(a, vec4, stream);
   return dispatch_spmm<kExact>(a, vec4, stream);
 }
-
-extern "C" int mgcn_aggregate_prescaled(const mgcn_csr_t* g, const float* x, int64_t n_in,
-                                        int64_t H, const float* post_scale, int reduce,
-                                        const float* bias, const float* residual, int act,
-                                        float* out, void* workspace, size_t* workspace_bytes,
-                                        void* stream) {
-  MGCN_REQUIRE(reduce == 0 || reduce == 1, MGCN_ERR_SHAPE);
-  MGCN_REQUIRE(act == 0 || act == 1, MGCN_ERR_SHAPE);
-  MGCN_REQUIRE(n_in >= 0, MGCN_ERR_RANGE);
-  MGCN_REQUIRE(H == 16 || H == 32 || H == 64 || H == 128, MGCN_ERR_SHAPE);
-  SpmmArgs a{};
-  bool done = false;
-  int rc = fill_args(g, x, H, 0, out, workspace, workspace_bytes, &a, &done);
-  if (rc != MGCN_OK || done) return rc;
-  MGCN_REQUIRE(aligned16(x) && aligned16(out) && aligned16(a.partial) &&
-                   (!bias || aligned16(bias)) && (!residual || aligned16(residual)),
-               MGCN_ERR_ALIGN);
-  a.row_scale = post_scale;
-  a.bias = bias;
-  a.residual = residual;
-  a.reduce = reduce;
-  a.act = act;
-  return dispatch_spmm<kPlain>(a, true, stream);
-}

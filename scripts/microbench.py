@@ -47,6 +47,7 @@ dis = ops.gcn_norm_impl(b.x[:, 1].contiguous(), 0)
 x = torch.randn(n, H, device=dev)
 w = torch.randn(H, H, device=dev)
 bytes_agg = b_agg(n, e, H)
+print(f"hub threshold {args.hub}")
 for name, fn in [
     ("spmm exact (sm weights)", lambda: ops.spmm_impl(gs.fwd, x, nbr_scale=dis, row_scale=dis, act=1)),
     ("spmm plain (no weights)", lambda: ops.spmm_impl(gs.fwd, x)),

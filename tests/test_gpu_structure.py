@@ -57,6 +57,19 @@ def check_against_oracle(ei_np, n, by, mode, hub_t=256):
     assert (np.diff(key) >= 0).all()
     same = np.diff(key) == 0
     assert (np.diff(b.order)[same] > 0).all()
+    # work descriptors {row, beg, end, partial_slot}
+    t = b.tasks.reshape(-1, 4)
+    rows = b.order
+    is_hub = deg[rows] > hub_t
+    assert (t[:n, 0][is_hub] == -1).all()
+    ok = ~is_hub
+    assert (t[:n, 0][ok] == rows[ok]).all()
+    assert (t[:n, 1][ok] == o_rowptr[rows[ok]]).all() and (t[:n, 2][ok] == o_rowptr[rows[ok] + 1]).all()
+    assert (t[:n, 3] == 0).all()
+    ts = t[n:n + total_segs]
+    assert (ts[:, 0] == b.seg_row[:total_segs]).all() and (ts[:, 1] == b.seg_beg[:total_segs]).all()
+    assert (ts[:, 2] == np.minimum(ts[:, 1] + hub_t, o_rowptr[ts[:, 0] + 1])).all()
+    assert (ts[:, 3] == np.arange(total_segs) + 1).all()
 
 
 @pytest.mark.parametrize("n,e", [(1, 1), (5, 0), (7, 3), (100, 4095), (100, 4096), (100, 4097), (300, 8193),
