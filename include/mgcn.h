@@ -45,7 +45,7 @@ extern "C" {
  * one lane group like an ordinary row, and the partial sums are combined left to right.  Rows at or
  * below it are summed by one lane group sequentially in edge_index order (bit-identical to the
  * reference's CPU scatter_add). */
-#define MGCN_DEFAULT_HUB_THRESHOLD 256
+#define MGCN_DEFAULT_HUB_THRESHOLD 64
 
 /* A row-owned adjacency (CSR when built by source, CSC when built by target).  All pointer members
  * are DEVICE buffers owned by the caller; mgcn_csr_build fills them.  Capacities come from
@@ -162,11 +162,30 @@ int mgcn_aggregate_prescaled(const mgcn_csr_t* g, const float* x, int64_t n_in, 
 int mgcn_linear(const float* x, int64_t N, int64_t Hi, const float* w, int64_t w_sk, int64_t w_sc,
                 int64_t Ho, const float* bias, const float* add, int act, float* y, void* stream);
 
+/* mgcn_linear with two fused extras used by the whole-model path:
+ *   xmask [N,Hi] (may be NULL): the operand is x * (xmask > 0)  — relu backward folded into the load
+ *   row_scale [N] (may be NULL): y[n,:] = row_scale[n] * act(...) — messages leave pre-scaled by
+ *   the per-source degree factor, so the aggregation needs no per-edge weight. */
+int mgcn_linear_ex(const float* x, const float* xmask, int64_t N, int64_t Hi, const float* w,
+                   int64_t w_sk, int64_t w_sc, int64_t Ho, const float* bias, const float* add,
+                   int act, const float* row_scale, float* y, void* stream);
+
 /* dW(k,c) = sum_n x[n,k] * g[n,c]  (written at dw[k*dw_sk + c*dw_sc]),  db[c] = sum_n g[n,c].
  * Two-stage fixed-order reduction: deterministic, no atomics.  db may be NULL. */
 int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, int64_t Ho, float* dw,
                       int64_t dw_sk, int64_t dw_sc, float* db, void* workspace,
                       size_t* workspace_bytes, void* stream);
+
+/* mgcn_linear_wgrad with the gradient operand masked: g * (gmask > 0)  (gmask [N,Ho], may be NULL) */
+int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const float* g, const float* gmask,
+                         int64_t Ho, float* dw, int64_t dw_sk, int64_t dw_sc, float* db,
+                         void* workspace, size_t* workspace_bytes, void* stream);
+
+/* out[n,c] = row_scale[n] * g[n,c] * (m1[n,c] > 0) * (m2[n,c] > 0); masks and scale may be NULL.
+ * H must be a multiple of 4.  (gradient entering the transposed aggregation: both ReLU masks of
+ * a GCNModel layer and the per-node degree factor in one pass) */
+int mgcn_masked_scale(const float* g, const float* m1, const float* m2, const float* row_scale,
+                      int64_t N, int64_t H, float* out, void* stream);
 
 /* g_in[n,c] = relu'(y[n,c]) * g[n,c]  (y = saved activation output; mask is y > 0). */
 int mgcn_relu_backward(const float* g, const float* y, int64_t count, float* g_in, void* stream);

@@ -455,7 +455,7 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
   int32_t* seg_count = const_cast<int32_t*>(out->seg_count);
   int4* tasks = reinterpret_cast<int4*>(const_cast<int32_t*>(out->tasks));
   MGCN_REQUIRE(rowptr && hub_count && seg_count, MGCN_ERR_NULL);
-  MGCN_REQUIRE(tasks == nullptr || (aligned16(tasks) && order != nullptr), MGCN_ERR_ALIGN);
+  MGCN_REQUIRE(tasks == nullptr || N == 0 || (aligned16(tasks) && order != nullptr), MGCN_ERR_ALIGN);
   MGCN_REQUIRE(total == 0 || (nbr && perm), MGCN_ERR_NULL);
   MGCN_REQUIRE(E == 0 || edge_index != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(out->hub_cap == 0 || (hub_rows && hub_seg0), MGCN_ERR_NULL);

@@ -14,10 +14,10 @@ constexpr int kBK = 32;   // K slab
 constexpr int kXsLd = kBK + 4;
 
 __global__ void __launch_bounds__(128)
-    k_linear(const float* __restrict__ x, int64_t N, int Hi, const float* __restrict__ w,
-             int64_t w_sk, int64_t w_sc, int Ho, const float* __restrict__ bias,
-             const float* __restrict__ add, int act, float* __restrict__ y, int x_vec4,
-             int y_vec4) {
+    k_linear(const float* __restrict__ x, const float* __restrict__ xmask, int64_t N, int Hi,
+             const float* __restrict__ w, int64_t w_sk, int64_t w_sc, int Ho,
+             const float* __restrict__ bias, const float* __restrict__ add, int act,
+             const float* __restrict__ row_scale, float* __restrict__ y, int x_vec4, int y_vec4) {
   __shared__ __align__(16) float Xs[kBM][kXsLd];
   __shared__ __align__(16) float Ws[kBK][kBN];
   const int tid = threadIdx.x;
@@ -41,7 +41,14 @@ __global__ void __launch_bounds__(128)
         const int64_t gr = row0 + r;
         const int kk = k0 + 4 * cg;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < N && kk < Hi) v = __ldg(reinterpret_cast<const float4*>(x + gr * Hi + kk));
+        if (gr < N && kk < Hi) {
+          v = __ldg(reinterpret_cast<const float4*>(x + gr * Hi + kk));
+          if (xmask) {  // relu backward folded into the operand load: x * (mask > 0)
+            const float4 m = __ldg(reinterpret_cast<const float4*>(xmask + gr * Hi + kk));
+            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+            v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+          }
+        }
         *reinterpret_cast<float4*>(&Xs[r][4 * cg]) = v;
       }
     } else {
@@ -49,7 +56,12 @@ __global__ void __launch_bounds__(128)
         const int r = idx / kBK, c = idx % kBK;
         const int64_t gr = row0 + r;
         const int kk = k0 + c;
-        Xs[r][c] = (gr < N && kk < Hi) ? __ldg(x + gr * Hi + kk) : 0.f;
+        float v = 0.f;
+        if (gr < N && kk < Hi) {
+          v = __ldg(x + gr * Hi + kk);
+          if (xmask && !(__ldg(xmask + gr * Hi + kk) > 0.f)) v = 0.f;
+        }
+        Xs[r][c] = v;
       }
     }
     // ---- stage W[k0:k0+32, col0:col0+32] ----
@@ -95,6 +107,7 @@ __global__ void __launch_bounds__(128)
   for (int i = 0; i < 8; ++i) {
     const int64_t gr = row0 + rg + 16 * i;
     if (gr >= N) continue;
+    const float rs = row_scale ? __ldg(row_scale + gr) : 1.f;
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = acc[i][j] + bv[j];
@@ -107,6 +120,10 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = o[j] < 0.f ? 0.f : o[j];
       }
+      if (row_scale) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] *= rs;
+      }
       *reinterpret_cast<float4*>(y + gr * Ho + cc) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
 #pragma unroll
@@ -115,6 +132,7 @@ __global__ void __launch_bounds__(128)
           float v = o[j];
           if (add) v += __ldg(add + gr * Ho + cc + j);
           if (act == 1) v = v < 0.f ? 0.f : v;
+          if (row_scale) v *= rs;
           y[gr * Ho + cc + j] = v;
         }
       }
@@ -132,8 +150,9 @@ constexpr int kWgLd = 36;
 
 __global__ void __launch_bounds__(256)
     k_wgrad_partial(const float* __restrict__ x, int64_t N, int Hi, const float* __restrict__ g,
-                    int Ho, int64_t rows_per_slab, float* __restrict__ partial,
-                    float* __restrict__ partial_b, int x_vec4, int g_vec4) {
+                    const float* __restrict__ gmask, int Ho, int64_t rows_per_slab,
+                    float* __restrict__ partial, float* __restrict__ partial_b, int x_vec4,
+                    int g_vec4) {
   __shared__ __align__(16) float Xs[kWgRows][kWgLd];
   __shared__ __align__(16) float Gs[kWgRows][kWgLd];
   __shared__ float red[4][32][33];
@@ -181,7 +200,14 @@ __global__ void __launch_bounds__(256)
         const int64_t gr = s0 + r;
         const int cc = ct0 + 4 * q;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gr < n1 && cc < Ho) v = __ldg(reinterpret_cast<const float4*>(g + gr * Ho + cc));
+        if (gr < n1 && cc < Ho) {
+          v = __ldg(reinterpret_cast<const float4*>(g + gr * Ho + cc));
+          if (gmask) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(gmask + gr * Ho + cc));
+            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+            v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+          }
+        }
         *reinterpret_cast<float4*>(&Gs[r][4 * q]) = v;
       }
     } else {
@@ -189,7 +215,12 @@ __global__ void __launch_bounds__(256)
         const int r = idx >> 5, c = idx & 31;
         const int64_t gr = s0 + r;
         const int cc = ct0 + c;
-        Gs[r][c] = (gr < n1 && cc < Ho) ? __ldg(g + gr * Ho + cc) : 0.f;
+        float v = 0.f;
+        if (gr < n1 && cc < Ho) {
+          v = __ldg(g + gr * Ho + cc);
+          if (gmask && !(__ldg(gmask + gr * Ho + cc) > 0.f)) v = 0.f;
+        }
+        Gs[r][c] = v;
       }
     }
     __syncthreads();
@@ -271,6 +302,32 @@ __global__ void __launch_bounds__(256) k_relu_backward(const float* __restrict__
     gin[i] = y[i] > 0.f ? g[i] : 0.f;
 }
 
+// out[n,c] = rs[n] * g[n,c] * (m1[n,c] > 0) * (m2[n,c] > 0)   (either mask / the scale may be absent)
+__global__ void __launch_bounds__(256)
+    k_masked_scale(const float4* __restrict__ g, const float4* __restrict__ m1,
+                   const float4* __restrict__ m2, const float* __restrict__ rs, int64_t count4,
+                   int h4, float4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride) {
+    float4 v = __ldg(g + i);
+    if (m1) {
+      const float4 m = __ldg(m1 + i);
+      v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+      v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    }
+    if (m2) {
+      const float4 m = __ldg(m2 + i);
+      v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+      v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    }
+    if (rs) {
+      const float s = __ldg(rs + i / h4);
+      v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    }
+    out[i] = v;
+  }
+}
+
 static int wgrad_slabs(int64_t N) {
   // enough slabs to fill the machine for a 32x32 tile, each at least one 64-row stage
   int64_t p = kNumSMs * 4;
@@ -283,25 +340,33 @@ static int wgrad_slabs(int64_t N) {
 
 using namespace mgcn;
 
-extern "C" int mgcn_linear(const float* x, int64_t N, int64_t Hi, const float* w, int64_t w_sk,
-                           int64_t w_sc, int64_t Ho, const float* bias, const float* add, int act,
-                           float* y, void* stream) {
+extern "C" int mgcn_linear_ex(const float* x, const float* xmask, int64_t N, int64_t Hi,
+                              const float* w, int64_t w_sk, int64_t w_sc, int64_t Ho,
+                              const float* bias, const float* add, int act, const float* row_scale,
+                              float* y, void* stream) {
   MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
   MGCN_REQUIRE(Hi >= 1 && Ho >= 1 && Hi <= 65536 && Ho <= 65536, MGCN_ERR_SHAPE);
   MGCN_REQUIRE(act == 0 || act == 1, MGCN_ERR_SHAPE);
   if (N == 0) return MGCN_OK;
   MGCN_REQUIRE(x && w && y, MGCN_ERR_NULL);
-  const int x_vec4 = (Hi % 4 == 0) && aligned16(x);
+  const int x_vec4 = (Hi % 4 == 0) && aligned16(x) && (!xmask || aligned16(xmask));
   const int y_vec4 = (Ho % 4 == 0) && aligned16(y) && (!add || aligned16(add));
   dim3 grid((unsigned)ceil_div(N, kBM), (unsigned)ceil_div(Ho, kBN));
-  MGCN_LAUNCH(k_linear, grid, 128, 0, stream, x, N, (int)Hi, w, w_sk, w_sc, (int)Ho, bias, add,
-              act, y, x_vec4, y_vec4);
+  MGCN_LAUNCH(k_linear, grid, 128, 0, stream, x, xmask, N, (int)Hi, w, w_sk, w_sc, (int)Ho, bias,
+              add, act, row_scale, y, x_vec4, y_vec4);
   return MGCN_OK;
 }
 
-extern "C" int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, int64_t Ho,
-                                 float* dw, int64_t dw_sk, int64_t dw_sc, float* db,
-                                 void* workspace, size_t* workspace_bytes, void* stream) {
+extern "C" int mgcn_linear(const float* x, int64_t N, int64_t Hi, const float* w, int64_t w_sk,
+                           int64_t w_sc, int64_t Ho, const float* bias, const float* add, int act,
+                           float* y, void* stream) {
+  return mgcn_linear_ex(x, nullptr, N, Hi, w, w_sk, w_sc, Ho, bias, add, act, nullptr, y, stream);
+}
+
+extern "C" int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const float* g,
+                                    const float* gmask, int64_t Ho, float* dw, int64_t dw_sk,
+                                    int64_t dw_sc, float* db, void* workspace,
+                                    size_t* workspace_bytes, void* stream) {
   MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
   MGCN_REQUIRE(Hi >= 1 && Ho >= 1 && Hi <= 65536 && Ho <= 65536, MGCN_ERR_SHAPE);
@@ -318,10 +383,10 @@ extern "C" int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const fl
   MGCN_REQUIRE(N == 0 || (x && g), MGCN_ERR_NULL);
   const int64_t rows_per_slab = ceil_div(ceil_div(N > 0 ? N : 1, P), kWgRows) * kWgRows;
   const int x_vec4 = (Hi % 4 == 0) && aligned16(x);
-  const int g_vec4 = (Ho % 4 == 0) && aligned16(g);
+  const int g_vec4 = (Ho % 4 == 0) && aligned16(g) && (!gmask || aligned16(gmask));
   dim3 grid((unsigned)P, (unsigned)ceil_div(Hi, 32), (unsigned)ceil_div(Ho, 32));
-  MGCN_LAUNCH(k_wgrad_partial, grid, 256, 0, stream, x, N, (int)Hi, g, (int)Ho, rows_per_slab,
-              partial, db ? partial_b : nullptr, x_vec4, g_vec4);
+  MGCN_LAUNCH(k_wgrad_partial, grid, 256, 0, stream, x, N, (int)Hi, g, gmask, (int)Ho,
+              rows_per_slab, partial, db ? partial_b : nullptr, x_vec4, g_vec4);
   const int64_t count = Hi * Ho;
   MGCN_LAUNCH(k_wgrad_reduce, (unsigned)ceil_div(count, 256), 256, 0, stream, partial, P, count,
               (int)Ho, dw, dw_sk, dw_sc);
@@ -329,6 +394,31 @@ extern "C" int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const fl
     MGCN_LAUNCH(k_wgrad_reduce, (unsigned)ceil_div(Ho, 256), 256, 0, stream, partial_b, P, Ho, 0,
                 db, (int64_t)0, (int64_t)0);
   }
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, int64_t Ho,
+                                 float* dw, int64_t dw_sk, int64_t dw_sc, float* db,
+                                 void* workspace, size_t* workspace_bytes, void* stream) {
+  return mgcn_linear_wgrad_ex(x, N, Hi, g, nullptr, Ho, dw, dw_sk, dw_sc, db, workspace,
+                              workspace_bytes, stream);
+}
+
+extern "C" int mgcn_masked_scale(const float* g, const float* m1, const float* m2,
+                                 const float* row_scale, int64_t N, int64_t H, float* out,
+                                 void* stream) {
+  MGCN_REQUIRE(N >= 0 && H >= 4 && H % 4 == 0, MGCN_ERR_SHAPE);
+  if (N == 0) return MGCN_OK;
+  MGCN_REQUIRE(g && out, MGCN_ERR_NULL);
+  MGCN_REQUIRE(aligned16(g) && aligned16(out) && (!m1 || aligned16(m1)) && (!m2 || aligned16(m2)),
+               MGCN_ERR_ALIGN);
+  const int64_t count4 = N * H / 4;
+  int64_t blocks = ceil_div(count4, 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  MGCN_LAUNCH(k_masked_scale, (unsigned)blocks, 256, 0, stream,
+              reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(m1),
+              reinterpret_cast<const float4*>(m2), row_scale, count4, (int)(H / 4),
+              reinterpret_cast<float4*>(out));
   return MGCN_OK;
 }
 

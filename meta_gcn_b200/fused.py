@@ -1,0 +1,79 @@
+"""Whole-stack autograd for the residual GCN of the botnet path (gcn_model.py:86-106 with
+residual_hop=1, ReLU activations, additive node model, aggr='add'):
+
+    x_{n+1} = act_n( relu( A_hat (x_n W_n) + b_n ) + x_n R_n^T + r_n ),   act_n = ReLU, identity for the last layer
+
+One Function for all L layers: the degree factors are applied once per layer by the transform that
+produces the messages (x~w = pre * xW), so the aggregation needs no per-edge weight; both ReLU
+masks of the backward are folded into operand loads; no autograd graph, no [N,H] temporaries
+beyond the saved layer outputs.  Per layer: forward = transform, aggregation, residual transform
+(3 launches); backward = weight-gradient x2, transform x2, mask/scale, transposed aggregation.
+"""
+import torch
+
+from . import ops
+
+FUSED_WIDTHS = (16, 32, 64, 128)
+
+
+class _ResidualGCNStack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph, pre, post, has_bias, last_relu, *params):
+        per = 4 if has_bias else 3
+        L = len(params) // per
+        layers = [params[i * per:(i + 1) * per] for i in range(L)]
+        xs, hs = [x.contiguous()], []
+        fwd = graph.fwd
+        xw = ops.linear_impl(xs[0], layers[0][0], False, row_scale=pre)
+        for n, lp in enumerate(layers):
+            w, b = lp[0], (lp[1] if has_bias else None)
+            res_w, res_b = lp[-2], lp[-1]
+            h = ops.aggregate_prescaled_impl(fwd, xw, post, 0, b, None, 1)
+            relu_out = last_relu or n < L - 1
+            xn = ops.linear_impl(xs[n], res_w, True, res_b, h, 1 if relu_out else 0)
+            hs.append(h)
+            xs.append(xn)
+            if n + 1 < L:
+                xw = ops.linear_impl(xn, layers[n + 1][0], False, row_scale=pre)
+        ctx.graph, ctx.cfg = graph, (L, per, has_bias, last_relu)
+        ctx.pre, ctx.post = pre, post
+        ctx.save_for_backward(*xs, *hs, *params)
+        return xs[-1]
+
+    @staticmethod
+    def backward(ctx, g):
+        L, per, has_bias, last_relu = ctx.cfg
+        saved = ctx.saved_tensors
+        xs, hs, params = saved[:L + 1], saved[L + 1:2 * L + 1], saved[2 * L + 1:]
+        layers = [params[i * per:(i + 1) * per] for i in range(L)]
+        pre, post, bwd = ctx.pre, ctx.post, ctx.graph.bwd
+        grads = [None] * len(params)
+        g = g.contiguous()
+        need_x = ctx.needs_input_grad[0]
+        for n in reversed(range(L)):
+            lp = layers[n]
+            w, res_w = lp[0], lp[-2]
+            omask = xs[n + 1] if (last_relu or n < L - 1) else None
+            d_res_w, d_res_b = ops.linear_wgrad_impl(xs[n], g, True, True, omask)
+            need_dx = n > 0 or need_x
+            dxres = ops.linear_impl(g, res_w, False, xmask=omask) if need_dx else None
+            if has_bias:
+                gsu = ops.masked_scale_impl(g, omask, hs[n], None)
+                grads[n * per + 1] = gsu.sum(0)
+                gs = ops.masked_scale_impl(gsu, None, None, post) if post is not None else gsu
+            else:
+                gs = ops.masked_scale_impl(g, omask, hs[n], post)
+            dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
+            grads[n * per] = ops.linear_wgrad_impl(xs[n], dxw, False, False)[0]
+            grads[n * per + per - 2] = d_res_w
+            grads[n * per + per - 1] = d_res_b
+            if need_dx:
+                g = ops.linear_impl(dxw, w, True, add=dxres)
+        return (g if need_x else None, None, None, None, None, None, *grads)
+
+
+def residual_gcn_stack(x, graph, pre, post, layer_params, has_bias, last_relu=False):
+    """layer_params: per layer (weight_node [Hin,H], [bias [H]], residual.weight [H,Hin],
+    residual.bias [H]).  pre/post: per-source / per-target degree factors (either may be None)."""
+    flat = [p for lp in layer_params for p in lp]
+    return _ResidualGCNStack.apply(x, graph, pre, post, has_bias, last_relu, *flat)

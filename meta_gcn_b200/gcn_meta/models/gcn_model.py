@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from ... import functional as F_mgcn
+from ... import fused
 from ...graph import structure_of
 from .common import activation
 from .gcn_base_models import NodeModelBase
@@ -99,8 +100,49 @@ class GCNModel(nn.Module):
             else edge_weight_K[0]
         return NodeModelBase.degree_factors(ei, x.size(0), deg, ew, nm.deg_norm)
 
+    def _stack_eligible(self, edge_index_K, edge_attr_K, edge_weight_K):
+        """the whole-stack path covers the botnet configuration family (train_botnet.py:200-212):
+        one edge set, additive node models, residual every layer, ReLU/ReLU, sum aggregation"""
+        if self.residual_hop != 1 or getattr(self, "num_residuals", 0) != self.num_layers:
+            return False
+        if self.non_linear_layer_wise != "relu" or self._res_act != "relu":
+            return False
+        if self.training and self.dropout.p > 0:
+            return False
+        if edge_attr_K is not None or edge_weight_K is not None:
+            return False
+        if not isinstance(edge_index_K, torch.Tensor):
+            if len(edge_index_K) != 1:
+                return False
+        if any(w not in fused.FUSED_WIDTHS for w in self.enc_sizes[1:]):
+            return False
+        nms = [layer.gcn.node_models for layer in self.gcn_net]
+        if any(len(m) != 1 or layer.gcn.kernel_combine != "add" for m, layer in zip(nms, self.gcn_net)):
+            return False
+        first = nms[0][0]
+        return all(m[0].aggr == "add" and m[0].deg_norm == first.deg_norm and m[0].in_edgedim is None
+                   and (m[0].bias is None) == (first.bias is None) for m in nms)
+
+    def _forward_stack(self, x, edge_index, dis):
+        nm0 = self.gcn_net[0].gcn.node_models[0]
+        graph = structure_of(edge_index, x.size(0))
+        pre = dis
+        post = dis if nm0.deg_norm == "sm" else None
+        has_bias = nm0.bias is not None
+        params = []
+        for layer, lin in zip(self.gcn_net, self.residuals):
+            nm = layer.gcn.node_models[0]
+            params.append((nm.weight_node, nm.bias, lin.weight, lin.bias) if has_bias
+                          else (nm.weight_node, lin.weight, lin.bias))
+        return fused.residual_gcn_stack(x, graph, pre, post, params, has_bias)
+
     def forward(self, x, edge_index_K, edge_attr_K=None, deg_K=None, edge_weight_K=None, **kwargs):
         dis = self._shared_degree_factors(x, edge_index_K, deg_K, edge_weight_K)
+        if self._stack_eligible(edge_index_K, edge_attr_K, edge_weight_K) and not kwargs.get("_no_stack"):
+            ei = edge_index_K if isinstance(edge_index_K, torch.Tensor) else edge_index_K[0]
+            x = self._forward_stack(x, ei, dis)
+            return self._head(x, kwargs)
+        kwargs.pop("_no_stack", None)
         hop = self.residual_hop
         xr_src, add_xr_at, res_idx = None, -1, -1
         for n, net in enumerate(self.gcn_net):
@@ -120,6 +162,9 @@ class GCNModel(nn.Module):
                     if not last and not fuse_relu:
                         xo = self.non_linear(xo)
             x = xo
+        return self._head(x, kwargs)
+
+    def _head(self, x, kwargs):
         if self.final_type == "proj":
             x = F_mgcn.linear(x, self.final.weight, self.final.bias, weight_layout="out_in")
         if self.pred_on == "graph":

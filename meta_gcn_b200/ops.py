@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import MgcnCsr
 
-DEFAULT_HUB_THRESHOLD = 256
+DEFAULT_HUB_THRESHOLD = 64
 
 
 def _ptr(t):
@@ -206,13 +206,16 @@ def aggregate_prescaled_impl(csr, x, post_scale=None, reduce=0, bias=None, resid
     return out
 
 
-def linear_impl(x, w, w_out_in, bias=None, add=None, act=0):
-    """y = act(x @ W + bias + add); w is [Hi,Ho] (weight_node) or, if w_out_in, [Ho,Hi] (nn.Linear)."""
-    _need_cuda(x, w, bias, add)
+def linear_impl(x, w, w_out_in, bias=None, add=None, act=0, xmask=None, row_scale=None):
+    """y = row_scale * act((x * (xmask > 0)) @ W + bias + add); w is [Hi,Ho] (weight_node) or, if
+    w_out_in, [Ho,Hi] (nn.Linear)."""
+    _need_cuda(x, w, bias, add, xmask, row_scale)
     x = _f32c(x, "x")
     w = _f32c(w, "w")
     bias = _f32c(bias, "bias")
     add = _f32c(add, "add")
+    xmask = _f32c(xmask, "xmask")
+    row_scale = _f32c(row_scale, "row_scale")
     N, Hi = x.shape
     if w_out_in:
         Ho, Hi_w = w.shape
@@ -222,16 +225,19 @@ def linear_impl(x, w, w_out_in, bias=None, add=None, act=0):
         sk, sc = Ho, 1
     if Hi_w != Hi:
         raise ValueError(f"width mismatch: x has {Hi}, weight expects {Hi_w}")
+    if xmask is not None and xmask.shape != x.shape:
+        raise ValueError("xmask must have the shape of x")
     y = torch.empty(N, Ho, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().mgcn_linear(_ptr(x), N, Hi, _ptr(w), sk, sc, Ho, _ptr(bias), _ptr(add),
-                                       int(act), _ptr(y), _stream()))
+    _lib.check(_lib.load().mgcn_linear_ex(_ptr(x), _ptr(xmask), N, Hi, _ptr(w), sk, sc, Ho, _ptr(bias),
+                                          _ptr(add), int(act), _ptr(row_scale), _ptr(y), _stream()))
     return y
 
 
-def linear_wgrad_impl(x, g, w_out_in, want_bias):
-    _need_cuda(x, g)
+def linear_wgrad_impl(x, g, w_out_in, want_bias, gmask=None):
+    _need_cuda(x, g, gmask)
     x = _f32c(x, "x")
     g = _f32c(g, "g")
+    gmask = _f32c(gmask, "gmask")
     N, Hi = x.shape
     Ho = g.size(1)
     dev = x.device
@@ -243,12 +249,23 @@ def linear_wgrad_impl(x, g, w_out_in, want_bias):
         sk, sc = Ho, 1
     db = torch.empty(Ho if want_bias else 0, dtype=torch.float32, device=dev)
     lib = _lib.load()
-    nbytes = ctypes.c_size_t(0)
-    args = (_ptr(x), N, Hi, _ptr(g), Ho, _ptr(dw), sk, sc, _ptr(db) if want_bias else None)
-    _lib.check(lib.mgcn_linear_wgrad(*args, None, ctypes.byref(nbytes), None))
-    ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-    _lib.check(lib.mgcn_linear_wgrad(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    args = (_ptr(x), N, Hi, _ptr(g), _ptr(gmask), Ho, _ptr(dw), sk, sc, _ptr(db) if want_bias else None)
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_linear_wgrad_ex(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_linear_wgrad_ex(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
     return dw, db
+
+
+def masked_scale_impl(g, m1=None, m2=None, row_scale=None):
+    """out = row_scale[:,None] * g * (m1 > 0) * (m2 > 0)"""
+    _need_cuda(g, m1, m2, row_scale)
+    g = _f32c(g, "g")
+    m1 = _f32c(m1, "m1")
+    m2 = _f32c(m2, "m2")
+    row_scale = _f32c(row_scale, "row_scale")
+    out = torch.empty_like(g)
+    _lib.check(_lib.load().mgcn_masked_scale(_ptr(g), _ptr(m1), _ptr(m2), _ptr(row_scale), g.size(0),
+                                             g.size(1), _ptr(out), _stream()))
+    return out
 
 
 def relu_backward_impl(g, y):
@@ -305,8 +322,11 @@ _LIBDEF.define("spmm(Tensor[] csr, int hub_threshold, Tensor x, bool gather_perm
                "int act) -> Tensor")
 _LIBDEF.define("aggregate_prescaled(Tensor[] csr, int hub_threshold, Tensor x, Tensor? post_scale, "
                "int reduce, Tensor? bias, Tensor? residual, int act) -> Tensor")
-_LIBDEF.define("linear(Tensor x, Tensor w, bool w_out_in, Tensor? bias, Tensor? add, int act) -> Tensor")
-_LIBDEF.define("linear_wgrad(Tensor x, Tensor g, bool w_out_in, bool want_bias) -> (Tensor, Tensor)")
+_LIBDEF.define("linear(Tensor x, Tensor w, bool w_out_in, Tensor? bias, Tensor? add, int act, "
+               "Tensor? xmask=None, Tensor? row_scale=None) -> Tensor")
+_LIBDEF.define("linear_wgrad(Tensor x, Tensor g, bool w_out_in, bool want_bias, Tensor? gmask=None) -> "
+               "(Tensor, Tensor)")
+_LIBDEF.define("masked_scale(Tensor g, Tensor? m1, Tensor? m2, Tensor? row_scale) -> Tensor")
 _LIBDEF.define("relu_backward(Tensor g, Tensor y) -> Tensor")
 _LIBDEF.define("batch_to_offsets(Tensor batch, int G) -> Tensor")
 _LIBDEF.define("segment_reduce(Tensor x, Tensor offsets, int mode) -> Tensor")
@@ -346,6 +366,7 @@ _IMPLS = {
     "aggregate_prescaled": _op_aggregate_prescaled,
     "linear": linear_impl,
     "linear_wgrad": linear_wgrad_impl,
+    "masked_scale": masked_scale_impl,
     "relu_backward": relu_backward_impl,
     "batch_to_offsets": batch_to_offsets_impl,
     "segment_reduce": segment_reduce_impl,
@@ -407,14 +428,19 @@ def _(csr, hub_threshold, x, post_scale, reduce, bias, residual, act):
     return torch.empty(csr[0].numel() - 1, x.size(1), dtype=torch.float32, device=x.device)
 
 
+@torch.library.register_fake("mgcn::masked_scale")
+def _(g, m1, m2, row_scale):
+    return torch.empty_like(g)
+
+
 @torch.library.register_fake("mgcn::linear")
-def _(x, w, w_out_in, bias, add, act):
+def _(x, w, w_out_in, bias, add, act, xmask=None, row_scale=None):
     Ho = w.size(0) if w_out_in else w.size(1)
     return torch.empty(x.size(0), Ho, dtype=torch.float32, device=x.device)
 
 
 @torch.library.register_fake("mgcn::linear_wgrad")
-def _(x, g, w_out_in, want_bias):
+def _(x, g, w_out_in, want_bias, gmask=None):
     Hi, Ho = x.size(1), g.size(1)
     shape = (Ho, Hi) if w_out_in else (Hi, Ho)
     return (torch.empty(shape, dtype=torch.float32, device=x.device),

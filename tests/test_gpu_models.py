@@ -31,26 +31,34 @@ CASES = {
 }
 
 
-def run_case(model, g, opts, dev):
+def run_case(model, g, opts, dev, **extra):
     x = torch.from_numpy(g["x"]).to(dev)
     ei = torch.from_numpy(g["edge_index"]).to(dev)
     deg = torch.from_numpy(g["deg"]).to(dev) if opts.get("use_deg", True) else None
     ew = torch.from_numpy(g["edge_weight"]).to(dev) if opts.get("edge_weight") else None
     kw = {"batch_slices_x": g["batch_slices_x"].tolist()} if opts.get("graph") else {}
+    kw.update(extra)
     out = model(x, ei, deg_K=deg, edge_weight_K=ew, **kw)
     loss = torch.nn.CrossEntropyLoss()(out, torch.from_numpy(g["y"]).to(dev))
     loss.backward()
     return out, loss
 
 
+@pytest.mark.parametrize("path", ["stack", "per_layer"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_gcn_model_matches_reference_golden(name):
+def test_gcn_model_matches_reference_golden(name, path):
+    """both host paths of the mirror: the whole-stack Function (botnet family) and the per-layer
+    composition of differentiable ops (every other configuration)"""
     cfg, opts = CASES[name]
     g = golden(name)
     model = GCNModel(**cfg)
     model.load_state_dict(params_of(g), strict=True)
     model.to(DEV).train()
-    out, loss = run_case(model, g, opts, DEV)
+    eligible = model._stack_eligible(None if False else torch.zeros(2, 0), None,
+                                     True if opts.get("edge_weight") else None)
+    if path == "stack" and not eligible:
+        pytest.skip("configuration outside the whole-stack family")
+    out, loss = run_case(model, g, opts, DEV, **({"_no_stack": True} if path == "per_layer" else {}))
     assert_parity(out, g["out"], name + ".out")
     assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(1.0, abs(float(g["loss"])))
     for k, p in model.named_parameters():
