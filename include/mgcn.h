@@ -203,6 +203,18 @@ int mgcn_segment_reduce(const float* x, int64_t H, const int32_t* offsets, int64
 int mgcn_segment_broadcast(const float* gout, int64_t H, const int32_t* offsets, int64_t G,
                            int64_t N, int mode, float* dx, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Node-level cross entropy — nn.CrossEntropyLoss()(x, batch.y.long()) (train_botnet.py:225,287).
+ * loss[0] = sum_n ( logsumexp(logits[n,:]) - logits[n, target[n]] ) (* 1/N if mean), fixed-order
+ * two-stage sum.  bad_target int32[1] is set if a label is outside [0,C).
+ * bwd: dlogits = (softmax - onehot) * (1/N if mean) * upstream[0]   (upstream: device scalar or NULL)
+ */
+int mgcn_cross_entropy_fwd(const float* logits, const int64_t* target, int64_t N, int64_t C, int mean,
+                           float* loss, int32_t* bad_target, void* workspace, size_t* workspace_bytes,
+                           void* stream);
+int mgcn_cross_entropy_bwd(const float* logits, const int64_t* target, int64_t N, int64_t C, int mean,
+                           const float* upstream, float* dlogits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,25 @@ def scatter_rows(src, index, dim_size=None, reduce="add"):
     if squeeze:
         return out.squeeze(1)
     return out.reshape(dim_size, *src.shape[1:])
+
+
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, mean):
+        loss, _bad = ops.cross_entropy_fwd_impl(logits, target, mean)
+        ctx.mean = mean
+        ctx.save_for_backward(logits, target)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target = ctx.saved_tensors
+        return ops.cross_entropy_bwd_impl(logits, target, ctx.mean, g.contiguous()), None, None
+
+
+def cross_entropy(logits, target, reduction="mean"):
+    """nn.CrossEntropyLoss(reduction=...)(logits, target) over node logits (train_botnet.py:225,287)
+    as two deterministic kernels; target is int64 class ids."""
+    if reduction not in ("mean", "sum"):
+        raise ValueError("reduction must be 'mean' or 'sum'")
+    return _CrossEntropy.apply(logits, target, reduction == "mean")

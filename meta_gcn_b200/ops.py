@@ -268,6 +268,33 @@ def masked_scale_impl(g, m1=None, m2=None, row_scale=None):
     return out
 
 
+def cross_entropy_fwd_impl(logits, target, mean):
+    _need_cuda(logits, target)
+    logits = _f32c(logits, "logits")
+    if target.dtype != torch.int64:
+        raise TypeError("target must be int64 (batch.y.long())")
+    target = target.contiguous()
+    N, C = logits.shape
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    bad = torch.empty(1, dtype=torch.int32, device=logits.device)
+    lib = _lib.load()
+    args = (_ptr(logits), _ptr(target), N, C, int(bool(mean)), _ptr(loss), _ptr(bad))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_cross_entropy_fwd(*args, w_, nb, stm), logits.device)
+    _lib.check(lib.mgcn_cross_entropy_fwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return loss, bad
+
+
+def cross_entropy_bwd_impl(logits, target, mean, upstream):
+    _need_cuda(logits, target, upstream)
+    logits = _f32c(logits, "logits")
+    N, C = logits.shape
+    up = None if upstream is None else _f32c(upstream, "upstream").reshape(-1)
+    out = torch.empty_like(logits)
+    _lib.check(_lib.load().mgcn_cross_entropy_bwd(_ptr(logits), _ptr(target.contiguous()), N, C,
+                                                  int(bool(mean)), _ptr(up), _ptr(out), _stream()))
+    return out
+
+
 def relu_backward_impl(g, y):
     _need_cuda(g, y)
     g = _f32c(g, "g")
@@ -328,6 +355,8 @@ _LIBDEF.define("linear_wgrad(Tensor x, Tensor g, bool w_out_in, bool want_bias, 
                "(Tensor, Tensor)")
 _LIBDEF.define("masked_scale(Tensor g, Tensor? m1, Tensor? m2, Tensor? row_scale) -> Tensor")
 _LIBDEF.define("relu_backward(Tensor g, Tensor y) -> Tensor")
+_LIBDEF.define("cross_entropy_fwd(Tensor logits, Tensor target, bool mean) -> (Tensor, Tensor)")
+_LIBDEF.define("cross_entropy_bwd(Tensor logits, Tensor target, bool mean, Tensor? upstream) -> Tensor")
 _LIBDEF.define("batch_to_offsets(Tensor batch, int G) -> Tensor")
 _LIBDEF.define("segment_reduce(Tensor x, Tensor offsets, int mode) -> Tensor")
 _LIBDEF.define("segment_broadcast(Tensor gout, Tensor offsets, int N, int mode) -> Tensor")
@@ -368,6 +397,8 @@ _IMPLS = {
     "linear_wgrad": linear_wgrad_impl,
     "masked_scale": masked_scale_impl,
     "relu_backward": relu_backward_impl,
+    "cross_entropy_fwd": cross_entropy_fwd_impl,
+    "cross_entropy_bwd": cross_entropy_bwd_impl,
     "batch_to_offsets": batch_to_offsets_impl,
     "segment_reduce": segment_reduce_impl,
     "segment_broadcast": segment_broadcast_impl,
@@ -445,6 +476,17 @@ def _(x, g, w_out_in, want_bias, gmask=None):
     shape = (Ho, Hi) if w_out_in else (Hi, Ho)
     return (torch.empty(shape, dtype=torch.float32, device=x.device),
             torch.empty(Ho if want_bias else 0, dtype=torch.float32, device=x.device))
+
+
+@torch.library.register_fake("mgcn::cross_entropy_fwd")
+def _(logits, target, mean):
+    return (torch.empty(1, dtype=torch.float32, device=logits.device),
+            torch.empty(1, dtype=torch.int32, device=logits.device))
+
+
+@torch.library.register_fake("mgcn::cross_entropy_bwd")
+def _(logits, target, mean, upstream):
+    return torch.empty_like(logits)
 
 
 @torch.library.register_fake("mgcn::relu_backward")

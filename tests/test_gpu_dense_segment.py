@@ -104,3 +104,38 @@ def test_segment_reduce_large_graphs_and_backward(H):
     assert_parity(xd.grad, x.grad, "mean pool backward")
     out_b = F_mgcn.pool_by_batch(xd, batch.to(DEV), len(sizes), "mean")
     assert_bitexact(out_b, out, "deterministic")
+
+
+@pytest.mark.parametrize("C", [2, 5, 16])
+@pytest.mark.parametrize("reduction", ["mean", "sum"])
+def test_cross_entropy_matches_torch(C, reduction):
+    N = 70001
+    g = torch.Generator().manual_seed(C)
+    z = (torch.randn(N, C, generator=g) * 3).requires_grad_(True)
+    y = torch.randint(0, C, (N,), generator=g)
+    ref = torch.nn.CrossEntropyLoss(reduction=reduction)(z.double(), y)
+    ref.backward()
+    zd = z.detach().to(DEV).requires_grad_(True)
+    loss = F_mgcn.cross_entropy(zd, y.to(DEV), reduction)
+    (loss * 1.5).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert_parity(zd.grad, 1.5 * z.grad, "dlogits")
+    loss2 = F_mgcn.cross_entropy(zd, y.to(DEV), reduction)
+    assert loss2.item() == loss.item()
+
+
+def test_masked_scale_and_masked_operands():
+    N, H = 5000, 32
+    g = torch.Generator().manual_seed(1)
+    a, m1, m2 = (torch.randn(N, H, generator=g) for _ in range(3))
+    rs = torch.rand(N, generator=g)
+    out = ops.masked_scale_impl(a.to(DEV), m1.to(DEV), m2.to(DEV), rs.to(DEV))
+    ref = rs.view(-1, 1) * (a * (m1 > 0) * (m2 > 0))
+    assert_bitexact(out, ref, "masked_scale")
+    w = torch.randn(H, H, generator=g) / H ** 0.5
+    y = ops.linear_impl(a.to(DEV), w.to(DEV), False, xmask=m1.to(DEV), row_scale=rs.to(DEV))
+    assert_parity(y, rs.double().view(-1, 1) * ((a * (m1 > 0)).double() @ w.double()), "masked, row-scaled linear")
+    dw, db = ops.linear_wgrad_impl(a.to(DEV), m2.to(DEV), True, True, gmask=m1.to(DEV))
+    gm = (m2 * (m1 > 0)).double()
+    assert_parity(dw, gm.t() @ a.double(), "masked wgrad")
+    assert_parity(db, gm.sum(0), "masked bias grad")
