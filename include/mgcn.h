@@ -191,6 +191,43 @@ int mgcn_masked_scale(const float* g, const float* m1, const float* m2, const fl
 int mgcn_relu_backward(const float* g, const float* y, int64_t count, float* g_in, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * One residual GCN layer of the botnet model at hidden width 32 — GCNModel.forward's loop body
+ * (gcn_model.py:89-106) around NodeModelAdditive.forward (gcn_base_models.py:199-243), and its
+ * autograd (train_botnet.py:293), as fused launches.  m = pre * (x W_n) are the layer's messages,
+ * already scaled by the per-source degree factor by whoever produced them (the previous layer's
+ * launch, or mgcn_linear_ex for the first layer).
+ *
+ * forward:   h      = relu( post * sum_{e: col[e]=i} m[row[e]] + bias )     rows of g (built by target)
+ *            y      = h + x res_w^T + res_b       (or h + resid when the residual term is precomputed:
+ *                                                  first layer, input width != 32; exactly one of
+ *                                                  x / resid is non-NULL)
+ *            x_next = act_out ? relu(y) : y
+ *            m_next = pre * (x_next w_next)       (w_next may be NULL: last layer)
+ *            hmask[i] bit c = (h[i,c] > 0)
+ * Sums run in edge_index order per row (hub rows: per segment, segments left to right); the dense
+ * products run on the tensor pipe as 3xTF32 (error ~2^-21 relative), fp32 accumulate.
+ */
+int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n_in, const float* x,
+                       const float* resid, const float* res_w, const float* res_b,
+                       const float* w_next, const float* bias, const float* pre, const float* post,
+                       int act_out, int64_t H, float* x_next, float* m_next, uint32_t* hmask,
+                       void* workspace, size_t* workspace_bytes, void* stream);
+
+/* backward, row-local part of layer n (dxw = pre * A^T gs comes from mgcn_aggregate_prescaled on the
+ * structure built by source):
+ *   G = dxw w^T + gy res_w;  dw = x^T dxw;  d_res_w = gy^T x;  d_res_b = colsum(gy)
+ *   gy_prev = G * (x > 0);   gs_prev = post * gy_prev * bits(hmask_prev)      (both NULL: not wanted)
+ * Weight gradients are reduced in a fixed order (deterministic, no atomics). */
+int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float* x, const float* w,
+                       const float* res_w, const uint32_t* hmask_prev, const float* post, int64_t N,
+                       int64_t H, float* gy_prev, float* gs_prev, float* dw, float* d_res_w,
+                       float* d_res_b, void* workspace, size_t* workspace_bytes, void* stream);
+
+/* gs[i,c] = post[i] * gy[i,c] * bit c of bits[i]   (H = 32; post may be NULL) */
+int mgcn_mask_bits_scale(const float* gy, const uint32_t* bits, const float* post, int64_t N,
+                         int64_t H, float* gs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Segment reductions — global_mean_pool / global_add_pool (kernel/gcn.py:29, gin.py:44,
  * graph_sage.py:29) and GCNModel's pred_on='graph' mean (gcn_model.py:112-123).
  * offsets int32[G+1] delimit contiguous node ranges (batch vector sorted ascending).

@@ -1,0 +1,719 @@
+// One residual GCN layer of the botnet model (gcn_model.py:89-106 around
+// NodeModelAdditive.forward, gcn_base_models.py:199-243) at hidden = 32, as three kernels:
+//
+//   k_layer_fwd   (forward, one launch per layer)
+//       h_i     = relu( post_i * sum_{e: col[e]=i} m[row[e]] + bias )          m = pre * (x W_n), written by
+//       y_i     = h_i + x_i R_n^T + r_n                                       the previous layer's launch
+//       x'_i    = act(y_i)                     -> x_next      (act = ReLU, identity for the last layer)
+//       m'_i    = pre_i * (x'_i W_{n+1})       -> m_next      (messages of the next layer)
+//       bits_i  = (h_i > 0) as one 32-bit word -> hmask       (all the backward needs of h)
+//     A lane group of 8 lanes owns a row (float4 per lane) and sums its entries in edge_index order —
+//     the reference's CPU scatter_add order — 4 rows per warp at a time, 16 rows per tile; the tile's
+//     two dense products run on the tensor pipe (mma.sync m16n8k8, 3xTF32) out of shared memory, so
+//     per layer the forward reads m (gathered) and x once and writes x' and m' once.
+//   k_agg_plain   (agg_pipelined.cu; backward, transposed aggregation)   dxw = pre * A^T gs
+//   k_layer_bwd   (backward, row-local):
+//       G       = dxw W_n^T + gy R_n;   dW_n = x_n^T dxw;   dR_n = gy^T x_n;   dr_n = colsum(gy)
+//       gy_prev = G * (x_n > 0);        gs_prev = post * gy_prev * bits_{n-1}
+//     gy is the gradient w.r.t. y_n (outer ReLU already applied), gs the operand of the transposed
+//     aggregation of layer n-1.  Weight gradients accumulate in registers over all tiles of a warp and
+//     are reduced warp -> CTA -> grid in a fixed order (deterministic, no atomics).
+//
+// Why the tensor pipe at H = 32: 6 products of [N,32]x[32,32] per layer are 0.53 TFLOP per step at the
+// botnet batch; the FP32 FMA peak (74 TFLOP/s) alone would cost 7 ms against a 5 ms HBM bound for the
+// whole step (measured: FMA transforms 0.28-0.54 ms per product, scripts/microbench.py).  fp32 parity
+// (rtol 1e-5) rules out single-pass TF32, hence the hi/lo split of mma_tile.cuh.
+#include <mutex>
+
+#include "common.cuh"
+#include "mma_tile.cuh"
+
+namespace mgcn {
+
+constexpr int kH = 32;
+constexpr int kLda = kH + 4;   // activation tiles: conflict-free row-major A fragments
+constexpr int kLdb = kH + 8;   // weight planes: conflict-free B fragments
+constexpr int kPlane = kH * kLdb;
+
+__device__ __forceinline__ float4 f4_add2(float4 a, float4 b) {
+  // two packed f32x2 adds (sm_100 FADD2): same IEEE result per element as four scalar adds
+  float4 r;
+  asm("{\n .reg .b64 a0, a1, b0, b1;\n mov.b64 a0, {%4, %5};\n mov.b64 a1, {%6, %7};\n"
+      " mov.b64 b0, {%8, %9};\n mov.b64 b1, {%10, %11};\n add.rn.f32x2 a0, a0, b0;\n"
+      " add.rn.f32x2 a1, a1, b1;\n mov.b64 {%0, %1}, a0;\n mov.b64 {%2, %3}, a1;\n}\n"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+      : "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w));
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// plane(k, c) = w[k*stride_k + c*stride_c] split into tf32 hi / lo, [kH][kLdb] each
+__device__ __forceinline__ void fill_plane(const float* __restrict__ w, int stride_k, int stride_c,
+                                           float* __restrict__ hi, float* __restrict__ lo, int tid,
+                                           int nthreads) {
+  for (int i = tid; i < kH * kH; i += nthreads) {
+    const int k = i / kH, c = i % kH;
+    uint32_t h, l;
+    split_tf32(__ldg(w + k * stride_k + c * stride_c), h, l);
+    hi[k * kLdb + c] = __uint_as_float(h);
+    lo[k * kLdb + c] = __uint_as_float(l);
+  }
+}
+
+struct LayerFwdArgs {
+  const int4* tasks;        // work descriptors (mgcn_csr_t::tasks)
+  const int32_t* nbr;
+  const int32_t* seg_count;
+  const int32_t* hub_rows;
+  const int32_t* hub_seg0;
+  const int32_t* hub_count;
+  const int32_t* rowptr;
+  const float* m;           // [n_in, 32] messages, pre-scaled by the per-source factor
+  const float* x;           // [N, 32] layer input (residual operand), or NULL when resid is given
+  const float* resid;       // [N, 32] finished residual term x R^T + r (first layer, H_in != 32)
+  const float* res_w;       // [32][32] nn.Linear.weight (out, in)
+  const float* res_b;       // [32] or NULL
+  const float* w_next;      // [32][32] weight_node of the next layer (in, out), or NULL
+  const float* bias;        // node-model bias [32] or NULL
+  const float* pre;         // per-source factor of the NEXT layer's messages, or NULL
+  const float* post;        // per-target factor, or NULL
+  float* x_next;            // [N, 32]
+  float* m_next;            // [N, 32] (with w_next)
+  uint32_t* hmask;          // [N]
+  float* partial;           // [seg_cap, 32] hub segment sums
+  int64_t n_rows;
+  int64_t seg_cap;
+  int64_t hub_cap;
+  int act_out;
+  int hub_threshold;
+};
+
+// Sum rows m[nbr[k]] for k in [beg, end), in order, for the 4 columns of this lane.  The 8 lanes of
+// a group call this together; gi holds nbr[beg + sub] (the first index batch, fetched earlier).
+__device__ __forceinline__ float4 gather_sum(const float* __restrict__ m, const int32_t* __restrict__ nbr,
+                                             int beg, int end, int gi, int sub, int grp_lane0,
+                                             unsigned gmask, int col) {
+  constexpr int U = 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int e = beg;
+  while (true) {
+    const int cnt = min(8, end - e);
+    const int e_next = e + 8;
+    int g_next = 0;
+    if (e_next + sub < end) g_next = __ldg(nbr + e_next + sub);  // next batch, before the gathers
+#pragma unroll
+    for (int t0 = 0; t0 < 8; t0 += U) {
+      if (t0 < cnt) {
+        int j[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = __shfl_sync(gmask, gi, grp_lane0 + t0 + u);
+        float4 xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t0 + u < cnt) xv[u] = __ldg(reinterpret_cast<const float4*>(m + (int64_t)j[u] * kH + col));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t0 + u < cnt) acc = f4_add2(acc, xv[u]);
+        }
+      }
+    }
+    if (e_next >= end) break;
+    e = e_next;
+    gi = g_next;
+  }
+  return acc;
+}
+
+// h = relu(post * acc + bias) -> Hs row, mask word -> hmask[row]
+__device__ __forceinline__ void finish_h(const LayerFwdArgs& a, float4 acc, float post, int64_t row,
+                                         float* __restrict__ hs_row, int sub, unsigned gmask, int col) {
+  if (a.post) {
+    acc.x = __fmul_rn(acc.x, post); acc.y = __fmul_rn(acc.y, post);
+    acc.z = __fmul_rn(acc.z, post); acc.w = __fmul_rn(acc.w, post);
+  }
+  if (a.bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col));
+    acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
+    acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+  }
+  acc.x = acc.x > 0.f ? acc.x : 0.f; acc.y = acc.y > 0.f ? acc.y : 0.f;
+  acc.z = acc.z > 0.f ? acc.z : 0.f; acc.w = acc.w > 0.f ? acc.w : 0.f;
+  *reinterpret_cast<float4*>(hs_row + col) = acc;
+  uint32_t bits = ((acc.x > 0.f ? 1u : 0u) | (acc.y > 0.f ? 2u : 0u) | (acc.z > 0.f ? 4u : 0u) |
+                   (acc.w > 0.f ? 8u : 0u)) << col;
+  bits |= __shfl_xor_sync(gmask, bits, 1);
+  bits |= __shfl_xor_sync(gmask, bits, 2);
+  bits |= __shfl_xor_sync(gmask, bits, 4);
+  if (sub == 0) a.hmask[row] = bits;
+}
+
+// residual operand rows (x, or the finished residual term) of a 16-row tile -> Xs, asynchronously
+__device__ __forceinline__ void stage_tile_async(const float* __restrict__ src, int myrow,
+                                                 float (*Xs)[kLda], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = i * 32 + lane;
+    const int r = c >> 3, q = c & 7;
+    const int rid = __shfl_sync(0xffffffffu, myrow, r);
+    cp_async16(&Xs[r][4 * q], src + (int64_t)(rid >= 0 ? rid : 0) * kH + 4 * q, rid >= 0 ? 16 : 0);
+  }
+}
+
+__device__ __forceinline__ void store_tile_rows(float* __restrict__ dst, int myrow,
+                                                const float (*Ts)[kLda], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = i * 32 + lane;
+    const int r = c >> 3, q = c & 7;
+    const int rid = __shfl_sync(0xffffffffu, myrow, r);
+    if (rid >= 0)
+      *reinterpret_cast<float4*>(dst + (int64_t)rid * kH + 4 * q) =
+          *reinterpret_cast<const float4*>(&Ts[r][4 * q]);
+  }
+}
+
+// Dense tail of a 16-row tile.  In: Hs = h rows, Xs = residual operand rows; lanes 0..15 hold the
+// tile's row ids (myrow, -1 = no row) and per-source factors (mypre).
+__device__ __forceinline__ void fwd_tile_tail(const LayerFwdArgs& a, float (*Xs)[kLda],
+                                              float (*Hs)[kLda], const float* __restrict__ planes,
+                                              int myrow, float mypre, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  float acc[kH / 8][4];
+  if (a.x) {
+    warp_gemm16<kH, kH>(&Xs[0][0], kLda, planes, planes + kPlane, kLdb, acc, lane);
+    __syncwarp();  // every lane's A fragments are read before the tile is overwritten
+  }
+#pragma unroll
+  for (int j = 0; j < kH / 8; ++j) {
+    const int c = 8 * j + 2 * t;
+    float b0 = 0.f, b1 = 0.f;
+    if (a.x && a.res_b) {
+      b0 = __ldg(a.res_b + c);
+      b1 = __ldg(a.res_b + c + 1);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int rr = g + 8 * half;
+      const float2 hv = *reinterpret_cast<const float2*>(&Hs[rr][c]);
+      float v0, v1;
+      if (a.x) {
+        v0 = (acc[j][2 * half] + b0) + hv.x;
+        v1 = (acc[j][2 * half + 1] + b1) + hv.y;
+      } else {
+        const float2 rv = *reinterpret_cast<const float2*>(&Xs[rr][c]);
+        v0 = hv.x + rv.x;
+        v1 = hv.y + rv.y;
+      }
+      if (a.act_out == 1) {
+        v0 = v0 > 0.f ? v0 : 0.f;
+        v1 = v1 > 0.f ? v1 : 0.f;
+      }
+      *reinterpret_cast<float2*>(&Xs[rr][c]) = make_float2(v0, v1);
+    }
+  }
+  __syncwarp();
+  store_tile_rows(a.x_next, myrow, Xs, lane);
+  if (a.w_next) {
+    warp_gemm16<kH, kH>(&Xs[0][0], kLda, planes + 2 * kPlane, planes + 3 * kPlane, kLdb, acc, lane);
+    const float p0 = __shfl_sync(0xffffffffu, mypre, g);
+    const float p1 = __shfl_sync(0xffffffffu, mypre, g + 8);
+#pragma unroll
+    for (int j = 0; j < kH / 8; ++j) {
+      const int c = 8 * j + 2 * t;
+      *reinterpret_cast<float2*>(&Hs[g][c]) = make_float2(acc[j][0] * p0, acc[j][1] * p0);
+      *reinterpret_cast<float2*>(&Hs[g + 8][c]) = make_float2(acc[j][2] * p1, acc[j][3] * p1);
+    }
+    __syncwarp();
+    store_tile_rows(a.m_next, myrow, Hs, lane);
+  }
+  __syncwarp();  // tile buffers are free for the next tile
+}
+
+constexpr int kFwdWarps = 8;
+constexpr int kFwdSmemFloats = 4 * kPlane + kFwdWarps * 2 * 16 * kLda;
+
+__device__ __forceinline__ void fwd_fill_planes(const LayerFwdArgs& a, float* planes, int tid, int nthreads) {
+  if (a.x) fill_plane(a.res_w, 1, kH, planes, planes + kPlane, tid, nthreads);                 // (k,c) = R[c][k]
+  if (a.w_next) fill_plane(a.w_next, kH, 1, planes + 2 * kPlane, planes + 3 * kPlane, tid, nthreads);  // W[k][c]
+}
+
+__global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd(const LayerFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* planes = smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float (*Xs)[kLda] = reinterpret_cast<float (*)[kLda]>(smem + 4 * kPlane + warp * 2 * 16 * kLda);
+  float (*Hs)[kLda] = Xs + 16;
+  fwd_fill_planes(a, planes, tid, kFwdWarps * 32);
+  __syncthreads();
+
+  const int sub = lane & 7, grp = lane >> 3, grp_lane0 = grp * 8;
+  const unsigned gmask = 0xffu << grp_lane0;
+  const int col = sub * 4;
+  const int64_t n_row_tiles = (a.n_rows + 15) >> 4;
+  int64_t nseg = 0;
+  if (a.seg_count) {
+    nseg = *a.seg_count;
+    if (nseg > a.seg_cap) nseg = a.seg_cap;
+  }
+  const int64_t n_tiles = n_row_tiles + ((nseg + 15) >> 4);
+  const int64_t stride = (int64_t)gridDim.x * kFwdWarps;
+  const int4 kNone = make_int4(-1, 0, 0, 0);
+
+  auto load_desc = [&](int64_t tl) -> int4 {
+    int4 d = kNone;
+    if (tl < n_tiles && lane < 16) {
+      if (tl < n_row_tiles) {
+        const int64_t idx = tl * 16 + lane;
+        if (idx < a.n_rows) d = __ldg(a.tasks + idx);
+      } else {
+        const int64_t s = (tl - n_row_tiles) * 16 + lane;
+        if (s < nseg) d = __ldg(a.tasks + a.n_rows + s);
+      }
+    }
+    return d;
+  };
+
+  int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp;
+  int4 dn = load_desc(tile);
+  for (; tile < n_tiles; tile += stride) {
+    const int4 d = dn;
+    dn = load_desc(tile + stride);
+    const bool row_tile = tile < n_row_tiles;
+    const int myrow = d.x;
+    float mypost = 1.f, mypre = 1.f;
+    if (row_tile && myrow >= 0) {
+      if (a.post) mypost = __ldg(a.post + myrow);
+      if (a.pre && a.w_next) mypre = __ldg(a.pre + myrow);
+    }
+    int beg[4], end[4], gi[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      beg[p] = __shfl_sync(0xffffffffu, d.y, 4 * p + grp);
+      end[p] = __shfl_sync(0xffffffffu, d.z, 4 * p + grp);
+      gi[p] = (beg[p] + sub < end[p]) ? __ldg(a.nbr + beg[p] + sub) : 0;
+    }
+    if (row_tile) stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int rowp = __shfl_sync(0xffffffffu, myrow, 4 * p + grp);
+      const int slot = __shfl_sync(0xffffffffu, d.w, 4 * p + grp);
+      const float postp = __shfl_sync(0xffffffffu, mypost, 4 * p + grp);
+      if (rowp >= 0) {
+        const float4 acc = gather_sum(a.m, a.nbr, beg[p], end[p], gi[p], sub, grp_lane0, gmask, col);
+        if (slot != 0) {
+          *reinterpret_cast<float4*>(a.partial + (int64_t)(slot - 1) * kH + col) = acc;
+        } else {
+          finish_h(a, acc, postp, rowp, &Hs[4 * p + grp][0], sub, gmask, col);
+        }
+      }
+    }
+    if (!row_tile) continue;
+    cp_async_wait_all();
+    __syncwarp();
+    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane);
+  }
+}
+
+// hub rows: partial sums of the row's segments added left to right, then the same tile tail
+__global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd_hubs(const LayerFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* planes = smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float (*Xs)[kLda] = reinterpret_cast<float (*)[kLda]>(smem + 4 * kPlane + warp * 2 * 16 * kLda);
+  float (*Hs)[kLda] = Xs + 16;
+  int64_t nh = *a.hub_count;
+  if (nh > a.hub_cap) nh = a.hub_cap;
+  const int64_t n_tiles = (nh + 15) >> 4;
+  if ((int64_t)blockIdx.x * kFwdWarps >= n_tiles) return;
+  fwd_fill_planes(a, planes, tid, kFwdWarps * 32);
+  __syncthreads();
+  const int sub = lane & 7, grp = lane >> 3, grp_lane0 = grp * 8;
+  const unsigned gmask = 0xffu << grp_lane0;
+  const int col = sub * 4;
+  for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < n_tiles;
+       tile += (int64_t)gridDim.x * kFwdWarps) {
+    int myrow = -1, myseg0 = 0, mynseg = 0;
+    float mypost = 1.f, mypre = 1.f;
+    const int64_t k = tile * 16 + lane;
+    if (lane < 16 && k < nh) {
+      myrow = __ldg(a.hub_rows + k);
+      myseg0 = __ldg(a.hub_seg0 + k);
+      const int len = __ldg(a.rowptr + myrow + 1) - __ldg(a.rowptr + myrow);
+      mynseg = (len + a.hub_threshold - 1) / a.hub_threshold;
+      if (a.post) mypost = __ldg(a.post + myrow);
+      if (a.pre && a.w_next) mypre = __ldg(a.pre + myrow);
+    }
+    stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int rowp = __shfl_sync(0xffffffffu, myrow, 4 * p + grp);
+      const int s0 = __shfl_sync(0xffffffffu, myseg0, 4 * p + grp);
+      const int ns = __shfl_sync(0xffffffffu, mynseg, 4 * p + grp);
+      const float postp = __shfl_sync(0xffffffffu, mypost, 4 * p + grp);
+      if (rowp >= 0) {
+        float4 tot = *reinterpret_cast<const float4*>(a.partial + (int64_t)s0 * kH + col);
+        for (int q = 1; q < ns; ++q)
+          tot = f4_add2(tot, *reinterpret_cast<const float4*>(a.partial + (int64_t)(s0 + q) * kH + col));
+        finish_h(a, tot, postp, rowp, &Hs[4 * p + grp][0], sub, gmask, col);
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward, row-local
+// -------------------------------------------------------------------------------------------------
+struct LayerBwdArgs {
+  const float* dxw;          // [N,32]  pre * A^T gs          (transposed aggregation)
+  const float* gy;           // [N,32]  gradient w.r.t. y_n
+  const float* x;            // [N,32]  layer input x_n
+  const float* w;            // weight_node (in, out)
+  const float* res_w;        // residual weight (out, in)
+  const uint32_t* hmask_prev;  // bits of h_{n-1} > 0
+  const float* post;         // per-target factor or NULL
+  float* gy_prev;            // [N,32] or NULL
+  float* gs_prev;            // [N,32] or NULL
+  float* part_w;             // [grid][32*32]
+  float* part_r;             // [grid][32*32]
+  float* part_b;             // [grid][32]
+  int64_t n_rows;
+};
+
+constexpr int kBwdWarps = 8;
+constexpr int kBwdRows = 16 * kBwdWarps;  // rows per CTA tile
+constexpr int kLdx = kH + 8;              // x tile: only ever a transposed-product operand
+constexpr int kBwdSmemFloats = 4 * kPlane + kBwdRows * (2 * kLda + kLdx);
+
+template <int LD>
+__device__ __forceinline__ void stage_rows_async(const float* __restrict__ src, int64_t row0, int64_t N,
+                                                 float (*dst)[LD], int tid) {
+#pragma unroll
+  for (int i = 0; i < kBwdRows * 8 / (kBwdWarps * 32); ++i) {
+    const int c = i * (kBwdWarps * 32) + tid;
+    const int r = c >> 3, q = c & 7;
+    const int64_t gr = row0 + r;
+    cp_async16(&dst[r][4 * q], src + (gr < N ? gr : 0) * kH + 4 * q, gr < N ? 16 : 0);
+  }
+}
+
+// 16 rows of a tile -> global, 128 bytes per row, 4 rows per instruction
+__device__ __forceinline__ void store_rows16(float* __restrict__ dst, int64_t row0, int64_t N,
+                                             const float (*src)[kLda], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = i * 32 + lane;
+    const int r = c >> 3, q = c & 7;
+    const int64_t gr = row0 + r;
+    if (gr < N)
+      *reinterpret_cast<float4*>(dst + gr * kH + 4 * q) = *reinterpret_cast<const float4*>(&src[r][4 * q]);
+  }
+}
+
+// One CTA walks 128-row tiles.  Row-local products (G): warp w owns rows [16w, 16w+16).  Weight
+// gradients: warp w owns one 16x16 block of dW (w < 4) or dR (w >= 4) over all 128 rows of the tile,
+// so the persistent accumulators are 8 registers per thread and no cross-warp reduction is needed.
+__global__ void __launch_bounds__(kBwdWarps * 32, 2) k_layer_bwd(const LayerBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* planes = smem;  // W^T hi/lo, R hi/lo
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float (*Dw)[kLda] = reinterpret_cast<float (*)[kLda]>(smem + 4 * kPlane);
+  float (*Gy)[kLda] = Dw + kBwdRows;
+  float (*Xs)[kLdx] = reinterpret_cast<float (*)[kLdx]>(smem + 4 * kPlane + 2 * kBwdRows * kLda);
+  fill_plane(a.w, 1, kH, planes, planes + kPlane, tid, kBwdWarps * 32);                  // (k=c, n=j) = W[j][c]
+  fill_plane(a.res_w, kH, 1, planes + 2 * kPlane, planes + 3 * kPlane, tid, kBwdWarps * 32);  // (k=c, n=j) = R[c][j]
+  const int prod = warp >> 2;            // 0: dW = x^T dxw, 1: dR = gy^T x
+  const int m0 = ((warp >> 1) & 1) * 16, n0 = (warp & 1) * 16;
+  float acc_blk[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc_blk[j][q] = 0.f;
+  float acc_b = 0.f;
+  const bool want_prev = a.gy_prev != nullptr;
+  const int64_t ntiles = (a.n_rows + kBwdRows - 1) / kBwdRows;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kBwdRows;
+    __syncthreads();  // previous tile fully consumed (also orders the plane fill)
+    stage_rows_async<kLda>(a.dxw, row0, a.n_rows, Dw, tid);
+    stage_rows_async<kLda>(a.gy, row0, a.n_rows, Gy, tid);
+    stage_rows_async<kLdx>(a.x, row0, a.n_rows, Xs, tid);
+    uint32_t mybits = 0;
+    float mypost = 1.f;
+    const int64_t myrow = row0 + warp * 16 + lane;
+    if (want_prev && lane < 16 && myrow < a.n_rows) {
+      mybits = __ldg(a.hmask_prev + myrow);
+      if (a.post) mypost = __ldg(a.post + myrow);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // weight-gradient block of this warp over the 128 rows, flushed to the RN accumulators every 32
+    {
+      const float* As = prod == 0 ? &Xs[0][0] : &Gy[0][0];
+      const int lda = prod == 0 ? kLdx : kLda;
+      const float* Bs = prod == 0 ? &Dw[0][0] : &Xs[0][0];
+      const int ldb = prod == 0 ? kLda : kLdx;
+#pragma unroll 1
+      for (int rc = 0; rc < kBwdRows; rc += 32) {
+        float mainc[2][4], corr[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) mainc[j][q] = corr[j][q] = 0.f;
+#pragma unroll
+        for (int r0 = rc; r0 < rc + 32; r0 += 8) {
+          uint32_t ahi[4], alo[4];
+          split_tf32(As[(r0 + t) * lda + m0 + g], ahi[0], alo[0]);
+          split_tf32(As[(r0 + t) * lda + m0 + g + 8], ahi[1], alo[1]);
+          split_tf32(As[(r0 + t + 4) * lda + m0 + g], ahi[2], alo[2]);
+          split_tf32(As[(r0 + t + 4) * lda + m0 + g + 8], ahi[3], alo[3]);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t bhi[2], blo[2];
+            split_tf32(Bs[(r0 + t) * ldb + n0 + 8 * j + g], bhi[0], blo[0]);
+            split_tf32(Bs[(r0 + t + 4) * ldb + n0 + 8 * j + g], bhi[1], blo[1]);
+            mma_tf32_16x8x8(corr[j], alo, bhi);
+            mma_tf32_16x8x8(corr[j], ahi, blo);
+            mma_tf32_16x8x8(mainc[j], ahi, bhi);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc_blk[j][q] += mainc[j][q] + corr[j][q];
+      }
+      float colsum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) colsum += Gy[warp * 16 + r][lane];
+      acc_b += colsum;
+    }
+    if (want_prev) {
+      __syncthreads();  // every warp is done reading all rows of Dw / Gy
+      float (*Dt)[kLda] = Dw + warp * 16;
+      float (*Gt)[kLda] = Gy + warp * 16;
+      float accg[4][4], second[4][4];
+      warp_gemm16<kH, kH>(&Dt[0][0], kLda, planes, planes + kPlane, kLdb, accg, lane);
+      warp_gemm16<kH, kH>(&Gt[0][0], kLda, planes + 2 * kPlane, planes + 3 * kPlane, kLdb, second, lane);
+      __syncwarp();  // all fragment reads of this warp's rows are done
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int rr = g + 8 * half;
+        const uint32_t bits = __shfl_sync(0xffffffffu, mybits, rr);
+        const float ps = __shfl_sync(0xffffffffu, mypost, rr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * j + 2 * t;
+          const float2 xv = *reinterpret_cast<const float2*>(&Xs[warp * 16 + rr][c]);
+          const float g0 = xv.x > 0.f ? accg[j][2 * half] + second[j][2 * half] : 0.f;
+          const float g1 = xv.y > 0.f ? accg[j][2 * half + 1] + second[j][2 * half + 1] : 0.f;
+          *reinterpret_cast<float2*>(&Dt[rr][c]) = make_float2(g0, g1);
+          const float s0 = ((bits >> c) & 1u) ? g0 * ps : 0.f;
+          const float s1 = ((bits >> (c + 1)) & 1u) ? g1 * ps : 0.f;
+          *reinterpret_cast<float2*>(&Gt[rr][c]) = make_float2(s0, s1);
+        }
+      }
+      __syncwarp();
+      store_rows16(a.gy_prev, row0 + warp * 16, a.n_rows, Dt, lane);
+      store_rows16(a.gs_prev, row0 + warp * 16, a.n_rows, Gt, lane);
+    }
+  }
+  // this warp's 16x16 block of dW (row = input j, col = output c) or dR (row = output c, col = input j)
+  float* part = (prod == 0 ? a.part_w : a.part_r) + (int64_t)blockIdx.x * kH * kH;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = n0 + 8 * j + 2 * t;
+    *reinterpret_cast<float2*>(part + (m0 + g) * kH + c) = make_float2(acc_blk[j][0], acc_blk[j][1]);
+    *reinterpret_cast<float2*>(part + (m0 + g + 8) * kH + c) = make_float2(acc_blk[j][2], acc_blk[j][3]);
+  }
+  __syncthreads();
+  float* red = smem + 4 * kPlane;
+  red[warp * 32 + lane] = acc_b;
+  __syncthreads();
+  if (tid < 32) {
+    float s = red[tid];
+#pragma unroll
+    for (int w = 1; w < kBwdWarps; ++w) s += red[w * 32 + tid];
+    a.part_b[(int64_t)blockIdx.x * kH + tid] = s;
+  }
+}
+
+// out[i] = sum_p partial[p*count + i], p ascending in 4 interleaved chains
+__global__ void __launch_bounds__(256) k_partial_reduce(const float* __restrict__ partial, int P,
+                                                        int count, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 4 <= P; p += 4) {
+    s0 += partial[(int64_t)(p + 0) * count + i];
+    s1 += partial[(int64_t)(p + 1) * count + i];
+    s2 += partial[(int64_t)(p + 2) * count + i];
+    s3 += partial[(int64_t)(p + 3) * count + i];
+  }
+  for (; p < P; ++p) s0 += partial[(int64_t)p * count + i];
+  out[i] = (s0 + s1) + (s2 + s3);
+}
+
+// gs = post * gy * bits   (seed of the backward: last layer has no outer ReLU)
+__global__ void __launch_bounds__(256) k_mask_bits_scale(const float* __restrict__ gy,
+                                                         const uint32_t* __restrict__ bits,
+                                                         const float* __restrict__ post, int64_t N,
+                                                         float* __restrict__ gs) {
+  const int64_t total = N * (kH / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i >> 3;
+    const int c = (int)(i & 7) * 4;
+    const uint32_t b = __ldg(bits + row) >> c;
+    const float s = post ? __ldg(post + row) : 1.f;
+    float4 v = __ldg(reinterpret_cast<const float4*>(gy) + i);
+    v.x = (b & 1u) ? v.x * s : 0.f;
+    v.y = (b & 2u) ? v.y * s : 0.f;
+    v.z = (b & 4u) ? v.z * s : 0.f;
+    v.w = (b & 8u) ? v.w * s : 0.f;
+    reinterpret_cast<float4*>(gs)[i] = v;
+  }
+}
+
+static int bwd_grid(int64_t N) {
+  const int64_t tiles = ceil_div(N > 0 ? N : 1, kBwdRows);
+  const int64_t p = (int64_t)kNumSMs * 2;
+  return (int)(tiles < p ? tiles : p);
+}
+
+}  // namespace mgcn
+
+using namespace mgcn;
+
+extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n_in, const float* x,
+                                  const float* resid, const float* res_w, const float* res_b,
+                                  const float* w_next, const float* bias, const float* pre,
+                                  const float* post, int act_out, int64_t H, float* x_next,
+                                  float* m_next, uint32_t* hmask, void* workspace,
+                                  size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(g != nullptr && workspace_bytes != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(H == kH, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(act_out == 0 || act_out == 1, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(n_in >= 0 && g->n_rows >= 0, MGCN_ERR_RANGE);
+  const bool hubs = g->hub_rows && g->hub_seg0 && g->hub_count && g->seg_count && g->hub_cap > 0 &&
+                    g->seg_cap > 0;
+  WorkspaceCarver ws(workspace);
+  float* partial = ws.take<float>(hubs ? (size_t)g->seg_cap * kH : 0);
+  if (workspace == nullptr) {
+    *workspace_bytes = ws.bytes();
+    return MGCN_OK;
+  }
+  MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
+  if (g->n_rows == 0) return MGCN_OK;
+  MGCN_REQUIRE(g->rowptr && g->tasks && x_next && hmask, MGCN_ERR_NULL);
+  MGCN_REQUIRE((x != nullptr) != (resid != nullptr), MGCN_ERR_NULL);   // exactly one residual form
+  MGCN_REQUIRE(!x || res_w, MGCN_ERR_NULL);
+  MGCN_REQUIRE(!w_next || m_next, MGCN_ERR_NULL);
+  MGCN_REQUIRE(g->nnz_cap == 0 || (g->nbr && m), MGCN_ERR_NULL);
+  MGCN_REQUIRE(aligned16(g->tasks) && aligned16(m) && aligned16(x_next) && aligned16(partial) &&
+                   (!x || aligned16(x)) && (!resid || aligned16(resid)) &&
+                   (!m_next || aligned16(m_next)) && (!bias || aligned16(bias)),
+               MGCN_ERR_ALIGN);
+  LayerFwdArgs a{};
+  a.tasks = reinterpret_cast<const int4*>(g->tasks);
+  a.nbr = g->nbr;
+  a.seg_count = hubs ? g->seg_count : nullptr;
+  a.hub_rows = g->hub_rows;
+  a.hub_seg0 = g->hub_seg0;
+  a.hub_count = g->hub_count;
+  a.rowptr = g->rowptr;
+  a.m = m; a.x = x; a.resid = resid; a.res_w = res_w; a.res_b = res_b; a.w_next = w_next;
+  a.bias = bias; a.pre = pre; a.post = post;
+  a.x_next = x_next; a.m_next = m_next; a.hmask = hmask; a.partial = partial;
+  a.n_rows = g->n_rows;
+  a.seg_cap = hubs ? g->seg_cap : 0;
+  a.hub_cap = hubs ? g->hub_cap : 0;
+  a.act_out = act_out;
+  a.hub_threshold = g->hub_threshold;
+  const size_t smem = sizeof(float) * kFwdSmemFloats;
+  static std::once_flag once;   // per process; the attribute is per function, set on the current device
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(k_layer_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(k_layer_fwd_hubs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  MGCN_CHECK_CUDA(attr_err);
+  const int64_t max_tiles = ceil_div(g->n_rows, 16) + ceil_div(a.seg_cap, 16);
+  int64_t blocks = ceil_div(max_tiles, kFwdWarps);
+  if (blocks > (int64_t)kNumSMs * 3) blocks = (int64_t)kNumSMs * 3;
+  MGCN_LAUNCH(k_layer_fwd, (unsigned)blocks, kFwdWarps * 32, smem, stream, a);
+  if (hubs) {
+    int64_t hb = ceil_div(ceil_div(a.hub_cap, 16), kFwdWarps);
+    if (hb > (int64_t)kNumSMs) hb = kNumSMs;
+    MGCN_LAUNCH(k_layer_fwd_hubs, (unsigned)hb, kFwdWarps * 32, smem, stream, a);
+  }
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float* x, const float* w,
+                                  const float* res_w, const uint32_t* hmask_prev, const float* post,
+                                  int64_t N, int64_t H, float* gy_prev, float* gs_prev, float* dw,
+                                  float* d_res_w, float* d_res_b, void* workspace,
+                                  size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(H == kH, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
+  const int P = bwd_grid(N);
+  WorkspaceCarver ws(workspace);
+  float* part_w = ws.take<float>((size_t)P * kH * kH);
+  float* part_r = ws.take<float>((size_t)P * kH * kH);
+  float* part_b = ws.take<float>((size_t)P * kH);
+  if (workspace == nullptr) {
+    *workspace_bytes = ws.bytes();
+    return MGCN_OK;
+  }
+  MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
+  MGCN_REQUIRE(dxw && gy && x && w && res_w && dw && d_res_w && d_res_b, MGCN_ERR_NULL);
+  MGCN_REQUIRE((gy_prev == nullptr) == (gs_prev == nullptr), MGCN_ERR_NULL);
+  MGCN_REQUIRE(!gy_prev || hmask_prev, MGCN_ERR_NULL);
+  MGCN_REQUIRE(aligned16(dxw) && aligned16(gy) && aligned16(x) && (!gy_prev || aligned16(gy_prev)) &&
+                   (!gs_prev || aligned16(gs_prev)),
+               MGCN_ERR_ALIGN);
+  LayerBwdArgs a{};
+  a.dxw = dxw; a.gy = gy; a.x = x; a.w = w; a.res_w = res_w; a.hmask_prev = hmask_prev; a.post = post;
+  a.gy_prev = gy_prev; a.gs_prev = gs_prev;
+  a.part_w = part_w; a.part_r = part_r; a.part_b = part_b;
+  a.n_rows = N;
+  const size_t smem = sizeof(float) * kBwdSmemFloats;
+  static std::once_flag once;
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(k_layer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  MGCN_CHECK_CUDA(attr_err);
+  MGCN_LAUNCH(k_layer_bwd, P, kBwdWarps * 32, smem, stream, a);
+  MGCN_LAUNCH(k_partial_reduce, (kH * kH + 255) / 256, 256, 0, stream, part_w, P, kH * kH, dw);
+  MGCN_LAUNCH(k_partial_reduce, (kH * kH + 255) / 256, 256, 0, stream, part_r, P, kH * kH, d_res_w);
+  MGCN_LAUNCH(k_partial_reduce, 1, 256, 0, stream, part_b, P, kH, d_res_b);
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_mask_bits_scale(const float* gy, const uint32_t* bits, const float* post,
+                                    int64_t N, int64_t H, float* gs, void* stream) {
+  MGCN_REQUIRE(H == kH, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
+  if (N == 0) return MGCN_OK;
+  MGCN_REQUIRE(gy && bits && gs, MGCN_ERR_NULL);
+  MGCN_REQUIRE(aligned16(gy) && aligned16(gs), MGCN_ERR_ALIGN);
+  int64_t blocks = ceil_div(N * (kH / 4), 256);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  MGCN_LAUNCH(k_mask_bits_scale, (unsigned)blocks, 256, 0, stream, gy, bits, post, N, gs);
+  return MGCN_OK;
+}

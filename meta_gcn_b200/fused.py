@@ -72,8 +72,66 @@ class _ResidualGCNStack(torch.autograd.Function):
         return (g if need_x else None, None, None, None, None, None, *grads)
 
 
+class _ResidualGCNStack32(torch.autograd.Function):
+    """hidden width 32, no node-model bias: one fused launch per layer forward (aggregation + both
+    dense products on the tensor pipe, csrc/gcn_layer.cu), transposed aggregation + one row-local
+    launch per layer backward.  Saved per layer: the layer input x_n and one mask word per row."""
+
+    @staticmethod
+    def forward(ctx, x, graph, pre, post, last_relu, *params):
+        L = len(params) // 3
+        layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
+        fwd = graph.fwd
+        x0 = x.contiguous()
+        xs, hmasks = [x0], []
+        m = ops.linear_impl(x0, layers[0][0], False, row_scale=pre)          # messages of layer 0
+        resid0 = ops.linear_impl(x0, layers[0][1], True, layers[0][2])       # x0 R0^T + r0
+        for n in range(L):
+            w_next = layers[n + 1][0] if n + 1 < L else None
+            act_out = 1 if (last_relu or n < L - 1) else 0
+            xn, m, hm = ops.gcn_layer_fwd_impl(
+                fwd, m, xs[n] if n > 0 else None, resid0 if n == 0 else None,
+                layers[n][1], layers[n][2], w_next, None, pre, post, act_out)
+            xs.append(xn)
+            hmasks.append(hm)
+        ctx.graph, ctx.cfg = graph, (L, last_relu)
+        ctx.pre, ctx.post = pre, post
+        ctx.save_for_backward(*xs, *hmasks, *params)
+        return xs[-1]
+
+    @staticmethod
+    def backward(ctx, g):
+        L, last_relu = ctx.cfg
+        saved = ctx.saved_tensors
+        xs, hmasks, params = saved[:L + 1], saved[L + 1:2 * L + 1], saved[2 * L + 1:]
+        layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
+        pre, post, bwd = ctx.pre, ctx.post, ctx.graph.bwd
+        grads = [None] * len(params)
+        gy = g.contiguous()
+        if last_relu:
+            gy = ops.relu_backward_impl(gy, xs[L])
+        gs = ops.mask_bits_scale_impl(gy, hmasks[L - 1], post)
+        for n in range(L - 1, 0, -1):
+            dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
+            gy_prev, gs_prev, dw, drw, drb = ops.gcn_layer_bwd_impl(
+                dxw, gy, xs[n], layers[n][0], layers[n][1], hmasks[n - 1], post, True)
+            grads[3 * n], grads[3 * n + 1], grads[3 * n + 2] = dw, drw, drb
+            gy, gs = gy_prev, gs_prev
+        dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
+        grads[0] = ops.linear_wgrad_impl(xs[0], dxw, False, False)[0]
+        grads[1], grads[2] = ops.linear_wgrad_impl(xs[0], gy, True, True)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.linear_impl(gy, layers[0][1], False)
+            gx = ops.linear_impl(dxw, layers[0][0], True, add=gx)
+        return (gx, None, None, None, None, *grads)
+
+
 def residual_gcn_stack(x, graph, pre, post, layer_params, has_bias, last_relu=False):
     """layer_params: per layer (weight_node [Hin,H], [bias [H]], residual.weight [H,Hin],
     residual.bias [H]).  pre/post: per-source / per-target degree factors (either may be None)."""
     flat = [p for lp in layer_params for p in lp]
+    widths = {lp[0].size(1) for lp in layer_params} | {lp[0].size(0) for lp in layer_params[1:]}
+    if not has_bias and widths == {32}:
+        return _ResidualGCNStack32.apply(x, graph, pre, post, last_relu, *flat)
     return _ResidualGCNStack.apply(x, graph, pre, post, has_bias, last_relu, *flat)

@@ -268,6 +268,69 @@ def masked_scale_impl(g, m1=None, m2=None, row_scale=None):
     return out
 
 
+def gcn_layer_fwd_impl(csr, m, x, resid, res_w, res_b, w_next, bias, pre, post, act_out):
+    """one fused forward layer at hidden 32 (mgcn_gcn_layer_fwd): returns (x_next, m_next | None,
+    hmask int32[N])"""
+    _need_cuda(csr.rowptr, m, x, resid, res_w, res_b, w_next, bias, pre, post)
+    m = _f32c(m, "m")
+    x = _f32c(x, "x")
+    resid = _f32c(resid, "resid")
+    res_w = _f32c(res_w, "res_w")
+    res_b = _f32c(res_b, "res_b")
+    w_next = _f32c(w_next, "w_next")
+    bias = _f32c(bias, "bias")
+    pre = _f32c(pre, "pre")
+    post = _f32c(post, "post")
+    n_rows, H = csr.n_rows, m.size(1)
+    dev = m.device
+    x_next = torch.empty(n_rows, H, dtype=torch.float32, device=dev)
+    m_next = torch.empty(n_rows, H, dtype=torch.float32, device=dev) if w_next is not None else None
+    hmask = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    args = (ctypes.byref(csr.struct()), _ptr(m), m.size(0), _ptr(x), _ptr(resid), _ptr(res_w), _ptr(res_b),
+            _ptr(w_next), _ptr(bias), _ptr(pre), _ptr(post), int(act_out), H, _ptr(x_next), _ptr(m_next),
+            _ptr(hmask))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_gcn_layer_fwd(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_gcn_layer_fwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return x_next, m_next, hmask
+
+
+def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True):
+    """row-local backward of one layer at hidden 32 (mgcn_gcn_layer_bwd): returns
+    (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b)"""
+    _need_cuda(dxw, gy, x, w, res_w, hmask_prev, post)
+    dxw = _f32c(dxw, "dxw")
+    gy = _f32c(gy, "gy")
+    x = _f32c(x, "x")
+    w = _f32c(w, "w")
+    res_w = _f32c(res_w, "res_w")
+    post = _f32c(post, "post")
+    N, H = x.shape
+    dev = x.device
+    gy_prev = torch.empty_like(x) if want_prev else None
+    gs_prev = torch.empty_like(x) if want_prev else None
+    dw = torch.empty(H, H, dtype=torch.float32, device=dev)
+    drw = torch.empty(H, H, dtype=torch.float32, device=dev)
+    drb = torch.empty(H, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    args = (_ptr(dxw), _ptr(gy), _ptr(x), _ptr(w), _ptr(res_w), _ptr(hmask_prev) if want_prev else None,
+            _ptr(post), N, H, _ptr(gy_prev), _ptr(gs_prev), _ptr(dw), _ptr(drw), _ptr(drb))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_gcn_layer_bwd(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_gcn_layer_bwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return gy_prev, gs_prev, dw, drw, drb
+
+
+def mask_bits_scale_impl(gy, bits, post):
+    """gs = post[:,None] * gy * bit(bits, column)   (H = 32)"""
+    _need_cuda(gy, bits, post)
+    gy = _f32c(gy, "gy")
+    post = _f32c(post, "post")
+    out = torch.empty_like(gy)
+    _lib.check(_lib.load().mgcn_mask_bits_scale(_ptr(gy), _ptr(bits), _ptr(post), gy.size(0), gy.size(1),
+                                                _ptr(out), _stream()))
+    return out
+
+
 def cross_entropy_fwd_impl(logits, target, mean):
     _need_cuda(logits, target)
     logits = _f32c(logits, "logits")

@@ -130,7 +130,7 @@ def test_masked_scale_and_masked_operands():
     a, m1, m2 = (torch.randn(N, H, generator=g) for _ in range(3))
     rs = torch.rand(N, generator=g)
     out = ops.masked_scale_impl(a.to(DEV), m1.to(DEV), m2.to(DEV), rs.to(DEV))
-    ref = rs.view(-1, 1) * (a * (m1 > 0) * (m2 > 0))
+    ref = rs.view(-1, 1) * torch.where((m1 > 0) & (m2 > 0), a, torch.zeros(()))
     assert_bitexact(out, ref, "masked_scale")
     w = torch.randn(H, H, generator=g) / H ** 0.5
     y = ops.linear_impl(a.to(DEV), w.to(DEV), False, xmask=m1.to(DEV), row_scale=rs.to(DEV))

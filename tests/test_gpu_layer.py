@@ -1,0 +1,124 @@
+"""Fused residual-GCN layer kernels (csrc/gcn_layer.cu) against an fp64 dense restatement of
+gcn_model.py:89-106 / gcn_base_models.py:199-243 on the same seeded inputs: forward outputs, mask
+words, and every backward product; ragged shapes (N not a multiple of the 16-row tile), empty rows,
+hub rows (longer than the hub threshold) and isolated nodes included."""
+import numpy as np
+import pytest
+import torch
+
+from meta_gcn_b200 import ops
+from meta_gcn_b200.graph import GraphStructure
+from util import assert_bitexact, assert_parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+H = 32
+
+
+def rand_graph(n, e, seed, hubs=2):
+    g = np.random.default_rng(seed)
+    src = g.integers(0, n, e)
+    dst = g.integers(0, n, e)
+    # a few hub targets / hub sources, and nodes n-3.. left isolated
+    for k in range(hubs):
+        dst[g.integers(0, e, 300)] = k
+        src[g.integers(0, e, 200)] = k + 5
+    keep = (src < n - 3) & (dst < n - 3)
+    ei = np.stack([src[keep], dst[keep]]).astype(np.int64)
+    return torch.from_numpy(ei)
+
+
+def dense_adj(ei, n):
+    """A[i, j] = number of edges j -> i (row = target), fp64"""
+    a = torch.zeros(n, n, dtype=torch.float64)
+    a.index_put_((ei[1], ei[0]), torch.ones(ei.size(1), dtype=torch.float64), accumulate=True)
+    return a
+
+
+@pytest.mark.parametrize("n,e,act_out,with_next,resid_mode", [
+    (1000, 9000, 1, True, False),
+    (1003, 12000, 0, False, False),
+    (517, 3000, 1, True, True),
+    (16, 40, 1, True, False),
+    (5, 0, 1, True, False),
+])
+def test_layer_fwd(n, e, act_out, with_next, resid_mode):
+    ei = rand_graph(n, e, seed=n) if e else torch.zeros(2, 0, dtype=torch.int64)
+    gen = torch.Generator().manual_seed(n + 1)
+    m = torch.randn(n, H, generator=gen)
+    x = torch.randn(n, H, generator=gen)
+    res_w = torch.randn(H, H, generator=gen) / H ** 0.5
+    res_b = torch.randn(H, generator=gen)
+    w_next = torch.randn(H, H, generator=gen) / H ** 0.5
+    pre = torch.rand(n, generator=gen) + 0.1
+    post = torch.rand(n, generator=gen) + 0.1
+    gs = GraphStructure(ei.to(DEV), n, hub_threshold=64)
+    d = lambda t: t.to(DEV)
+    resid = (x.double() @ res_w.double().t() + res_b.double()).float()
+    xn, mn, hm = ops.gcn_layer_fwd_impl(
+        gs.fwd, d(m), None if resid_mode else d(x), d(resid) if resid_mode else None, d(res_w), d(res_b),
+        d(w_next) if with_next else None, None, d(pre), d(post), act_out)
+    a = dense_adj(ei, n)
+    h = torch.relu(post.double().view(-1, 1) * (a @ m.double()))
+    y = h + (resid.double() if resid_mode else x.double() @ res_w.double().t() + res_b.double())
+    x_ref = torch.relu(y) if act_out else y
+    assert_parity(xn, x_ref, "x_next")
+    if with_next:
+        assert_parity(mn, pre.double().view(-1, 1) * (x_ref @ w_next.double()), "m_next")
+    else:
+        assert mn is None
+    # mask words: bit c = h[:, c] > 0; compare where h is not within rounding of 0
+    bits = hm.cpu().numpy().astype(np.uint32)
+    got = ((bits[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(bool)
+    hn = h.numpy()
+    sure = np.abs(hn) > 1e-6 * max(1.0, np.abs(hn).max())
+    assert (got[sure] == (hn[sure] > 0)).all()
+    assert not got[hn == 0].any()
+
+
+def test_layer_fwd_is_deterministic_and_order_exact():
+    """row sums run in edge_index order: with unit factors and no dense part the h bits equal a
+    sequential fp32 scatter_add (the reference's CPU order) for rows within the hub threshold"""
+    n, e = 800, 6000
+    ei = rand_graph(n, e, seed=3, hubs=0)
+    gen = torch.Generator().manual_seed(0)
+    m = torch.randn(n, H, generator=gen)
+    zeros = torch.zeros(n, H)
+    gs = GraphStructure(ei.to(DEV), n, hub_threshold=1 << 20)
+    outs = []
+    for _ in range(2):
+        xn, _, _ = ops.gcn_layer_fwd_impl(gs.fwd, m.to(DEV), None, zeros.to(DEV), None, None, None, None,
+                                          None, None, 0)
+        outs.append(xn.cpu())
+    assert_bitexact(outs[0], outs[1], "run-to-run")
+    ref = torch.zeros(n, H).scatter_add_(0, ei[1].view(-1, 1).expand(-1, H), m[ei[0]])
+    assert_bitexact(outs[0], torch.relu(ref), "edge-order sum")
+
+
+@pytest.mark.parametrize("n,want_prev", [(1000, True), (1003, True), (131, False), (7, True)])
+def test_layer_bwd(n, want_prev):
+    gen = torch.Generator().manual_seed(n)
+    dxw = torch.randn(n, H, generator=gen)
+    gy = torch.randn(n, H, generator=gen)
+    x = torch.randn(n, H, generator=gen)
+    w = torch.randn(H, H, generator=gen) / H ** 0.5
+    res_w = torch.randn(H, H, generator=gen) / H ** 0.5
+    post = torch.rand(n, generator=gen) + 0.1
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), generator=gen, dtype=torch.int64).to(torch.int32)
+    d = lambda t: t.to(DEV)
+    gyp, gsp, dw, drw, drb = ops.gcn_layer_bwd_impl(d(dxw), d(gy), d(x), d(w), d(res_w), d(bits), d(post),
+                                                    want_prev)
+    D = lambda t: t.double()
+    assert_parity(dw, D(x).t() @ D(dxw), "dW")
+    assert_parity(drw, D(gy).t() @ D(x), "dR")
+    assert_parity(drb, D(gy).sum(0), "dr")
+    if not want_prev:
+        assert gyp is None and gsp is None
+        return
+    G = D(dxw) @ D(w).t() + D(gy) @ D(res_w)
+    gy_ref = G * (x > 0)
+    assert_parity(gyp, gy_ref, "gy_prev")
+    b = ((bits.numpy().astype(np.uint32)[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(np.float64)
+    assert_parity(gsp, D(post).view(-1, 1) * gy_ref * torch.from_numpy(b), "gs_prev")
+    gs2 = ops.mask_bits_scale_impl(d(gy), d(bits), d(post))
+    assert_bitexact(gs2, post.view(-1, 1) * torch.where(torch.from_numpy(b > 0), gy, torch.zeros(())), "mask_bits_scale")
