@@ -71,8 +71,13 @@ typedef struct mgcn_csr {
   const int32_t* tasks;     /* [(N + seg_cap) * 4] work descriptors {row, beg, end, partial_slot}:
                                entries [0,N) are the rows in `order` (row = -1 for a hub row, which
                                is covered by its segments), entries [N, N+seg_count) are the hub
-                               segments (partial_slot = segment index + 1); 16-byte aligned; may be
-                               NULL (then mgcn_aggregate_prescaled is unavailable)              */
+                               segments (partial_slot = segment index + 1); beg/end index nbr_w;
+                               16-byte aligned; may be NULL (then the task-driven kernels —
+                               mgcn_aggregate_prescaled, mgcn_gcn_layer_fwd — are unavailable)  */
+  const int32_t* nbr_w;     /* [nnz_cap] nbr in WORK order: the entries of task s are
+                               nbr_w[tasks[s].beg .. tasks[s].end) in row order, and task s+1 starts
+                               where task s ends, so a kernel walking the tasks reads the index
+                               stream sequentially; NULL iff tasks is NULL                      */
 } mgcn_csr_t;
 
 int mgcn_version(void);

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libmgcn.so")
+LIB_PATH = os.environ.get("MGCN_LIB") or os.path.join(_PKG, "lib", "libmgcn.so")   # MGCN_LIB: tuning variants
 
 c_i64 = ctypes.c_int64
 c_i32 = ctypes.c_int32
@@ -37,6 +37,7 @@ class MgcnCsr(ctypes.Structure):
         ("seg_beg", c_ptr),
         ("seg_count", c_ptr),
         ("tasks", c_ptr),
+        ("nbr_w", c_ptr),
     ]
 
 

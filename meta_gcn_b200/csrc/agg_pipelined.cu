@@ -45,7 +45,7 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
 
 template <int LPR>
 __device__ __forceinline__ void finish_row(const PlainArgs& a, int64_t row, int len, int col,
-                                           float4 acc, float ps, float4 res) {
+                                           float4 acc, float ps, float4 res, uint64_t pol_stream) {
   constexpr int H = LPR * 4;
   if (a.post_scale) {
     acc.x = __fmul_rn(acc.x, ps); acc.y = __fmul_rn(acc.y, ps);
@@ -62,7 +62,7 @@ __device__ __forceinline__ void finish_row(const PlainArgs& a, int64_t row, int 
     acc.x = acc.x < 0.f ? 0.f : acc.x; acc.y = acc.y < 0.f ? 0.f : acc.y;
     acc.z = acc.z < 0.f ? 0.f : acc.z; acc.w = acc.w < 0.f ? 0.f : acc.w;
   }
-  *reinterpret_cast<float4*>(a.out + row * H + col) = acc;
+  st_f4_hint(a.out + row * H + col, acc, pol_stream);
 }
 
 template <int LPR>
@@ -86,9 +86,10 @@ __global__ void __launch_bounds__(256, 3) k_agg_plain(const PlainArgs a) {
     n_tasks += ns;
   }
   const int4 kNone = make_int4(-1, 0, 0, 0);
+  const uint64_t pol_stream = policy_evict_first();
 
-#define MGCN_LOAD_DESC(s) ((s) < n_tasks ? __ldg(a.tasks + (s)) : kNone)
-#define MGCN_LOAD_IDX(d) (((d).y + sub < (d).z) ? __ldg(a.nbr + (d).y + sub) : 0)
+#define MGCN_LOAD_DESC(s) ((s) < n_tasks ? ld_i4_hint(a.tasks + (s), pol_stream) : kNone)
+#define MGCN_LOAD_IDX(d) (((d).y + sub < (d).z) ? ld_i32_hint(a.nbr + (d).y + sub, pol_stream) : 0)
 #define MGCN_LOAD_PS(d) ((a.post_scale && (d).x >= 0 && (d).w == 0) ? __ldg(a.post_scale + (d).x) : 1.f)
 
   int4 d0 = MGCN_LOAD_DESC(gid);
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256, 3) k_agg_plain(const PlainArgs a) {
         const int cnt = min(LPR, end - e);
         const int e_next = e + LPR;
         int g_next = 0;
-        if (e_next + sub < end) g_next = __ldg(a.nbr + e_next + sub);  // next batch, before the gathers
+        if (e_next + sub < end) g_next = ld_i32_hint(a.nbr + e_next + sub, pol_stream);  // next batch, before the gathers
 #pragma unroll
         for (int t0 = 0; t0 < LPR; t0 += U) {
           if (t0 < cnt) {
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256, 3) k_agg_plain(const PlainArgs a) {
       if (d0.w != 0) {
         *reinterpret_cast<float4*>(a.partial + (int64_t)(d0.w - 1) * H + col) = acc;
       } else {
-        finish_row<LPR>(a, row, end - d0.y, col, acc, ps0, res);
+        finish_row<LPR>(a, row, end - d0.y, col, acc, ps0, res, pol_stream);
       }
     }
     d0 = d1; d1 = d2; d2 = d3;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256) k_agg_hub_combine(const PlainArgs a) {
     float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.residual) res = __ldg(reinterpret_cast<const float4*>(a.residual + row * H + col));
     const float ps = a.post_scale ? __ldg(a.post_scale + row) : 1.f;
-    finish_row<LPR>(a, row, len, col, tot, ps, res);
+    finish_row<LPR>(a, row, len, col, tot, ps, res, policy_evict_first());
   }
 }
 
@@ -224,13 +225,16 @@ extern "C" int mgcn_aggregate_prescaled(const mgcn_csr_t* g, const float* x, int
   MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
   if (g->n_rows == 0) return MGCN_OK;
   MGCN_REQUIRE(g->rowptr && g->tasks && out, MGCN_ERR_NULL);
-  MGCN_REQUIRE(g->nnz_cap == 0 || (g->nbr && x), MGCN_ERR_NULL);
+  MGCN_REQUIRE(g->nnz_cap == 0 || (g->nbr_w && x), MGCN_ERR_NULL);
   MGCN_REQUIRE(aligned16(g->tasks) && aligned16(x) && aligned16(out) && aligned16(partial) &&
                    (!bias || aligned16(bias)) && (!residual || aligned16(residual)),
                MGCN_ERR_ALIGN);
+  if (H == 32 && reduce == 0 && bias == nullptr && residual == nullptr &&
+      (reinterpret_cast<uintptr_t>(x) & 31u) == 0)
+    return launch_agg_flat32(g, x, post_scale, act, out, partial, hubs, stream);
   PlainArgs a{};
   a.tasks = reinterpret_cast<const int4*>(g->tasks);
-  a.nbr = g->nbr;
+  a.nbr = g->nbr_w;   // descriptors index the work-ordered stream
   a.rowptr = g->rowptr;
   a.x = x;
   a.post_scale = post_scale;

@@ -34,6 +34,55 @@ struct WorkspaceCarver {
   size_t bytes() const { return align_up(off, 256); }
 };
 
+// ---- L2 residency hints -------------------------------------------------------------------------
+// Measured (profiles/r1_layer_summary.md): with plain loads the aggregation kernels read 1.5x their
+// compulsory DRAM bytes — the index / descriptor / tile streams and the output stores push the
+// gathered feature rows (the only data with reuse) out of L2.  Streams are therefore tagged
+// evict-first and bypass L1; gathered rows keep the default policy.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int4 ld_i4_hint(const int4* p, uint64_t pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int ld_i32_hint(const int32_t* p, uint64_t pol) {
+  int r;
+  // allocates in L1: the batches of one row share sectors
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_f4_hint(float* p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, int src_bytes, uint64_t pol) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n"
+               :: "r"(d), "l"(gsrc), "r"(src_bytes), "l"(pol) : "memory");
+}
+#endif
+
+// H = 32 plain aggregation on the flat work-ordered gather (gcn_layer.cu)
+int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, int act, float* out,
+                      float* partial, bool hubs, void* stream);
+
 }  // namespace mgcn
 
 // Launch + count + error check.  Used inside functions returning int.

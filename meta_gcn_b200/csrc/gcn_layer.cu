@@ -46,10 +46,6 @@ __device__ __forceinline__ float4 f4_add2(float4 a, float4 b) {
   return r;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
 }
@@ -69,7 +65,7 @@ __device__ __forceinline__ void fill_plane(const float* __restrict__ w, int stri
 
 struct LayerFwdArgs {
   const int4* tasks;        // work descriptors (mgcn_csr_t::tasks)
-  const int32_t* nbr;
+  const int32_t* nbr_w;     // index stream in work order (mgcn_csr_t::nbr_w)
   const int32_t* seg_count;
   const int32_t* hub_rows;
   const int32_t* hub_seg0;
@@ -95,88 +91,165 @@ struct LayerFwdArgs {
   int hub_threshold;
 };
 
-// Sum rows m[nbr[k]] for k in [beg, end), in order, for the 4 columns of this lane.  The 8 lanes of
-// a group call this together; gi holds nbr[beg + sub] (the first index batch, fetched earlier).
-__device__ __forceinline__ float4 gather_sum(const float* __restrict__ m, const int32_t* __restrict__ nbr,
-                                             int beg, int end, int gi, int sub, int grp_lane0,
-                                             unsigned gmask, int col) {
-  constexpr int U = 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int e = beg;
-  while (true) {
-    const int cnt = min(8, end - e);
-    const int e_next = e + 8;
-    int g_next = 0;
-    if (e_next + sub < end) g_next = __ldg(nbr + e_next + sub);  // next batch, before the gathers
+// ---- row gather: 4 lanes x 256 bits per row ------------------------------------------------------
+// A lane group of 4 lanes owns a row, each lane 8 of the 32 columns (one sm_100 LDG.256 per gathered
+// row and lane), so a warp instruction fetches 8 rows.  Measured (scripts/ubench.cu, one-graph window,
+// 4 CTAs/SM): 16.8 TB/s against 11.4 TB/s for 8 lanes x LDG.128 — half the load / shuffle / address
+// instructions per gathered byte and twice the bytes in flight per warp.
+// The entries of a row are summed in row order (= edge_index order), one rounded add per entry, 4
+// gathers in flight per group; the index batch after next is fetched before the gathers are issued
+// (the index stream nbr_w is sequential in work order).
+#ifndef MGCN_GATHER_U
+#define MGCN_GATHER_U 4   // row gathers in flight per lane group
+#endif
+#ifndef MGCN_FWD_MINB
+#define MGCN_FWD_MINB 2   // resident CTAs per SM the forward kernel is compiled for
+#endif
+#ifndef MGCN_AGG_MINB
+#define MGCN_AGG_MINB 3
+#endif
+
+struct Row8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Row8 ld_row8(const float* p) {
+  Row8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]),
+                 "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void row8_add(Row8& acc, const Row8& b) {
+  // four packed f32x2 adds (sm_100 FADD2): same IEEE result per element as eight scalar adds
 #pragma unroll
-    for (int t0 = 0; t0 < 8; t0 += U) {
+  for (int q = 0; q < 8; q += 2) {
+    asm("{\n .reg .b64 a0, b0;\n mov.b64 a0, {%0, %1};\n mov.b64 b0, {%2, %3};\n"
+        " add.rn.f32x2 a0, a0, b0;\n mov.b64 {%0, %1}, a0;\n}\n"
+        : "+f"(acc.v[q]), "+f"(acc.v[q + 1])
+        : "f"(b.v[q]), "f"(b.v[q + 1]));
+  }
+}
+
+// Sum rows m[nbr_w[k]] for k in [beg, end), in order, for the 8 columns of this lane.  The 4 lanes of
+// a group call this together; gi holds nbr_w[beg + sub] and gi_n holds nbr_w[beg + 4 + sub].
+__device__ __forceinline__ Row8 gather_sum(const float* __restrict__ m, const int32_t* __restrict__ nbr_w,
+                                           int beg, int end, int gi, int gi_n, int sub, int grp_lane0,
+                                           unsigned gmask, int col, uint64_t pol) {
+  Row8 acc;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
+  constexpr int U = MGCN_GATHER_U;
+  int e = beg;
+  while (e < end) {
+    const int cnt = min(4, end - e);
+    int gi_nn = 0;
+    if (e + 8 + sub < end) gi_nn = ld_i32_hint(nbr_w + e + 8 + sub, pol);
+#pragma unroll
+    for (int t0 = 0; t0 < 4; t0 += U) {
       if (t0 < cnt) {
         int j[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) j[u] = __shfl_sync(gmask, gi, grp_lane0 + t0 + u);
-        float4 xv[U];
+        for (int u = 0; u < U; ++u) j[u] = __shfl_sync(gmask, gi, grp_lane0 + ((t0 + u) & 3));
+        Row8 xv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t0 + u < cnt) xv[u] = __ldg(reinterpret_cast<const float4*>(m + (int64_t)j[u] * kH + col));
+          if (t0 + u < cnt) xv[u] = ld_row8(m + (int64_t)j[u] * kH + col);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t0 + u < cnt) acc = f4_add2(acc, xv[u]);
+          if (t0 + u < cnt) row8_add(acc, xv[u]);
         }
       }
     }
-    if (e_next >= end) break;
-    e = e_next;
-    gi = g_next;
+    e += 4;
+    gi = gi_n;
+    gi_n = gi_nn;
   }
   return acc;
 }
 
+// Descriptors of a 16-task tile: lanes 0..15 load one each (empty task past `limit`).
+__device__ __forceinline__ int4 load_tile_desc(const int4* __restrict__ tasks, int64_t base, int64_t limit,
+                                               int lane, uint64_t pol) {
+  int4 d = make_int4(-1, 0, 0, 0);
+  if (lane < 16 && base + lane < limit) d = ld_i4_hint(tasks + base + lane, pol);
+  return d;
+}
+
 // h = relu(post * acc + bias) -> Hs row, mask word -> hmask[row]
-__device__ __forceinline__ void finish_h(const LayerFwdArgs& a, float4 acc, float post, int64_t row,
+__device__ __forceinline__ void finish_h(const LayerFwdArgs& a, Row8 acc, float post, int64_t row,
                                          float* __restrict__ hs_row, int sub, unsigned gmask, int col) {
   if (a.post) {
-    acc.x = __fmul_rn(acc.x, post); acc.y = __fmul_rn(acc.y, post);
-    acc.z = __fmul_rn(acc.z, post); acc.w = __fmul_rn(acc.w, post);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc.v[q] = __fmul_rn(acc.v[q], post);
   }
   if (a.bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col));
-    acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
-    acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc.v[q] = __fadd_rn(acc.v[q], __ldg(a.bias + col + q));
   }
-  acc.x = acc.x > 0.f ? acc.x : 0.f; acc.y = acc.y > 0.f ? acc.y : 0.f;
-  acc.z = acc.z > 0.f ? acc.z : 0.f; acc.w = acc.w > 0.f ? acc.w : 0.f;
-  *reinterpret_cast<float4*>(hs_row + col) = acc;
-  uint32_t bits = ((acc.x > 0.f ? 1u : 0u) | (acc.y > 0.f ? 2u : 0u) | (acc.z > 0.f ? 4u : 0u) |
-                   (acc.w > 0.f ? 8u : 0u)) << col;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    acc.v[q] = acc.v[q] > 0.f ? acc.v[q] : 0.f;
+    bits |= (acc.v[q] > 0.f ? 1u : 0u) << q;
+  }
+  *reinterpret_cast<float4*>(hs_row + col) = make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  *reinterpret_cast<float4*>(hs_row + col + 4) = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+  bits <<= col;
   bits |= __shfl_xor_sync(gmask, bits, 1);
   bits |= __shfl_xor_sync(gmask, bits, 2);
-  bits |= __shfl_xor_sync(gmask, bits, 4);
   if (sub == 0) a.hmask[row] = bits;
+}
+
+__device__ __forceinline__ void store_partial(float* __restrict__ partial, int slot, int col, const Row8& acc) {
+  float* p = partial + (int64_t)(slot - 1) * kH + col;
+  *reinterpret_cast<float4*>(p) = make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+}
+
+// partial rows of a hub's segments, added left to right
+__device__ __forceinline__ Row8 sum_partials(const float* __restrict__ partial, int s0, int ns, int col) {
+  Row8 tot;
+  const float* p = partial + (int64_t)s0 * kH + col;
+  float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+  tot.v[0] = lo.x; tot.v[1] = lo.y; tot.v[2] = lo.z; tot.v[3] = lo.w;
+  tot.v[4] = hi.x; tot.v[5] = hi.y; tot.v[6] = hi.z; tot.v[7] = hi.w;
+  for (int q = 1; q < ns; ++q) {
+    Row8 b;
+    p += kH;
+    lo = *reinterpret_cast<const float4*>(p);
+    hi = *reinterpret_cast<const float4*>(p + 4);
+    b.v[0] = lo.x; b.v[1] = lo.y; b.v[2] = lo.z; b.v[3] = lo.w;
+    b.v[4] = hi.x; b.v[5] = hi.y; b.v[6] = hi.z; b.v[7] = hi.w;
+    row8_add(tot, b);
+  }
+  return tot;
 }
 
 // residual operand rows (x, or the finished residual term) of a 16-row tile -> Xs, asynchronously
 __device__ __forceinline__ void stage_tile_async(const float* __restrict__ src, int myrow,
-                                                 float (*Xs)[kLda], int lane) {
+                                                 float (*Xs)[kLda], int lane, uint64_t pol) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = i * 32 + lane;
     const int r = c >> 3, q = c & 7;
     const int rid = __shfl_sync(0xffffffffu, myrow, r);
-    cp_async16(&Xs[r][4 * q], src + (int64_t)(rid >= 0 ? rid : 0) * kH + 4 * q, rid >= 0 ? 16 : 0);
+    cp_async16_hint(&Xs[r][4 * q], src + (int64_t)(rid >= 0 ? rid : 0) * kH + 4 * q, rid >= 0 ? 16 : 0, pol);
   }
 }
 
 __device__ __forceinline__ void store_tile_rows(float* __restrict__ dst, int myrow,
-                                                const float (*Ts)[kLda], int lane) {
+                                                const float (*Ts)[kLda], int lane, uint64_t pol) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = i * 32 + lane;
     const int r = c >> 3, q = c & 7;
     const int rid = __shfl_sync(0xffffffffu, myrow, r);
     if (rid >= 0)
-      *reinterpret_cast<float4*>(dst + (int64_t)rid * kH + 4 * q) =
-          *reinterpret_cast<const float4*>(&Ts[r][4 * q]);
+      st_f4_hint(dst + (int64_t)rid * kH + 4 * q, *reinterpret_cast<const float4*>(&Ts[r][4 * q]), pol);
   }
 }
 
@@ -184,7 +257,7 @@ __device__ __forceinline__ void store_tile_rows(float* __restrict__ dst, int myr
 // tile's row ids (myrow, -1 = no row) and per-source factors (mypre).
 __device__ __forceinline__ void fwd_tile_tail(const LayerFwdArgs& a, float (*Xs)[kLda],
                                               float (*Hs)[kLda], const float* __restrict__ planes,
-                                              int myrow, float mypre, int lane) {
+                                              int myrow, float mypre, int lane, uint64_t pol) {
   const int g = lane >> 2, t = lane & 3;
   float acc[kH / 8][4];
   if (a.x) {
@@ -220,7 +293,7 @@ __device__ __forceinline__ void fwd_tile_tail(const LayerFwdArgs& a, float (*Xs)
     }
   }
   __syncwarp();
-  store_tile_rows(a.x_next, myrow, Xs, lane);
+  store_tile_rows(a.x_next, myrow, Xs, lane, pol);
   if (a.w_next) {
     warp_gemm16<kH, kH>(&Xs[0][0], kLda, planes + 2 * kPlane, planes + 3 * kPlane, kLdb, acc, lane);
     const float p0 = __shfl_sync(0xffffffffu, mypre, g);
@@ -232,7 +305,7 @@ __device__ __forceinline__ void fwd_tile_tail(const LayerFwdArgs& a, float (*Xs)
       *reinterpret_cast<float2*>(&Hs[g + 8][c]) = make_float2(acc[j][2] * p1, acc[j][3] * p1);
     }
     __syncwarp();
-    store_tile_rows(a.m_next, myrow, Hs, lane);
+    store_tile_rows(a.m_next, myrow, Hs, lane, pol);
   }
   __syncwarp();  // tile buffers are free for the next tile
 }
@@ -245,7 +318,7 @@ __device__ __forceinline__ void fwd_fill_planes(const LayerFwdArgs& a, float* pl
   if (a.w_next) fill_plane(a.w_next, kH, 1, planes + 2 * kPlane, planes + 3 * kPlane, tid, nthreads);  // W[k][c]
 }
 
-__global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd(const LayerFwdArgs a) {
+__global__ void __launch_bounds__(kFwdWarps * 32, MGCN_FWD_MINB) k_layer_fwd(const LayerFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* planes = smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -254,71 +327,58 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd(const LayerFwdA
   fwd_fill_planes(a, planes, tid, kFwdWarps * 32);
   __syncthreads();
 
-  const int sub = lane & 7, grp = lane >> 3, grp_lane0 = grp * 8;
-  const unsigned gmask = 0xffu << grp_lane0;
-  const int col = sub * 4;
-  const int64_t n_row_tiles = (a.n_rows + 15) >> 4;
+  const int sub = lane & 3, grp = lane >> 2, grp_lane0 = grp * 4;
+  const unsigned gmask = 0xfu << grp_lane0;
+  const int col = sub * 8;
   int64_t nseg = 0;
   if (a.seg_count) {
     nseg = *a.seg_count;
     if (nseg > a.seg_cap) nseg = a.seg_cap;
   }
-  const int64_t n_tiles = n_row_tiles + ((nseg + 15) >> 4);
+  const int64_t limit = a.n_rows + nseg;          // tasks in work order: rows and hub segments mixed
+  const int64_t n_tiles = (limit + 15) >> 4;
   const int64_t stride = (int64_t)gridDim.x * kFwdWarps;
-  const int4 kNone = make_int4(-1, 0, 0, 0);
-
-  auto load_desc = [&](int64_t tl) -> int4 {
-    int4 d = kNone;
-    if (tl < n_tiles && lane < 16) {
-      if (tl < n_row_tiles) {
-        const int64_t idx = tl * 16 + lane;
-        if (idx < a.n_rows) d = __ldg(a.tasks + idx);
-      } else {
-        const int64_t s = (tl - n_row_tiles) * 16 + lane;
-        if (s < nseg) d = __ldg(a.tasks + a.n_rows + s);
-      }
-    }
-    return d;
-  };
+  const uint64_t pol = policy_evict_first();
 
   int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp;
-  int4 dn = load_desc(tile);
+  int4 dn = make_int4(-1, 0, 0, 0);
+  if (tile < n_tiles) dn = load_tile_desc(a.tasks, tile * 16, limit, lane, pol);
   for (; tile < n_tiles; tile += stride) {
     const int4 d = dn;
-    dn = load_desc(tile + stride);
-    const bool row_tile = tile < n_row_tiles;
-    const int myrow = d.x;
+    if (tile + stride < n_tiles) dn = load_tile_desc(a.tasks, (tile + stride) * 16, limit, lane, pol);
+    const int myrow = (d.x >= 0 && d.w == 0) ? d.x : -1;   // rows this tile finishes (lanes 0..15)
     float mypost = 1.f, mypre = 1.f;
-    if (row_tile && myrow >= 0) {
+    if (myrow >= 0) {
       if (a.post) mypost = __ldg(a.post + myrow);
       if (a.pre && a.w_next) mypre = __ldg(a.pre + myrow);
     }
-    int beg[4], end[4], gi[4];
+    // pass p: group g sums task 8p + g; first two index batches of both passes are fetched up front
+    int beg[2], end[2], gi[2], gin[2];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      beg[p] = __shfl_sync(0xffffffffu, d.y, 4 * p + grp);
-      end[p] = __shfl_sync(0xffffffffu, d.z, 4 * p + grp);
-      gi[p] = (beg[p] + sub < end[p]) ? __ldg(a.nbr + beg[p] + sub) : 0;
+    for (int p = 0; p < 2; ++p) {
+      beg[p] = __shfl_sync(0xffffffffu, d.y, 8 * p + grp);
+      end[p] = __shfl_sync(0xffffffffu, d.z, 8 * p + grp);
+      gi[p] = (beg[p] + sub < end[p]) ? ld_i32_hint(a.nbr_w + beg[p] + sub, pol) : 0;
+      gin[p] = (beg[p] + 4 + sub < end[p]) ? ld_i32_hint(a.nbr_w + beg[p] + 4 + sub, pol) : 0;
     }
-    if (row_tile) stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane);
+    stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane, pol);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int rowp = __shfl_sync(0xffffffffu, myrow, 4 * p + grp);
-      const int slot = __shfl_sync(0xffffffffu, d.w, 4 * p + grp);
-      const float postp = __shfl_sync(0xffffffffu, mypost, 4 * p + grp);
+    for (int p = 0; p < 2; ++p) {
+      const int rowp = __shfl_sync(0xffffffffu, d.x, 8 * p + grp);
+      const int slot = __shfl_sync(0xffffffffu, d.w, 8 * p + grp);
+      const float postp = __shfl_sync(0xffffffffu, mypost, 8 * p + grp);
       if (rowp >= 0) {
-        const float4 acc = gather_sum(a.m, a.nbr, beg[p], end[p], gi[p], sub, grp_lane0, gmask, col);
+        const Row8 acc = gather_sum(a.m, a.nbr_w, beg[p], end[p], gi[p], gin[p], sub, grp_lane0, gmask, col, pol);
         if (slot != 0) {
-          *reinterpret_cast<float4*>(a.partial + (int64_t)(slot - 1) * kH + col) = acc;
+          store_partial(a.partial, slot, col, acc);
         } else {
-          finish_h(a, acc, postp, rowp, &Hs[4 * p + grp][0], sub, gmask, col);
+          finish_h(a, acc, postp, rowp, &Hs[8 * p + grp][0], sub, gmask, col);
         }
       }
     }
-    if (!row_tile) continue;
     cp_async_wait_all();
     __syncwarp();
-    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane);
+    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane, pol);
   }
 }
 
@@ -335,9 +395,10 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd_hubs(const Laye
   if ((int64_t)blockIdx.x * kFwdWarps >= n_tiles) return;
   fwd_fill_planes(a, planes, tid, kFwdWarps * 32);
   __syncthreads();
-  const int sub = lane & 7, grp = lane >> 3, grp_lane0 = grp * 8;
-  const unsigned gmask = 0xffu << grp_lane0;
-  const int col = sub * 4;
+  const int sub = lane & 3, grp = lane >> 2, grp_lane0 = grp * 4;
+  const unsigned gmask = 0xfu << grp_lane0;
+  const int col = sub * 8;
+  const uint64_t pol = policy_evict_first();
   for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < n_tiles;
        tile += (int64_t)gridDim.x * kFwdWarps) {
     int myrow = -1, myseg0 = 0, mynseg = 0;
@@ -351,24 +412,157 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd_hubs(const Laye
       if (a.post) mypost = __ldg(a.post + myrow);
       if (a.pre && a.w_next) mypre = __ldg(a.pre + myrow);
     }
-    stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane);
+    stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane, pol);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int rowp = __shfl_sync(0xffffffffu, myrow, 4 * p + grp);
-      const int s0 = __shfl_sync(0xffffffffu, myseg0, 4 * p + grp);
-      const int ns = __shfl_sync(0xffffffffu, mynseg, 4 * p + grp);
-      const float postp = __shfl_sync(0xffffffffu, mypost, 4 * p + grp);
+    for (int p = 0; p < 2; ++p) {
+      const int rowp = __shfl_sync(0xffffffffu, myrow, 8 * p + grp);
+      const int s0 = __shfl_sync(0xffffffffu, myseg0, 8 * p + grp);
+      const int ns = __shfl_sync(0xffffffffu, mynseg, 8 * p + grp);
+      const float postp = __shfl_sync(0xffffffffu, mypost, 8 * p + grp);
       if (rowp >= 0) {
-        float4 tot = *reinterpret_cast<const float4*>(a.partial + (int64_t)s0 * kH + col);
-        for (int q = 1; q < ns; ++q)
-          tot = f4_add2(tot, *reinterpret_cast<const float4*>(a.partial + (int64_t)(s0 + q) * kH + col));
-        finish_h(a, tot, postp, rowp, &Hs[4 * p + grp][0], sub, gmask, col);
+        Row8 tot = sum_partials(a.partial, s0, ns, col);
+        finish_h(a, tot, postp, rowp, &Hs[8 * p + grp][0], sub, gmask, col);
       }
     }
     cp_async_wait_all();
     __syncwarp();
-    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane);
+    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane, pol);
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// plain aggregation on the same flat gather (the transposed pass of the backward):
+//   out_i = act( post_i * sum_k x[nbr_k] )
+// -------------------------------------------------------------------------------------------------
+struct AggFlatArgs {
+  const int4* tasks;
+  const int32_t* nbr_w;
+  const int32_t* seg_count;
+  const int32_t* hub_rows;
+  const int32_t* hub_seg0;
+  const int32_t* hub_count;
+  const int32_t* rowptr;
+  const float* x;
+  const float* post;
+  float* out;
+  float* partial;
+  int64_t n_rows;
+  int64_t seg_cap;
+  int64_t hub_cap;
+  int act;
+  int hub_threshold;
+};
+
+__device__ __forceinline__ void agg_finish_row(const AggFlatArgs& a, Row8 acc, float ps, int64_t row,
+                                               int col, uint64_t pol) {
+  if (a.post) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc.v[q] = __fmul_rn(acc.v[q], ps);
+  }
+  if (a.act == 1) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc.v[q] = acc.v[q] > 0.f ? acc.v[q] : 0.f;
+  }
+  float* o = a.out + row * kH + col;
+  st_f4_hint(o, make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]), pol);
+  st_f4_hint(o + 4, make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]), pol);
+}
+
+__global__ void __launch_bounds__(256, MGCN_AGG_MINB) k_agg_flat(const AggFlatArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 3, grp = lane >> 2, grp_lane0 = grp * 4;
+  const unsigned gmask = 0xfu << grp_lane0;
+  const int col = sub * 8;
+  int64_t nseg = 0;
+  if (a.seg_count) {
+    nseg = *a.seg_count;
+    if (nseg > a.seg_cap) nseg = a.seg_cap;
+  }
+  const int64_t limit = a.n_rows + nseg;
+  const int64_t n_tiles = (limit + 15) >> 4;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  const uint64_t pol = policy_evict_first();
+  int64_t tile = (int64_t)blockIdx.x * 8 + warp;
+  int4 dn = make_int4(-1, 0, 0, 0);
+  if (tile < n_tiles) dn = load_tile_desc(a.tasks, tile * 16, limit, lane, pol);
+  for (; tile < n_tiles; tile += stride) {
+    const int4 d = dn;
+    if (tile + stride < n_tiles) dn = load_tile_desc(a.tasks, (tile + stride) * 16, limit, lane, pol);
+    float mypost = 1.f;
+    if (a.post && d.x >= 0 && d.w == 0) mypost = __ldg(a.post + d.x);
+    int beg[2], end[2], gi[2], gin[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      beg[p] = __shfl_sync(0xffffffffu, d.y, 8 * p + grp);
+      end[p] = __shfl_sync(0xffffffffu, d.z, 8 * p + grp);
+      gi[p] = (beg[p] + sub < end[p]) ? ld_i32_hint(a.nbr_w + beg[p] + sub, pol) : 0;
+      gin[p] = (beg[p] + 4 + sub < end[p]) ? ld_i32_hint(a.nbr_w + beg[p] + 4 + sub, pol) : 0;
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int rowp = __shfl_sync(0xffffffffu, d.x, 8 * p + grp);
+      const int slot = __shfl_sync(0xffffffffu, d.w, 8 * p + grp);
+      const float postp = __shfl_sync(0xffffffffu, mypost, 8 * p + grp);
+      if (rowp >= 0) {
+        const Row8 acc = gather_sum(a.x, a.nbr_w, beg[p], end[p], gi[p], gin[p], sub, grp_lane0, gmask, col, pol);
+        if (slot != 0) {
+          store_partial(a.partial, slot, col, acc);
+        } else {
+          agg_finish_row(a, acc, postp, rowp, col, pol);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_agg_flat_hubs(const AggFlatArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 3, grp = lane >> 2;
+  const int col = sub * 8;
+  const int64_t G = (int64_t)gridDim.x * 64;
+  int64_t nh = *a.hub_count;
+  if (nh > a.hub_cap) nh = a.hub_cap;
+  const uint64_t pol = policy_evict_first();
+  for (int64_t k = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 8 + grp; k < nh; k += G) {
+    const int64_t row = __ldg(a.hub_rows + k);
+    const int s0 = __ldg(a.hub_seg0 + k);
+    const int len = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+    const int nseg = (len + a.hub_threshold - 1) / a.hub_threshold;
+    const Row8 tot = sum_partials(a.partial, s0, nseg, col);
+    agg_finish_row(a, tot, a.post ? __ldg(a.post + row) : 1.f, row, col, pol);
+  }
+}
+
+// called by mgcn_aggregate_prescaled (agg_pipelined.cu) for H = 32 without bias / residual / mean
+int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, int act, float* out,
+                      float* partial, bool hubs, void* stream) {
+  AggFlatArgs a{};
+  a.tasks = reinterpret_cast<const int4*>(g->tasks);
+  a.nbr_w = g->nbr_w;
+  a.seg_count = hubs ? g->seg_count : nullptr;
+  a.hub_rows = g->hub_rows;
+  a.hub_seg0 = g->hub_seg0;
+  a.hub_count = g->hub_count;
+  a.rowptr = g->rowptr;
+  a.x = x;
+  a.post = post;
+  a.out = out;
+  a.partial = partial;
+  a.n_rows = g->n_rows;
+  a.seg_cap = hubs ? g->seg_cap : 0;
+  a.hub_cap = hubs ? g->hub_cap : 0;
+  a.act = act;
+  a.hub_threshold = g->hub_threshold;
+  const int64_t max_tiles = ceil_div(g->n_rows + a.seg_cap, 16);
+  int64_t blocks = ceil_div(max_tiles, 8);
+  if (blocks > (int64_t)kNumSMs * MGCN_AGG_MINB) blocks = (int64_t)kNumSMs * MGCN_AGG_MINB;
+  MGCN_LAUNCH(k_agg_flat, (unsigned)blocks, 256, 0, stream, a);
+  if (hubs) {
+    int64_t hb = ceil_div(a.hub_cap, 64);
+    if (hb > (int64_t)kNumSMs * 2) hb = (int64_t)kNumSMs * 2;
+    MGCN_LAUNCH(k_agg_flat_hubs, (unsigned)hb, 256, 0, stream, a);
+  }
+  return MGCN_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -397,26 +591,25 @@ constexpr int kBwdSmemFloats = 4 * kPlane + kBwdRows * (2 * kLda + kLdx);
 
 template <int LD>
 __device__ __forceinline__ void stage_rows_async(const float* __restrict__ src, int64_t row0, int64_t N,
-                                                 float (*dst)[LD], int tid) {
+                                                 float (*dst)[LD], int tid, uint64_t pol) {
 #pragma unroll
   for (int i = 0; i < kBwdRows * 8 / (kBwdWarps * 32); ++i) {
     const int c = i * (kBwdWarps * 32) + tid;
     const int r = c >> 3, q = c & 7;
     const int64_t gr = row0 + r;
-    cp_async16(&dst[r][4 * q], src + (gr < N ? gr : 0) * kH + 4 * q, gr < N ? 16 : 0);
+    cp_async16_hint(&dst[r][4 * q], src + (gr < N ? gr : 0) * kH + 4 * q, gr < N ? 16 : 0, pol);
   }
 }
 
 // 16 rows of a tile -> global, 128 bytes per row, 4 rows per instruction
 __device__ __forceinline__ void store_rows16(float* __restrict__ dst, int64_t row0, int64_t N,
-                                             const float (*src)[kLda], int lane) {
+                                             const float (*src)[kLda], int lane, uint64_t pol) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = i * 32 + lane;
     const int r = c >> 3, q = c & 7;
     const int64_t gr = row0 + r;
-    if (gr < N)
-      *reinterpret_cast<float4*>(dst + gr * kH + 4 * q) = *reinterpret_cast<const float4*>(&src[r][4 * q]);
+    if (gr < N) st_f4_hint(dst + gr * kH + 4 * q, *reinterpret_cast<const float4*>(&src[r][4 * q]), pol);
   }
 }
 
@@ -442,13 +635,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) k_layer_bwd(const LayerBwdA
     for (int q = 0; q < 4; ++q) acc_blk[j][q] = 0.f;
   float acc_b = 0.f;
   const bool want_prev = a.gy_prev != nullptr;
+  const uint64_t pol = policy_evict_first();
   const int64_t ntiles = (a.n_rows + kBwdRows - 1) / kBwdRows;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * kBwdRows;
     __syncthreads();  // previous tile fully consumed (also orders the plane fill)
-    stage_rows_async<kLda>(a.dxw, row0, a.n_rows, Dw, tid);
-    stage_rows_async<kLda>(a.gy, row0, a.n_rows, Gy, tid);
-    stage_rows_async<kLdx>(a.x, row0, a.n_rows, Xs, tid);
+    stage_rows_async<kLda>(a.dxw, row0, a.n_rows, Dw, tid, pol);
+    stage_rows_async<kLda>(a.gy, row0, a.n_rows, Gy, tid, pol);
+    stage_rows_async<kLdx>(a.x, row0, a.n_rows, Xs, tid, pol);
     uint32_t mybits = 0;
     float mypost = 1.f;
     const int64_t myrow = row0 + warp * 16 + lane;
@@ -524,8 +718,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) k_layer_bwd(const LayerBwdA
         }
       }
       __syncwarp();
-      store_rows16(a.gy_prev, row0 + warp * 16, a.n_rows, Dt, lane);
-      store_rows16(a.gs_prev, row0 + warp * 16, a.n_rows, Gt, lane);
+      store_rows16(a.gy_prev, row0 + warp * 16, a.n_rows, Dt, lane, pol);
+      store_rows16(a.gs_prev, row0 + warp * 16, a.n_rows, Gt, lane, pol);
     }
   }
   // this warp's 16x16 block of dW (row = input j, col = output c) or dR (row = output c, col = input j)
@@ -620,14 +814,15 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
   MGCN_REQUIRE((x != nullptr) != (resid != nullptr), MGCN_ERR_NULL);   // exactly one residual form
   MGCN_REQUIRE(!x || res_w, MGCN_ERR_NULL);
   MGCN_REQUIRE(!w_next || m_next, MGCN_ERR_NULL);
-  MGCN_REQUIRE(g->nnz_cap == 0 || (g->nbr && m), MGCN_ERR_NULL);
+  MGCN_REQUIRE(g->nnz_cap == 0 || (g->nbr_w && m), MGCN_ERR_NULL);
+  MGCN_REQUIRE((reinterpret_cast<uintptr_t>(m) & 31u) == 0, MGCN_ERR_ALIGN);   // 256-bit row gathers
   MGCN_REQUIRE(aligned16(g->tasks) && aligned16(m) && aligned16(x_next) && aligned16(partial) &&
                    (!x || aligned16(x)) && (!resid || aligned16(resid)) &&
                    (!m_next || aligned16(m_next)) && (!bias || aligned16(bias)),
                MGCN_ERR_ALIGN);
   LayerFwdArgs a{};
   a.tasks = reinterpret_cast<const int4*>(g->tasks);
-  a.nbr = g->nbr;
+  a.nbr_w = g->nbr_w;
   a.seg_count = hubs ? g->seg_count : nullptr;
   a.hub_rows = g->hub_rows;
   a.hub_seg0 = g->hub_seg0;
@@ -650,9 +845,9 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
       attr_err = cudaFuncSetAttribute(k_layer_fwd_hubs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   });
   MGCN_CHECK_CUDA(attr_err);
-  const int64_t max_tiles = ceil_div(g->n_rows, 16) + ceil_div(a.seg_cap, 16);
+  const int64_t max_tiles = ceil_div(g->n_rows + a.seg_cap, 16);
   int64_t blocks = ceil_div(max_tiles, kFwdWarps);
-  if (blocks > (int64_t)kNumSMs * 3) blocks = (int64_t)kNumSMs * 3;
+  if (blocks > (int64_t)kNumSMs * MGCN_FWD_MINB) blocks = (int64_t)kNumSMs * MGCN_FWD_MINB;
   MGCN_LAUNCH(k_layer_fwd, (unsigned)blocks, kFwdWarps * 32, smem, stream, a);
   if (hubs) {
     int64_t hb = ceil_div(ceil_div(a.hub_cap, 16), kFwdWarps);

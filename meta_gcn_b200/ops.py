@@ -41,7 +41,7 @@ def _f32c(t, name):
 
 
 CSR_FIELDS = ("rowptr", "nbr", "perm", "order", "hub_rows", "hub_seg0", "hub_count", "seg_row",
-              "seg_beg", "seg_count", "tasks")
+              "seg_beg", "seg_count", "tasks", "nbr_w")
 
 
 class Csr:
@@ -102,7 +102,8 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRES
     nnz_cap, hub_cap, seg_cap = (c.value for c in caps)
     i32 = dict(dtype=torch.int32, device=dev)
     sizes = dict(rowptr=N + 1, nbr=nnz_cap, perm=nnz_cap, order=N, hub_rows=hub_cap, hub_seg0=hub_cap,
-                 hub_count=1, seg_row=seg_cap, seg_beg=seg_cap, seg_count=1, tasks=4 * (N + seg_cap))
+                 hub_count=1, seg_row=seg_cap, seg_beg=seg_cap, seg_count=1, tasks=4 * (N + seg_cap),
+                 nbr_w=nnz_cap)
     csr = Csr([torch.empty(sizes[n], **i32) for n in CSR_FIELDS], hub_threshold,
               torch.empty(1, **i32))
     nbytes = ctypes.c_size_t(0)
@@ -488,7 +489,7 @@ def _(edge_index, N, by, loop_mode, hub_threshold):
     hub_cap = cap // max(hub_threshold, 1) + 1
     seg_cap = cap // max(hub_threshold, 1) + hub_cap + 1
     i32 = dict(dtype=torch.int32, device=edge_index.device)
-    sizes = (N + 1, cap, cap, N, hub_cap, hub_cap, 1, seg_cap, seg_cap, 1, 4 * (N + seg_cap))
+    sizes = (N + 1, cap, cap, N, hub_cap, hub_cap, 1, seg_cap, seg_cap, 1, 4 * (N + seg_cap), cap)
     return [torch.empty(n, **i32) for n in sizes]
 
 

@@ -40,6 +40,37 @@ __global__ void __launch_bounds__(256) k_gather(const float* __restrict__ x, flo
   }
 }
 
+// 4 lanes x 256-bit per row (sm_100 LDG.256): 8 rows per warp instruction
+template <int U>
+__global__ void __launch_bounds__(256) k_gather256(const float* __restrict__ x, float* __restrict__ out,
+                                                   int64_t n_rows, int deg, uint32_t window) {
+  const int lane = threadIdx.x & 31, sub = lane & 3;
+  const int64_t G = (int64_t)gridDim.x * blockDim.x / 4;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 4; row < n_rows; row += G) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int64_t base = row / window * window;
+    const uint32_t span = (uint32_t)min((int64_t)window, n_rows - base);
+    for (int k = 0; k < deg; k += U) {
+      float v[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t j = base + hash32((uint32_t)row * 131u + k + u) % span;
+        const float* p = x + j * 32 + sub * 8;
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[u][0]), "=f"(v[u][1]), "=f"(v[u][2]), "=f"(v[u][3]), "=f"(v[u][4]), "=f"(v[u][5]),
+                       "=f"(v[u][6]), "=f"(v[u][7]) : "l"(p));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += v[u][q];
+    }
+    float4* o = reinterpret_cast<float4*>(out + row * 32 + sub * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_copy(const float4* __restrict__ a, float4* __restrict__ b, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     b[i] = a[i];
@@ -118,6 +149,19 @@ int main() {
     printf("window 143107 U=4: %.3f ms gather %.2f TB/s\n", ms, (double)n_big * deg * 128 / ms / 1e9);
     ms = time_ms([&] { k_gather<16><<<148 * 8, 256>>>(x, out, n_big, deg, 143107); }, 5);
     printf("window 143107 U=16: %.3f ms gather %.2f TB/s\n", ms, (double)n_big * deg * 128 / ms / 1e9);
+  }
+  printf("== 128-bit x 8 lanes vs 256-bit x 4 lanes, window 143107 (one graph), by CTAs/SM and loads in flight ==\n");
+  for (int cps = 2; cps <= 8; cps *= 2) {
+    float ms = time_ms([&] { k_gather<4><<<148 * cps, 256>>>(x, out, n_big, deg, 143107); }, 5);
+    printf("LDG.128 U=4 %d CTA/SM: %.3f ms %.2f TB/s\n", cps, ms, (double)n_big * deg * 128 / ms / 1e9);
+    ms = time_ms([&] { k_gather<8><<<148 * cps, 256>>>(x, out, n_big, deg, 143107); }, 5);
+    printf("LDG.128 U=8 %d CTA/SM: %.3f ms %.2f TB/s\n", cps, ms, (double)n_big * deg * 128 / ms / 1e9);
+    ms = time_ms([&] { k_gather256<2><<<148 * cps, 256>>>(x, out, n_big, deg, 143107); }, 5);
+    printf("LDG.256 U=2 %d CTA/SM: %.3f ms %.2f TB/s\n", cps, ms, (double)n_big * deg * 128 / ms / 1e9);
+    ms = time_ms([&] { k_gather256<4><<<148 * cps, 256>>>(x, out, n_big, deg, 143107); }, 5);
+    printf("LDG.256 U=4 %d CTA/SM: %.3f ms %.2f TB/s\n", cps, ms, (double)n_big * deg * 128 / ms / 1e9);
+    ms = time_ms([&] { k_gather256<8><<<148 * cps, 256>>>(x, out, n_big, deg, 143107); }, 5);
+    printf("LDG.256 U=8 %d CTA/SM: %.3f ms %.2f TB/s\n", cps, ms, (double)n_big * deg * 128 / ms / 1e9);
   }
   {
     float ms = time_ms([&] { k_copy<<<148 * 8, 256>>>((const float4*)x, (float4*)out, n_big * 8); }, 10);

@@ -57,19 +57,40 @@ def check_against_oracle(ei_np, n, by, mode, hub_t=256):
     assert (np.diff(key) >= 0).all()
     same = np.diff(key) == 0
     assert (np.diff(b.order)[same] > 0).all()
-    # work descriptors {row, beg, end, partial_slot}
+    # work descriptors {row, beg, end, partial_slot}: n + total_segs tasks sorted (stably, by task id)
+    # by (window, length; segments behind the rows of their window); positions contiguous in nbr_w
     t = b.tasks.reshape(-1, 4)
-    rows = b.order
-    is_hub = deg[rows] > hub_t
-    assert (t[:n, 0][is_hub] == -1).all()
-    ok = ~is_hub
-    assert (t[:n, 0][ok] == rows[ok]).all()
-    assert (t[:n, 1][ok] == o_rowptr[rows[ok]]).all() and (t[:n, 2][ok] == o_rowptr[rows[ok] + 1]).all()
-    assert (t[:n, 3] == 0).all()
-    ts = t[n:n + total_segs]
-    assert (ts[:, 0] == b.seg_row[:total_segs]).all() and (ts[:, 1] == b.seg_beg[:total_segs]).all()
-    assert (ts[:, 2] == np.minimum(ts[:, 1] + hub_t, o_rowptr[ts[:, 0] + 1])).all()
-    assert (ts[:, 3] == np.arange(total_segs) + 1).all()
+    nt = n + total_segs
+    tid_len = np.concatenate([np.minimum(deg, 1023), np.full(total_segs, 1024)]).astype(np.int64)
+    tid_win = np.concatenate([np.arange(n) >> 14, b.seg_row[:total_segs] >> 14]).astype(np.int64)
+    want = np.argsort(tid_win * 2048 + tid_len, kind="stable")
+    pos = 0
+    rows_seen, segs_seen = [], []
+    for p in range(nt):
+        s_id = int(want[p])
+        row, beg, end, slot = (int(v) for v in t[p])
+        assert beg == pos, (p, beg, pos)
+        if s_id < n:
+            assert slot == 0
+            if deg[s_id] > hub_t:
+                assert row == -1 and end == beg
+            else:
+                assert row == s_id and end - beg == deg[s_id]
+                assert (b.nbr_w[beg:end] == o_nbr[o_rowptr[s_id]:o_rowptr[s_id + 1]]).all()
+                rows_seen.append(s_id)
+        else:
+            q = s_id - n
+            assert slot == q + 1 and row == b.seg_row[q]
+            sb = int(b.seg_beg[q])
+            se = min(sb + hub_t, int(o_rowptr[row + 1]))
+            assert end - beg == se - sb
+            assert (b.nbr_w[beg:end] == o_nbr[sb:se]).all()
+            segs_seen.append(q)
+        pos = end
+    assert pos == nnz
+    assert sorted(segs_seen) == list(range(total_segs))
+    pad = t[nt:]
+    assert (pad[:, 0] == -1).all() and (pad[:, 1] == nnz).all() and (pad[:, 2] == nnz).all()
 
 
 @pytest.mark.parametrize("n,e", [(1, 1), (5, 0), (7, 3), (100, 4095), (100, 4096), (100, 4097), (300, 8193),
