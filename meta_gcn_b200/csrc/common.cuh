@@ -83,6 +83,21 @@ __device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc
 int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, int act, float* out,
                       float* partial, bool hubs, void* stream);
 
+// narrow-side dense transforms (dense_narrow.cu)
+bool narrow_linear_applies(int64_t Hi, int64_t Ho, const float* x, const float* xmask, const float* add,
+                           const float* y);
+int launch_narrow_linear(const float* x, const float* xmask, int64_t N, int64_t Hi, const float* w,
+                         int64_t w_sk, int64_t w_sc, int64_t Ho, const float* bias, const float* add,
+                         int act, const float* row_scale, float* y, void* stream);
+bool narrow_wgrad_applies(int64_t Hi, int64_t Ho, const float* x, const float* g, const float* gmask);
+size_t narrow_wgrad_blocks(int64_t N);
+int launch_narrow_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, const float* gmask,
+                        int64_t Ho, float* dw, int64_t dw_sk, int64_t dw_sc, float* db, float* part,
+                        float* part_db, void* stream);
+// out[k*sk + c*sc] = sum_p partial[p*count + k*Hc + c], fixed order
+int launch_reduce_partials(const float* partial, int P, int count, int Hc, float* out, int64_t sk,
+                           int64_t sc, void* stream);
+
 }  // namespace mgcn
 
 // Launch + count + error check.  Used inside functions returning int.

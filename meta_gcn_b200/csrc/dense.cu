@@ -349,6 +349,8 @@ extern "C" int mgcn_linear_ex(const float* x, const float* xmask, int64_t N, int
   MGCN_REQUIRE(act == 0 || act == 1, MGCN_ERR_SHAPE);
   if (N == 0) return MGCN_OK;
   MGCN_REQUIRE(x && w && y, MGCN_ERR_NULL);
+  if (narrow_linear_applies(Hi, Ho, x, xmask, add, y))
+    return launch_narrow_linear(x, xmask, N, Hi, w, w_sk, w_sc, Ho, bias, add, act, row_scale, y, stream);
   const int x_vec4 = (Hi % 4 == 0) && aligned16(x) && (!xmask || aligned16(xmask));
   const int y_vec4 = (Ho % 4 == 0) && aligned16(y) && (!add || aligned16(add));
   dim3 grid((unsigned)ceil_div(N, kBM), (unsigned)ceil_div(Ho, kBN));
@@ -371,9 +373,10 @@ extern "C" int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const
   MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
   MGCN_REQUIRE(Hi >= 1 && Ho >= 1 && Hi <= 65536 && Ho <= 65536, MGCN_ERR_SHAPE);
   const int P = wgrad_slabs(N);
+  const size_t p_max = (size_t)P > narrow_wgrad_blocks(N) ? (size_t)P : narrow_wgrad_blocks(N);
   WorkspaceCarver ws(workspace);
-  float* partial = ws.take<float>((size_t)P * Hi * Ho);
-  float* partial_b = ws.take<float>((size_t)P * Ho);
+  float* partial = ws.take<float>(p_max * Hi * Ho);
+  float* partial_b = ws.take<float>(p_max * Ho);
   if (workspace == nullptr) {
     *workspace_bytes = ws.bytes();
     return MGCN_OK;
@@ -381,6 +384,8 @@ extern "C" int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const
   MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
   MGCN_REQUIRE(dw != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(N == 0 || (x && g), MGCN_ERR_NULL);
+  if (N > 0 && narrow_wgrad_applies(Hi, Ho, x, g, gmask))
+    return launch_narrow_wgrad(x, N, Hi, g, gmask, Ho, dw, dw_sk, dw_sc, db, partial, partial_b, stream);
   const int64_t rows_per_slab = ceil_div(ceil_div(N > 0 ? N : 1, P), kWgRows) * kWgRows;
   const int x_vec4 = (Hi % 4 == 0) && aligned16(x);
   const int g_vec4 = (Ho % 4 == 0) && aligned16(g) && (!gmask || aligned16(gmask));
@@ -388,13 +393,10 @@ extern "C" int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const
   MGCN_LAUNCH(k_wgrad_partial, grid, 256, 0, stream, x, N, (int)Hi, g, gmask, (int)Ho,
               rows_per_slab, partial, db ? partial_b : nullptr, x_vec4, g_vec4);
   const int64_t count = Hi * Ho;
-  MGCN_LAUNCH(k_wgrad_reduce, (unsigned)ceil_div(count, 256), 256, 0, stream, partial, P, count,
-              (int)Ho, dw, dw_sk, dw_sc);
-  if (db) {
-    MGCN_LAUNCH(k_wgrad_reduce, (unsigned)ceil_div(Ho, 256), 256, 0, stream, partial_b, P, Ho, 0,
-                db, (int64_t)0, (int64_t)0);
-  }
-  return MGCN_OK;
+  int rc = launch_reduce_partials(partial, P, (int)count, (int)Ho, dw, dw_sk, dw_sc, stream);
+  if (rc != MGCN_OK) return rc;
+  if (db) rc = launch_reduce_partials(partial_b, P, (int)Ho, (int)Ho, db, 0, 1, stream);
+  return rc;
 }
 
 extern "C" int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, int64_t Ho,

@@ -742,23 +742,6 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) k_layer_bwd(const LayerBwdA
   }
 }
 
-// out[i] = sum_p partial[p*count + i], p ascending in 4 interleaved chains
-__global__ void __launch_bounds__(256) k_partial_reduce(const float* __restrict__ partial, int P,
-                                                        int count, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int p = 0;
-  for (; p + 4 <= P; p += 4) {
-    s0 += partial[(int64_t)(p + 0) * count + i];
-    s1 += partial[(int64_t)(p + 1) * count + i];
-    s2 += partial[(int64_t)(p + 2) * count + i];
-    s3 += partial[(int64_t)(p + 3) * count + i];
-  }
-  for (; p < P; ++p) s0 += partial[(int64_t)p * count + i];
-  out[i] = (s0 + s1) + (s2 + s3);
-}
-
 // gs = post * gy * bits   (seed of the backward: last layer has no outer ReLU)
 __global__ void __launch_bounds__(256) k_mask_bits_scale(const float* __restrict__ gy,
                                                          const uint32_t* __restrict__ bits,
@@ -894,10 +877,10 @@ extern "C" int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float
   });
   MGCN_CHECK_CUDA(attr_err);
   MGCN_LAUNCH(k_layer_bwd, P, kBwdWarps * 32, smem, stream, a);
-  MGCN_LAUNCH(k_partial_reduce, (kH * kH + 255) / 256, 256, 0, stream, part_w, P, kH * kH, dw);
-  MGCN_LAUNCH(k_partial_reduce, (kH * kH + 255) / 256, 256, 0, stream, part_r, P, kH * kH, d_res_w);
-  MGCN_LAUNCH(k_partial_reduce, 1, 256, 0, stream, part_b, P, kH, d_res_b);
-  return MGCN_OK;
+  int rc = launch_reduce_partials(part_w, P, kH * kH, kH, dw, kH, 1, stream);
+  if (rc == MGCN_OK) rc = launch_reduce_partials(part_r, P, kH * kH, kH, d_res_w, kH, 1, stream);
+  if (rc == MGCN_OK) rc = launch_reduce_partials(part_b, P, kH, kH, d_res_b, 0, 1, stream);
+  return rc;
 }
 
 extern "C" int mgcn_mask_bits_scale(const float* gy, const uint32_t* bits, const float* post,
