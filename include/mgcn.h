@@ -181,6 +181,14 @@ int mgcn_linear_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, int
                       int64_t dw_sk, int64_t dw_sc, float* db, void* workspace,
                       size_t* workspace_bytes, void* stream);
 
+/* The same transform for wide outputs on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+ * tensor memory): Ho in {64,128,192,256}, Hi % 4 == 0.  SAGEConv / GCNConv `matmul(x, weight) (+ bias)`
+ * at hidden >= 64 (kernel/graph_sage.py:10,13; kernel/gcn.py:10,13; PyG 1.3 update()).  fp32 parity
+ * through 3xTF32 with separately accumulated correction terms.  workspace holds the pre-split weight. */
+int mgcn_linear_wide(const float* x, int64_t N, int64_t Hi, const float* w, int64_t w_sk, int64_t w_sc,
+                     int64_t Ho, const float* bias, const float* add, int act, const float* row_scale,
+                     float* y, void* workspace, size_t* workspace_bytes, void* stream);
+
 /* mgcn_linear_wgrad with the gradient operand masked: g * (gmask > 0)  (gmask [N,Ho], may be NULL) */
 int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const float* g, const float* gmask,
                          int64_t Ho, float* dw, int64_t dw_sk, int64_t dw_sc, float* db,

@@ -64,6 +64,8 @@ SIGNATURES = {
                             c_ptr, c_ptr]),
     "mgcn_linear_ex": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr,
                                c_int, c_ptr, c_ptr, c_ptr]),
+    "mgcn_linear_wide": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_int, c_ptr,
+                                 c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_linear_wgrad_ex": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64,
                                      c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_masked_scale": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),

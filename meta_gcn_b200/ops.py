@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import MgcnCsr
 
 DEFAULT_HUB_THRESHOLD = 64
+WIDE_WIDTHS = (64, 128, 192, 256)   # output widths served by the tcgen05 transform
 
 
 def _ptr(t):
@@ -229,6 +230,13 @@ def linear_impl(x, w, w_out_in, bias=None, add=None, act=0, xmask=None, row_scal
     if xmask is not None and xmask.shape != x.shape:
         raise ValueError("xmask must have the shape of x")
     y = torch.empty(N, Ho, dtype=torch.float32, device=x.device)
+    if xmask is None and Ho in WIDE_WIDTHS and Hi >= 32 and Hi % 4 == 0 and N > 0:
+        # wide output: tcgen05 / TMEM tile GEMM (csrc/linear_wide.cu)
+        lib = _lib.load()
+        args = (_ptr(x), N, Hi, _ptr(w), sk, sc, Ho, _ptr(bias), _ptr(add), int(act), _ptr(row_scale), _ptr(y))
+        ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_linear_wide(*args, w_, nb, stm), x.device)
+        _lib.check(lib.mgcn_linear_wide(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+        return y
     _lib.check(_lib.load().mgcn_linear_ex(_ptr(x), _ptr(xmask), N, Hi, _ptr(w), sk, sc, Ho, _ptr(bias),
                                           _ptr(add), int(act), _ptr(row_scale), _ptr(y), _stream()))
     return y
