@@ -23,6 +23,7 @@
 // botnet batch; the FP32 FMA peak (74 TFLOP/s) alone would cost 7 ms against a 5 ms HBM bound for the
 // whole step (measured: FMA transforms 0.28-0.54 ms per product, scripts/microbench.py).  fp32 parity
 // (rtol 1e-5) rules out single-pass TF32, hence the hi/lo split of mma_tile.cuh.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -864,6 +865,7 @@ extern "C" int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float
   MGCN_REQUIRE(aligned16(dxw) && aligned16(gy) && aligned16(x) && (!gy_prev || aligned16(gy_prev)) &&
                    (!gs_prev || aligned16(gs_prev)),
                MGCN_ERR_ALIGN);
+  if (N == 0) return MGCN_OK;
   LayerBwdArgs a{};
   a.dxw = dxw; a.gy = gy; a.x = x; a.w = w; a.res_w = res_w; a.hmask_prev = hmask_prev; a.post = post;
   a.gy_prev = gy_prev; a.gs_prev = gs_prev;
@@ -881,6 +883,34 @@ extern "C" int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float
   if (rc == MGCN_OK) rc = launch_reduce_partials(part_r, P, kH * kH, kH, d_res_w, kH, 1, stream);
   if (rc == MGCN_OK) rc = launch_reduce_partials(part_b, P, kH, kH, d_res_b, 0, 1, stream);
   return rc;
+}
+
+// Same contract on tcgen05 / TMEM (gcn_layer_tc.cu).  Measured 0.99 ms against 0.83 ms for the mma.sync
+// kernel above at the botnet batch (profiles/r1_layer_summary.md): correct, not yet the default.
+extern "C" int mgcn_gcn_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* w,
+                                     const float* res_w, const uint32_t* hmask_prev, const float* post,
+                                     int64_t N, int64_t H, float* gy_prev, float* gs_prev, float* dw,
+                                     float* d_res_w, float* d_res_b, void* workspace,
+                                     size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(H == kH, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
+  WorkspaceCarver ws(workspace);
+  float* tc_ws = ws.take<float>(bwd_tc_workspace_floats(N));
+  if (workspace == nullptr) {
+    *workspace_bytes = ws.bytes();
+    return MGCN_OK;
+  }
+  MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
+  MGCN_REQUIRE(dxw && gy && x && w && res_w && dw && d_res_w && d_res_b, MGCN_ERR_NULL);
+  MGCN_REQUIRE((gy_prev == nullptr) == (gs_prev == nullptr), MGCN_ERR_NULL);
+  MGCN_REQUIRE(!gy_prev || hmask_prev, MGCN_ERR_NULL);
+  MGCN_REQUIRE(aligned16(dxw) && aligned16(gy) && aligned16(x) && (!gy_prev || aligned16(gy_prev)) &&
+                   (!gs_prev || aligned16(gs_prev)),
+               MGCN_ERR_ALIGN);
+  if (N == 0) return MGCN_OK;
+  return launch_layer_bwd_tc(dxw, gy, x, w, res_w, hmask_prev, post, N, gy_prev, gs_prev, dw, d_res_w,
+                             d_res_b, tc_ws, stream);
 }
 
 extern "C" int mgcn_mask_bits_scale(const float* gy, const uint32_t* bits, const float* post,

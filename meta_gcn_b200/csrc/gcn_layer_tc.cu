@@ -1,0 +1,360 @@
+// Row-local backward of one residual GCN layer at hidden 32 on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in tensor memory) — same contract as k_layer_bwd (gcn_layer.cu):
+//     G = dxw W^T + gy R;   dW = x^T dxw;   dR = gy^T x;   dr = colsum(gy)
+//     gy_prev = G * (x > 0);   gs_prev = post * gy_prev * bits(hmask_prev)
+// Every operand element is split ONCE into hi/lo tf32 images in shared memory and one thread issues 24
+// tcgen05.mma per 64-row tile:
+//   row-local   D[64 x 64|32] (+)= A_K[64 x 8] * B_K[64|32 x 8]^T        K-major, un-swizzled interleaved images
+//               TMEM cols [0,32) main = dxw_hi Wt_hi + gy_hi R_hi; [32,64) = hi * B_lo; [64,96) = lo * B_hi
+//               (M = 64 accumulators live in lanes 0..15 of each 32-lane TMEM quarter)
+//   transposed  [D1 | D2][128 x 64] (+)= [dxw_hi|gy_hi|dxw_lo|gy_lo]^T[128 x 8 rows] * [x_hi | x_lo][8 rows x 64]
+//               MN-major, SWIZZLE_128B_BASE32B images, TMEM cols [96,160)
+//               rows 0-31 -> dW^T, 32-63 -> dR (main terms), 64-127 -> their corrections
+// (a 32-bit MN-major operand is only read correctly from the BASE32B image, a K-major one never from it —
+// scripts/tc_probe.cu — hence dxw and gy are stored in both images.)  Chains through the TMEM accumulator
+// stay short (8 steps) and start from zero in every tile; sums over tiles are RN adds in registers;
+// per-CTA partials are reduced in a fixed order.  Two persistent CTAs per SM (98 KB of images, 256 TMEM
+// columns each); the next tile is prefetched into registers while the current one is processed.
+//
+// Status (profiles/r1_layer_summary.md): parity-green, 0.99 ms per layer at the botnet batch against 0.83 ms
+// for the mma.sync kernel — 23 % of warp time waits on the MMA barrier, 16 % on the end-of-tile barrier
+// (the G epilogue runs on 64 of 256 threads), 14 % on the prefetched loads.  Next step: warp-specialised
+// producer / MMA / epilogue roles over double-buffered images instead of CTA-wide phases.
+#include <mutex>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace mgcn {
+
+constexpr int kTH = 32;
+constexpr int kTRows = 64;                 // rows per tile: two CTAs (98 KB of images each) share an SM, so one
+                                           // CTA's split / epilogue overlaps the other's tensor-core phase
+constexpr int kTileB = kTRows * kTH * 4;   // 8 KB per image
+
+struct BwdTcArgs {
+  const float* dxw;
+  const float* gy;
+  const float* x;
+  const float* w;            // weight_node (in j, out c)
+  const float* res_w;        // residual weight (out c, in j)
+  const uint32_t* hmask_prev;
+  const float* post;
+  float* gy_prev;
+  float* gs_prev;
+  float* part_t;             // [grid][128][32]
+  float* part_b;             // [grid][32]
+  int64_t n_rows;
+};
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr int kOffKDh = 0;                 // K-major images of dxw_hi, dxw_lo, gy_hi, gy_lo
+constexpr int kOffKDl = 1 * kTileB;
+constexpr int kOffKGh = 2 * kTileB;
+constexpr int kOffKGl = 3 * kTileB;
+constexpr int kOffMN = 4 * kTileB;         // MN-major images [dxw_hi | gy_hi | dxw_lo | gy_lo]
+constexpr int kOffMXh = 8 * kTileB;        // MN-major x_hi, x_lo
+constexpr int kOffMXl = 9 * kTileB;
+constexpr int kOffB1 = 10 * kTileB;        // [Wt_hi ; Wt_lo]  64 x 32, K-major
+constexpr int kOffB2 = kOffB1 + 8192;      // [R_hi ; R_lo]
+constexpr int kOffMisc = kOffB2 + 8192;    // barrier, tmem slot, xbits[64], dr reduction scratch
+constexpr int kBwdTcSmem = kOffMisc + 64 + 256 + 64 * 32 * 4 + 1024;
+
+__device__ __forceinline__ int k_image_off(int r, int q) {      // bytes; 16-byte chunk q of row r, interleaved
+  return ((r >> 3) << 10) + (q << 7) + ((r & 7) << 4);
+}
+__device__ __forceinline__ int mn_image_off(int r, int q) {     // bytes; SWIZZLE_128B_BASE32B
+  return (r << 7) + ((((q >> 1) ^ (r & 3)) << 5) | ((q & 1) << 4));
+}
+
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  const float e[4] = {v.x, v.y, v.z, v.w};
+  float h[4], l[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    h[t] = __uint_as_float(round_tf32_bits(__float_as_uint(e[t])));
+    l[t] = __uint_as_float(round_tf32_bits(__float_as_uint(e[t] - h[t])));
+  }
+  hi = make_float4(h[0], h[1], h[2], h[3]);
+  lo = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(256, 2) k_layer_bwd_tc(const BwdTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte alignment as an offset on the __shared__ array (keeps the shared address space: STS, not ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffMisc);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 16);
+  uint32_t* xbits = reinterpret_cast<uint32_t*>(smem + kOffMisc + 64);
+  float* dr_red = reinterpret_cast<float*>(smem + kOffMisc + 64 + 256);   // [64 slots][32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool want_prev = a.gy_prev != nullptr;
+
+  // weight images: B1(n, k) = W[n][k] (hi rows 0..31, lo rows 32..63); B2(n, k) = R[k][n]
+  for (int i = tid; i < 32 * 32; i += 256) {
+    const int n = i >> 5, k = i & 31;
+    const float w1 = __ldg(a.w + n * 32 + k), w2 = __ldg(a.res_w + k * 32 + n);
+    const float h1 = __uint_as_float(round_tf32_bits(__float_as_uint(w1)));
+    const float h2 = __uint_as_float(round_tf32_bits(__float_as_uint(w2)));
+    float* b1 = reinterpret_cast<float*>(smem + kOffB1);
+    float* b2 = reinterpret_cast<float*>(smem + kOffB2);
+    const int o_hi = (k_image_off(n, k >> 2) >> 2) + (k & 3), o_lo = (k_image_off(n + 32, k >> 2) >> 2) + (k & 3);
+    b1[o_hi] = h1;
+    b1[o_lo] = __uint_as_float(round_tf32_bits(__float_as_uint(w1 - h1)));
+    b2[o_hi] = h2;
+    b2[o_lo] = __uint_as_float(round_tf32_bits(__float_as_uint(w2 - h2)));
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const uint64_t pol = policy_evict_first();
+
+  // this thread's elements of a tile: row r0, 16-byte chunks q0 and q0 + 4 (the four lanes with equal lane % 8
+  // cover one row's 8 chunks)
+  const int r0 = (lane & 7) + 8 * warp, q0 = lane >> 3;
+  const int64_t n_tiles = (a.n_rows + kTRows - 1) / kTRows;
+  float4 cur[3][2], nxt[3][2];
+  auto load_tile = [&](float4 (&dst)[3][2], int64_t tile) {
+    const float* src[3] = {a.dxw, a.gy, a.x};
+#pragma unroll
+    for (int arr = 0; arr < 3; ++arr)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t gr = tile * kTRows + r0;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tile < n_tiles && gr < a.n_rows) v = __ldg(reinterpret_cast<const float4*>(src[arr] + gr * kTH + 4 * (q0 + 4 * i)));
+        dst[arr][i] = v;
+      }
+  };
+
+  float acc_t[32];   // warps 4..7: running transposed-product row of this TMEM lane
+#pragma unroll
+  for (int t = 0; t < 32; ++t) acc_t[t] = 0.f;
+  float acc_dr[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc_dr[i][t] = 0.f;
+
+  const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32), idT = umma_idesc_tf32(128, 64, 1, 1);
+  const uint32_t sbase = smem_u32(smem);
+  // descriptor templates: the start-address field (bits 0..13, 16-byte units) is added per k step
+  const uint64_t dK = umma_desc(sbase, 128, 1024, 0), dM = umma_desc(sbase, kTileB, 512, 1);
+  uint32_t phase = 0;
+  int64_t tile = blockIdx.x;
+  load_tile(cur, tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    load_tile(nxt, tile + gridDim.x);
+    // ---- split once, write the operand images ----
+    {
+      const int r = r0;
+      uint32_t b = 0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = q0 + 4 * i;
+        const int ko = k_image_off(r, q), mo = mn_image_off(r, q);
+        float4 hi, lo;
+        split4(cur[0][i], hi, lo);                 // dxw
+        *reinterpret_cast<float4*>(smem + kOffKDh + ko) = hi;
+        *reinterpret_cast<float4*>(smem + kOffKDl + ko) = lo;
+        *reinterpret_cast<float4*>(smem + kOffMN + 0 * kTileB + mo) = hi;
+        *reinterpret_cast<float4*>(smem + kOffMN + 2 * kTileB + mo) = lo;
+        const float4 gv = cur[1][i];               // gy
+        acc_dr[i][0] += gv.x; acc_dr[i][1] += gv.y; acc_dr[i][2] += gv.z; acc_dr[i][3] += gv.w;
+        split4(gv, hi, lo);
+        *reinterpret_cast<float4*>(smem + kOffKGh + ko) = hi;
+        *reinterpret_cast<float4*>(smem + kOffKGl + ko) = lo;
+        *reinterpret_cast<float4*>(smem + kOffMN + 1 * kTileB + mo) = hi;
+        *reinterpret_cast<float4*>(smem + kOffMN + 3 * kTileB + mo) = lo;
+        const float4 xv = cur[2][i];               // x
+        split4(xv, hi, lo);
+        *reinterpret_cast<float4*>(smem + kOffMXh + mo) = hi;
+        *reinterpret_cast<float4*>(smem + kOffMXl + mo) = lo;
+        b |= ((xv.x > 0.f ? 1u : 0u) | (xv.y > 0.f ? 2u : 0u) | (xv.z > 0.f ? 4u : 0u) | (xv.w > 0.f ? 8u : 0u)) << (4 * q);
+      }
+      b |= __shfl_xor_sync(0xffffffffu, b, 8);
+      b |= __shfl_xor_sync(0xffffffffu, b, 16);
+      if (q0 == 0) xbits[r] = b;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (want_prev) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
+          const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
+          umma_tf32(tmem + 0, dK + ((kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
+          umma_tf32(tmem + 0, dK + ((kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
+          umma_tf32(tmem + 64, dK + ((kOffKDl >> 4) + ko), b1, idG32, k > 0);   // dxw_lo Wt_hi
+          umma_tf32(tmem + 64, dK + ((kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kTRows / 8; ++k) {
+        const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
+        // B = [x_hi | x_lo]: two 32-column MN atoms one image apart -> D1 | D2 in one N = 64 instruction
+        umma_tf32(tmem + 96, dM + ((kOffMN >> 4) + ko), dM + ((kOffMXh >> 4) + ko), idT, k > 0);
+      }
+      umma_commit(bar);
+    }
+    // scalars of the row this thread finishes below (warps 0..3, lanes 0..15: M = 64 accumulators live in
+    // lanes 0..15 of every 32-lane TMEM quarter)
+    const int my_row = 16 * (warp & 3) + (lane & 15);
+    const int64_t g_row = tile * kTRows + my_row;
+    const bool fin = want_prev && warp < 4 && lane < 16 && g_row < a.n_rows;
+    uint32_t hbits = 0;
+    float postv = 1.f;
+    if (fin) {
+      hbits = __ldg(a.hmask_prev + g_row);
+      if (a.post) postv = __ldg(a.post + g_row);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    if (warp >= 4) {
+      // transposed products of this tile -> running fp32 sums (RN)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t d1[16], d2[16];
+        tmem_ld16(lane_addr + 96 + 16 * h, d1);
+        tmem_ld16(lane_addr + 128 + 16 * h, d2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc_t[16 * h + t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
+      }
+    } else if (want_prev) {
+      // G row of this lane -> gy_prev, gs_prev rows, 8 columns at a time
+      const uint32_t xb = xbits[my_row];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t m[8], c1[8], c2[8];
+        tmem_ld8(lane_addr + 0 + 8 * h, m);
+        tmem_ld8(lane_addr + 32 + 8 * h, c1);
+        tmem_ld8(lane_addr + 64 + 8 * h, c2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (fin) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float g[4], s[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int c = 8 * h + 4 * q + t;
+              const float gv = __uint_as_float(m[4 * q + t]) + (__uint_as_float(c1[4 * q + t]) + __uint_as_float(c2[4 * q + t]));
+              g[t] = ((xb >> c) & 1u) ? gv : 0.f;
+              s[t] = ((hbits >> c) & 1u) ? g[t] * postv : 0.f;
+            }
+            st_f4_hint(a.gy_prev + g_row * kTH + 8 * h + 4 * q, make_float4(g[0], g[1], g[2], g[3]), pol);
+            st_f4_hint(a.gs_prev + g_row * kTH + 8 * h + 4 * q, make_float4(s[0], s[1], s[2], s[3]), pol);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();   // TMEM and xbits reads done; images may be rewritten
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int arr = 0; arr < 3; ++arr)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) cur[arr][i] = nxt[arr][i];
+  }
+  // ---- per-CTA partials ----
+  if (warp >= 4) {
+    float* p = a.part_t + ((int64_t)blockIdx.x * 128 + 32 * (warp & 3) + lane) * 32;
+#pragma unroll
+    for (int t = 0; t < 32; t += 4) *reinterpret_cast<float4*>(p + t) = make_float4(acc_t[t], acc_t[t + 1], acc_t[t + 2], acc_t[t + 3]);
+  }
+  // dr[c]: this thread holds columns 4*(q0 + 4i) + t summed over its rows; fixed-order sum over the 64 row slots
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dr_red[((warp * 8 + (lane & 7)) * 8 + (q0 + 4 * i)) * 4 + t] = acc_dr[i][t];
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    for (int slot = 0; slot < 64; ++slot) s += dr_red[slot * 32 + tid];
+    a.part_b[(int64_t)blockIdx.x * 32 + tid] = s;
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+// dW[j][c] = sum_p part[p][c][j] + part[p][64 + c][j];   dR[c][j] = sum_p part[p][32 + c][j] + part[p][96 + c][j]
+__global__ void __launch_bounds__(256) k_bwd_tc_reduce(const float* __restrict__ part, int P, float* __restrict__ dw,
+                                                       float* __restrict__ d_res_w) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;          // 0..2047
+  const int which = o >> 10, a0 = (o >> 5) & 31, b0 = o & 31;
+  // dW[j = a0][c = b0]: rows c, 64 + c, column j;  dR[c = a0][j = b0]: rows 32 + c, 96 + c, column j
+  const int row = which == 0 ? b0 : 32 + a0, col = which == 0 ? a0 : b0;
+  const int per = (P + 7) / 8, p0 = warp * per, p1 = min(P, p0 + per);
+  float s_main = 0.f, s_corr = 0.f;
+  for (int p = p0; p < p1; ++p) {
+    s_main += part[((int64_t)p * 128 + row) * 32 + col];
+    s_corr += part[((int64_t)p * 128 + row + 64) * 32 + col];
+  }
+  red[warp][lane] = s_main + s_corr;
+  __syncthreads();
+  if (warp == 0) {
+    float s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][lane];
+    (which == 0 ? dw : d_res_w)[a0 * 32 + b0] = s;
+  }
+}
+
+int bwd_tc_grid(int64_t N) {
+  const int64_t tiles = ceil_div(N > 0 ? N : 1, kTRows);
+  return (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+}
+
+size_t bwd_tc_workspace_floats(int64_t N) { return (size_t)bwd_tc_grid(N) * (128 * 32 + 32); }
+
+int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* w, const float* res_w,
+                        const uint32_t* hmask_prev, const float* post, int64_t N, float* gy_prev, float* gs_prev,
+                        float* dw, float* d_res_w, float* d_res_b, float* ws, void* stream) {
+  const int P = bwd_tc_grid(N);
+  BwdTcArgs a{};
+  a.dxw = dxw; a.gy = gy; a.x = x; a.w = w; a.res_w = res_w; a.hmask_prev = hmask_prev; a.post = post;
+  a.gy_prev = gy_prev; a.gs_prev = gs_prev;
+  a.part_t = ws;
+  a.part_b = ws + (size_t)P * 128 * 32;
+  a.n_rows = N;
+  static std::once_flag once;
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(k_layer_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
+  });
+  MGCN_CHECK_CUDA(attr_err);
+  MGCN_LAUNCH(k_layer_bwd_tc, P, 256, kBwdTcSmem, stream, a);
+  MGCN_LAUNCH(k_bwd_tc_reduce, 64, 256, 0, stream, a.part_t, P, dw, d_res_w);
+  return launch_reduce_partials(a.part_b, P, 32, 32, d_res_b, 0, 1, stream);
+}
+
+}  // namespace mgcn

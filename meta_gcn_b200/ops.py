@@ -304,7 +304,7 @@ def gcn_layer_fwd_impl(csr, m, x, resid, res_w, res_b, w_next, bias, pre, post, 
     return x_next, m_next, hmask
 
 
-def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True):
+def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, tensor_memory=False):
     """row-local backward of one layer at hidden 32 (mgcn_gcn_layer_bwd): returns
     (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b)"""
     _need_cuda(dxw, gy, x, w, res_w, hmask_prev, post)
@@ -324,8 +324,9 @@ def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True):
     lib = _lib.load()
     args = (_ptr(dxw), _ptr(gy), _ptr(x), _ptr(w), _ptr(res_w), _ptr(hmask_prev) if want_prev else None,
             _ptr(post), N, H, _ptr(gy_prev), _ptr(gs_prev), _ptr(dw), _ptr(drw), _ptr(drb))
-    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_gcn_layer_bwd(*args, w_, nb, stm), dev)
-    _lib.check(lib.mgcn_gcn_layer_bwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    fn = lib.mgcn_gcn_layer_bwd_tc if tensor_memory else lib.mgcn_gcn_layer_bwd
+    ws, nbytes = _workspace(lambda w_, nb, stm: fn(*args, w_, nb, stm), dev)
+    _lib.check(fn(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
     return gy_prev, gs_prev, dw, drw, drb
 
 

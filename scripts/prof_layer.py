@@ -60,5 +60,6 @@ timeit("agg_plain bwd structure", lambda: ops.aggregate_prescaled_impl(gs.bwd, g
 timeit("agg_plain fwd structure", lambda: ops.aggregate_prescaled_impl(gs.fwd, gy, dis, 0, None, None, 1),
        b_agg(n, e, H))
 timeit("layer_bwd (row-local, 4 products)", lambda: ops.gcn_layer_bwd_impl(m, gy, x, w, r, bits, dis, True), 5 * nh + 8 * n)
+timeit("layer_bwd tcgen05 variant", lambda: ops.gcn_layer_bwd_impl(m, gy, x, w, r, bits, dis, True, True), 5 * nh + 8 * n)
 timeit("mask_bits_scale", lambda: ops.mask_bits_scale_impl(gy, bits, dis), 2 * nh + 8 * n)
 timeit("torch copy", lambda: m.copy_(x), 2 * nh)

@@ -95,8 +95,9 @@ def test_layer_fwd_is_deterministic_and_order_exact():
     assert_bitexact(outs[0], torch.relu(ref), "edge-order sum")
 
 
-@pytest.mark.parametrize("n,want_prev", [(1000, True), (1003, True), (131, False), (7, True)])
-def test_layer_bwd(n, want_prev):
+@pytest.mark.parametrize("tensor_memory", [False, True])
+@pytest.mark.parametrize("n,want_prev", [(1000, True), (1003, True), (131, False), (7, True), (40000, True)])
+def test_layer_bwd(n, want_prev, tensor_memory):
     gen = torch.Generator().manual_seed(n)
     dxw = torch.randn(n, H, generator=gen)
     gy = torch.randn(n, H, generator=gen)
@@ -107,7 +108,7 @@ def test_layer_bwd(n, want_prev):
     bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), generator=gen, dtype=torch.int64).to(torch.int32)
     d = lambda t: t.to(DEV)
     gyp, gsp, dw, drw, drb = ops.gcn_layer_bwd_impl(d(dxw), d(gy), d(x), d(w), d(res_w), d(bits), d(post),
-                                                    want_prev)
+                                                    want_prev, tensor_memory)
     D = lambda t: t.double()
     assert_parity(dw, D(x).t() @ D(dxw), "dW")
     assert_parity(drw, D(gy).t() @ D(x), "dR")
