@@ -218,7 +218,9 @@ int mgcn_relu_backward(const float* g, const float* y, int64_t count, float* g_i
  *            m_next = pre * (x_next w_next)       (w_next may be NULL: last layer)
  *            hmask[i] bit c = (h[i,c] > 0)
  * Sums run in edge_index order per row (hub rows: per segment, segments left to right); the dense
- * products run on the tensor pipe as 3xTF32 (error ~2^-21 relative), fp32 accumulate.
+ * products run on the tensor pipe as 3xTF32 with separately accumulated correction terms.
+ * Row-local mode, g == NULL: m[i] is the finished pre-activation of row i (n_in rows) — used for a first
+ * layer of small input width, which is aggregated BEFORE its transform: (A_hat x) W instead of A_hat (x W).
  */
 int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n_in, const float* x,
                        const float* resid, const float* res_w, const float* res_b,

@@ -342,6 +342,30 @@ __global__ void __launch_bounds__(kFwdWarps * 32, MGCN_FWD_MINB) k_layer_fwd(con
   const uint64_t pol = policy_evict_first();
 
   int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp;
+  if (a.tasks == nullptr) {
+    // row-local mode (first layer, aggregated before the transform): a.m holds the finished
+    // pre-activation z = post * (A_hat x) W of every row; tiles are 16 consecutive rows
+    const int64_t n_loc = (a.n_rows + 15) >> 4;
+    for (; tile < n_loc; tile += stride) {
+      const int64_t r = tile * 16 + lane;
+      const int myrow = (lane < 16 && r < a.n_rows) ? (int)r : -1;
+      float mypre = 1.f;
+      if (myrow >= 0 && a.pre && a.w_next) mypre = __ldg(a.pre + myrow);
+      stage_tile_async(a.x ? a.x : a.resid, myrow, Xs, lane, pol);
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int rowp = __shfl_sync(0xffffffffu, myrow, 8 * p + grp);
+        if (rowp >= 0) {
+          const Row8 z = ld_row8(a.m + (int64_t)rowp * kH + col);
+          finish_h(a, z, 1.f, rowp, &Hs[8 * p + grp][0], sub, gmask, col);
+        }
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane, pol);
+    }
+    return;
+  }
   int4 dn = make_int4(-1, 0, 0, 0);
   if (tile < n_tiles) dn = load_tile_desc(a.tasks, tile * 16, limit, lane, pol);
   for (; tile < n_tiles; tile += stride) {
@@ -780,12 +804,14 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
                                   const float* post, int act_out, int64_t H, float* x_next,
                                   float* m_next, uint32_t* hmask, void* workspace,
                                   size_t* workspace_bytes, void* stream) {
-  MGCN_REQUIRE(g != nullptr && workspace_bytes != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(H == kH, MGCN_ERR_SHAPE);
   MGCN_REQUIRE(act_out == 0 || act_out == 1, MGCN_ERR_SHAPE);
-  MGCN_REQUIRE(n_in >= 0 && g->n_rows >= 0, MGCN_ERR_RANGE);
-  const bool hubs = g->hub_rows && g->hub_seg0 && g->hub_count && g->seg_count && g->hub_cap > 0 &&
-                    g->seg_cap > 0;
+  MGCN_REQUIRE(n_in >= 0 && (!g || g->n_rows >= 0), MGCN_ERR_RANGE);
+  const bool local = g == nullptr;   // row-local mode: m is the finished pre-activation of row i
+  const int64_t n_rows = local ? n_in : g->n_rows;
+  const bool hubs = !local && g->hub_rows && g->hub_seg0 && g->hub_count && g->seg_count &&
+                    g->hub_cap > 0 && g->seg_cap > 0;
   WorkspaceCarver ws(workspace);
   float* partial = ws.take<float>(hubs ? (size_t)g->seg_cap * kH : 0);
   if (workspace == nullptr) {
@@ -793,33 +819,36 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
     return MGCN_OK;
   }
   MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
-  if (g->n_rows == 0) return MGCN_OK;
-  MGCN_REQUIRE(g->rowptr && g->tasks && x_next && hmask, MGCN_ERR_NULL);
+  if (n_rows == 0) return MGCN_OK;
+  MGCN_REQUIRE(x_next && hmask && m, MGCN_ERR_NULL);
+  MGCN_REQUIRE(local || (g->rowptr && g->tasks), MGCN_ERR_NULL);
   MGCN_REQUIRE((x != nullptr) != (resid != nullptr), MGCN_ERR_NULL);   // exactly one residual form
   MGCN_REQUIRE(!x || res_w, MGCN_ERR_NULL);
   MGCN_REQUIRE(!w_next || m_next, MGCN_ERR_NULL);
-  MGCN_REQUIRE(g->nnz_cap == 0 || (g->nbr_w && m), MGCN_ERR_NULL);
+  MGCN_REQUIRE(local || g->nnz_cap == 0 || g->nbr_w, MGCN_ERR_NULL);
   MGCN_REQUIRE((reinterpret_cast<uintptr_t>(m) & 31u) == 0, MGCN_ERR_ALIGN);   // 256-bit row gathers
-  MGCN_REQUIRE(aligned16(g->tasks) && aligned16(m) && aligned16(x_next) && aligned16(partial) &&
+  MGCN_REQUIRE((local || aligned16(g->tasks)) && aligned16(x_next) && aligned16(partial) &&
                    (!x || aligned16(x)) && (!resid || aligned16(resid)) &&
                    (!m_next || aligned16(m_next)) && (!bias || aligned16(bias)),
                MGCN_ERR_ALIGN);
   LayerFwdArgs a{};
-  a.tasks = reinterpret_cast<const int4*>(g->tasks);
-  a.nbr_w = g->nbr_w;
-  a.seg_count = hubs ? g->seg_count : nullptr;
-  a.hub_rows = g->hub_rows;
-  a.hub_seg0 = g->hub_seg0;
-  a.hub_count = g->hub_count;
-  a.rowptr = g->rowptr;
+  if (!local) {
+    a.tasks = reinterpret_cast<const int4*>(g->tasks);
+    a.nbr_w = g->nbr_w;
+    a.seg_count = hubs ? g->seg_count : nullptr;
+    a.hub_rows = g->hub_rows;
+    a.hub_seg0 = g->hub_seg0;
+    a.hub_count = g->hub_count;
+    a.rowptr = g->rowptr;
+    a.hub_threshold = g->hub_threshold;
+  }
   a.m = m; a.x = x; a.resid = resid; a.res_w = res_w; a.res_b = res_b; a.w_next = w_next;
   a.bias = bias; a.pre = pre; a.post = post;
   a.x_next = x_next; a.m_next = m_next; a.hmask = hmask; a.partial = partial;
-  a.n_rows = g->n_rows;
+  a.n_rows = n_rows;
   a.seg_cap = hubs ? g->seg_cap : 0;
   a.hub_cap = hubs ? g->hub_cap : 0;
   a.act_out = act_out;
-  a.hub_threshold = g->hub_threshold;
   const size_t smem = sizeof(float) * kFwdSmemFloats;
   static std::once_flag once;   // per process; the attribute is per function, set on the current device
   cudaError_t attr_err = cudaSuccess;
@@ -829,7 +858,7 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
       attr_err = cudaFuncSetAttribute(k_layer_fwd_hubs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   });
   MGCN_CHECK_CUDA(attr_err);
-  const int64_t max_tiles = ceil_div(g->n_rows + a.seg_cap, 16);
+  const int64_t max_tiles = ceil_div(n_rows + a.seg_cap, 16);
   int64_t blocks = ceil_div(max_tiles, kFwdWarps);
   if (blocks > (int64_t)kNumSMs * MGCN_FWD_MINB) blocks = (int64_t)kNumSMs * MGCN_FWD_MINB;
   MGCN_LAUNCH(k_layer_fwd, (unsigned)blocks, kFwdWarps * 32, smem, stream, a);

@@ -84,16 +84,31 @@ class _ResidualGCNStack32(torch.autograd.Function):
         fwd = graph.fwd
         x0 = x.contiguous()
         xs, hmasks = [x0], []
-        m = ops.linear_impl(x0, layers[0][0], False, row_scale=pre)          # messages of layer 0
         resid0 = ops.linear_impl(x0, layers[0][1], True, layers[0][2])       # x0 R0^T + r0
+        # A first layer of small input width is aggregated BEFORE its transform — (A_hat x) W instead of
+        # A_hat (x W): the gather moves H_in instead of 32 floats per entry, and its backward needs no
+        # transposed aggregation at all:  dW_0 = s^T gs_0  with  s = sum_j pre_j x_j  saved here.
+        agg_first = x0.size(1) <= 4 and not ctx.needs_input_grad[0]
+        s0 = None
+        if agg_first:
+            s0 = ops.spmm_impl(fwd, x0, nbr_scale=pre)                        # [N, H_in]
+            m = ops.linear_impl(s0, layers[0][0], False, row_scale=post)      # z0 = post * (s0 W0)
+        else:
+            m = ops.linear_impl(x0, layers[0][0], False, row_scale=pre)       # messages of layer 0
         for n in range(L):
             w_next = layers[n + 1][0] if n + 1 < L else None
             act_out = 1 if (last_relu or n < L - 1) else 0
-            xn, m, hm = ops.gcn_layer_fwd_impl(
-                fwd, m, xs[n] if n > 0 else None, resid0 if n == 0 else None,
-                layers[n][1], layers[n][2], w_next, None, pre, post, act_out)
+            if n == 0 and agg_first:
+                xn, m, hm = ops.gcn_layer_fwd_impl(None, m, None, resid0, layers[0][1], layers[0][2], w_next,
+                                                   None, pre, None, act_out)
+            else:
+                xn, m, hm = ops.gcn_layer_fwd_impl(
+                    fwd, m, xs[n] if n > 0 else None, resid0 if n == 0 else None,
+                    layers[n][1], layers[n][2], w_next, None, pre, post, act_out)
             xs.append(xn)
             hmasks.append(hm)
+        ctx.agg_first = agg_first
+        ctx.s0 = s0
         ctx.graph, ctx.cfg = graph, (L, last_relu)
         ctx.pre, ctx.post = pre, post
         ctx.save_for_backward(*xs, *hmasks, *params)
@@ -117,13 +132,16 @@ class _ResidualGCNStack32(torch.autograd.Function):
                 dxw, gy, xs[n], layers[n][0], layers[n][1], hmasks[n - 1], post, True)
             grads[3 * n], grads[3 * n + 1], grads[3 * n + 2] = dw, drw, drb
             gy, gs = gy_prev, gs_prev
-        dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
-        grads[0] = ops.linear_wgrad_impl(xs[0], dxw, False, False)[0]
         grads[1], grads[2] = ops.linear_wgrad_impl(xs[0], gy, True, True)
         gx = None
-        if ctx.needs_input_grad[0]:
-            gx = ops.linear_impl(gy, layers[0][1], False)
-            gx = ops.linear_impl(dxw, layers[0][0], True, add=gx)
+        if ctx.agg_first:
+            grads[0] = ops.linear_wgrad_impl(ctx.s0, gs, False, False)[0]    # dW0 = s0^T gs0
+        else:
+            dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
+            grads[0] = ops.linear_wgrad_impl(xs[0], dxw, False, False)[0]
+            if ctx.needs_input_grad[0]:
+                gx = ops.linear_impl(gy, layers[0][1], False)
+                gx = ops.linear_impl(dxw, layers[0][0], True, add=gx)
         return (gx, None, None, None, None, *grads)
 
 

@@ -279,8 +279,8 @@ def masked_scale_impl(g, m1=None, m2=None, row_scale=None):
 
 def gcn_layer_fwd_impl(csr, m, x, resid, res_w, res_b, w_next, bias, pre, post, act_out):
     """one fused forward layer at hidden 32 (mgcn_gcn_layer_fwd): returns (x_next, m_next | None,
-    hmask int32[N])"""
-    _need_cuda(csr.rowptr, m, x, resid, res_w, res_b, w_next, bias, pre, post)
+    hmask int32[N]).  csr None = row-local mode (m is the finished pre-activation)."""
+    _need_cuda(m, x, resid, res_w, res_b, w_next, bias, pre, post)
     m = _f32c(m, "m")
     x = _f32c(x, "x")
     resid = _f32c(resid, "resid")
@@ -290,15 +290,15 @@ def gcn_layer_fwd_impl(csr, m, x, resid, res_w, res_b, w_next, bias, pre, post, 
     bias = _f32c(bias, "bias")
     pre = _f32c(pre, "pre")
     post = _f32c(post, "post")
-    n_rows, H = csr.n_rows, m.size(1)
+    n_rows, H = (csr.n_rows if csr is not None else m.size(0)), m.size(1)
     dev = m.device
     x_next = torch.empty(n_rows, H, dtype=torch.float32, device=dev)
     m_next = torch.empty(n_rows, H, dtype=torch.float32, device=dev) if w_next is not None else None
     hmask = torch.empty(n_rows, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    args = (ctypes.byref(csr.struct()), _ptr(m), m.size(0), _ptr(x), _ptr(resid), _ptr(res_w), _ptr(res_b),
-            _ptr(w_next), _ptr(bias), _ptr(pre), _ptr(post), int(act_out), H, _ptr(x_next), _ptr(m_next),
-            _ptr(hmask))
+    args = (ctypes.byref(csr.struct()) if csr is not None else None, _ptr(m), m.size(0), _ptr(x), _ptr(resid),
+            _ptr(res_w), _ptr(res_b), _ptr(w_next), _ptr(bias), _ptr(pre), _ptr(post), int(act_out), H,
+            _ptr(x_next), _ptr(m_next), _ptr(hmask))
     ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_gcn_layer_fwd(*args, w_, nb, stm), dev)
     _lib.check(lib.mgcn_gcn_layer_fwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
     return x_next, m_next, hmask

@@ -123,3 +123,22 @@ def test_layer_bwd(n, want_prev, tensor_memory):
     assert_parity(gsp, D(post).view(-1, 1) * gy_ref * torch.from_numpy(b), "gs_prev")
     gs2 = ops.mask_bits_scale_impl(d(gy), d(bits), d(post))
     assert_bitexact(gs2, post.view(-1, 1) * torch.where(torch.from_numpy(b > 0), gy, torch.zeros(())), "mask_bits_scale")
+
+
+@pytest.mark.parametrize("n", [1000, 1003, 9])
+def test_layer_fwd_row_local_mode(n):
+    """csr None: m is the finished pre-activation of every row (first layer aggregated before its transform)"""
+    gen = torch.Generator().manual_seed(n + 5)
+    z = torch.randn(n, H, generator=gen)
+    resid = torch.randn(n, H, generator=gen)
+    w_next = torch.randn(H, H, generator=gen) / H ** 0.5
+    pre = torch.rand(n, generator=gen) + 0.1
+    d = lambda t: t.to(DEV)
+    xn, mn, hm = ops.gcn_layer_fwd_impl(None, d(z), None, d(resid), None, None, d(w_next), None, d(pre), None, 1)
+    h = torch.relu(z.double())
+    x_ref = torch.relu(h + resid.double())
+    assert_parity(xn, x_ref, "x_next")
+    assert_parity(mn, pre.double().view(-1, 1) * (x_ref @ w_next.double()), "m_next")
+    bits = hm.cpu().numpy().astype(np.uint32)
+    got = ((bits[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(bool)
+    assert (got == (z.numpy() > 0)).all()
