@@ -257,9 +257,11 @@ int mgcn_mask_bits_scale(const float* gy, const uint32_t* bits, const float* pos
  * offsets int32[G+1] delimit contiguous node ranges (batch vector sorted ascending).
  */
 int mgcn_batch_to_offsets(const int64_t* batch, int64_t N, int64_t G, int32_t* offsets, void* stream);
-/* out[g,:] = sum (mode 0) or mean with count clamped to >= 1 (mode 1) of x[offsets[g]:offsets[g+1],:] */
-int mgcn_segment_reduce(const float* x, int64_t H, const int32_t* offsets, int64_t G, int mode,
-                        float* out, void* stream);
+/* out[g,:] = sum (mode 0) or mean with count clamped to >= 1 (mode 1) of x[offsets[g]:offsets[g+1],:].
+ * N = offsets[G] (total rows, host value: decides how many CTAs share a long segment).  Segments of up to
+ * 64 rows are summed in row order (the reference's scatter order); longer ones in fixed contiguous chunks. */
+int mgcn_segment_reduce(const float* x, int64_t H, const int32_t* offsets, int64_t G, int64_t N, int mode,
+                        float* out, void* workspace, size_t* workspace_bytes, void* stream);
 /* dx[n,:] = gout[g(n),:] (mode 0) or gout[g(n),:] / max(len_g,1) (mode 1) */
 int mgcn_segment_broadcast(const float* gout, int64_t H, const int32_t* offsets, int64_t G,
                            int64_t N, int mode, float* dx, void* stream);

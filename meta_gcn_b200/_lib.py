@@ -83,7 +83,7 @@ SIGNATURES = {
     "mgcn_cross_entropy_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "mgcn_relu_backward": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "mgcn_batch_to_offsets": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
-    "mgcn_segment_reduce": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "mgcn_segment_reduce": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_segment_broadcast": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr]),
 }
 

@@ -392,8 +392,10 @@ def segment_reduce_impl(x, offsets, mode):
     x = _f32c(x, "x")
     G = offsets.numel() - 1
     out = torch.empty(G, x.size(1), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.load().mgcn_segment_reduce(_ptr(x), x.size(1), _ptr(offsets), G, int(mode),
-                                               _ptr(out), _stream()))
+    lib = _lib.load()
+    args = (_ptr(x), x.size(1), _ptr(offsets), G, x.size(0), int(mode), _ptr(out))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_segment_reduce(*args, w_, nb, stm), x.device)
+    _lib.check(lib.mgcn_segment_reduce(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
     return out
 
 

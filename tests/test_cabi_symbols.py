@@ -62,7 +62,7 @@ def test_argument_errors_without_device():
     assert lib.mgcn_linear(None, 5, 0, None, 1, 1, 4, None, None, 0, None, None) == -3
     assert lib.mgcn_linear(None, 5, 4, None, 1, 1, 4, None, None, 0, None, None) == -1
     assert lib.mgcn_gcn_norm(None, 5, 3, None, None) == -3
-    assert lib.mgcn_segment_reduce(None, 8, None, 3, 5, None, None) == -3
+    assert lib.mgcn_segment_reduce(None, 8, None, 3, 100, 5, None, None, ctypes.byref(n), None) == -3
     rc = lib.mgcn_linear_wgrad(None, 1000, 32, None, 32, None, 32, 1, None, None, ctypes.byref(n), None)
     assert rc == 0 and n.value >= 32 * 32 * 4
 

@@ -106,6 +106,20 @@ def test_segment_reduce_large_graphs_and_backward(H):
     assert_bitexact(out_b, out, "deterministic")
 
 
+@pytest.mark.parametrize("sizes", [[150000], [40000, 90000], [30000, 2, 0, 70000]])
+def test_segment_reduce_sliced_long_segments(sizes):
+    """average segment > 4096 rows: several CTAs share a segment (slices added in order), still deterministic"""
+    H = 32
+    n = sum(sizes)
+    batch = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)])
+    x = torch.randn(n, H)
+    for mode in ("mean", "add"):
+        ref = port.scatter_rows(mode, x.double(), batch, len(sizes))
+        out = F_mgcn.pool_by_batch(x.to(DEV), batch.to(DEV), len(sizes), mode)
+        assert_parity(out, ref, f"{mode} pool, sliced")
+        assert_bitexact(F_mgcn.pool_by_batch(x.to(DEV), batch.to(DEV), len(sizes), mode), out, "deterministic")
+
+
 @pytest.mark.parametrize("C", [2, 5, 16])
 @pytest.mark.parametrize("reduction", ["mean", "sum"])
 def test_cross_entropy_matches_torch(C, reduction):
