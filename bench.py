@@ -30,7 +30,7 @@ LAYERS = 12
 HIDDEN = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of k_layer_fwd per launch at the default workload, from
 # the ncu --set full capture summarised in profiles/ (None until captured for the current kernel)
-TRAFFIC_FWD_BYTES = None
+TRAFFIC_FWD_BYTES = 2_089_572_000   # profiles/r1_ncu_k_layer_fwd.csv: 1.1997 GB read + 0.8899 GB written
 CFG = dict(in_channels=1, enc_sizes=[HIDDEN] * LAYERS, num_classes=2, non_linear="relu",
            non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj",
            pred_on="node", nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="add", bias=False)
