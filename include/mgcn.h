@@ -109,6 +109,19 @@ int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by, int 
                    const mgcn_csr_t* out, int32_t* bad_index, void* workspace,
                    size_t* workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Edge preprocessing that defines the botnet edge order: to_undirected_ey +
+ * sort_unique_edges (data_procs/undirected.py:6-35: both directions, unique over row*N+col in lexicographic
+ * (row, col) order, first occurrence kept), add_self_loops_ey (data_procs/loop.py:13-17: (i,i) for every
+ * node appended at the END) and the out-degree feature (data_procs/data_add_degree.py:45-65, float32).
+ * edge_index int64 [2,E]; out int64 [2,cap] (row 0 at out, row 1 at out+cap), cap >= (undirected ? 2E : E)
+ * + (add_loops ? N : 0); count[0] = number of valid columns; perm[k] = index into the doubled edge list
+ * (i < E: edge i, i >= E: edge i-E reversed) of the kept occurrence, -1 for appended loops; deg float[N].
+ * Integer work: bit-exact and independent of scheduling. */
+int mgcn_preprocess_edges(const int64_t* edge_index, int64_t E, int64_t N, int undirected, int add_loops,
+                          int64_t cap, int64_t* out, int32_t* perm, float* deg, int64_t* count,
+                          int32_t* bad_index, void* workspace, size_t* workspace_bytes, void* stream);
+
 /* deg[i] = float(rowptr[i+1]-rowptr[i]): the unweighted scatter_add(ones, row) of
  * gcn_base_models.py:126 and data_procs/data_add_degree.py:60-63. */
 int mgcn_degree_from_rowptr(const int32_t* rowptr, int64_t N, float* deg, void* stream);

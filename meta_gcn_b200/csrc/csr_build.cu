@@ -432,14 +432,15 @@ static int radix_passes_for(uint64_t max_key) {
 // positions 0..n-1.  *sorted_vals points at the buffer holding the sorted positions.
 static int radix_sort_positions(uint32_t* keys_a, uint32_t* keys_b, int32_t* vals_a, int32_t* vals_b,
                                 int64_t n, uint64_t max_key, int32_t* block_hist,
-                                int32_t* tile_sums, const int32_t** sorted_vals, void* stream) {
+                                int32_t* tile_sums, const int32_t** sorted_vals, void* stream,
+                                const int32_t* vals_init = nullptr) {
   const int num_blocks = (int)ceil_div(n > 0 ? n : 1, kRsTile);
   const int64_t hist_len = (int64_t)256 * num_blocks;
   const int passes = radix_passes_for(max_key);
   const uint32_t* kin = keys_a;
   uint32_t* kout = keys_b;
-  const int32_t* vin = nullptr;  // identity on the first pass
-  int32_t* vout = vals_a;
+  const int32_t* vin = vals_init;  // nullptr: identity on the first pass
+  int32_t* vout = (vals_init == vals_a) ? vals_b : vals_a;
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
     MGCN_LAUNCH(k_radix_hist, num_blocks, 256, 0, stream, kin, n, shift, block_hist, num_blocks);
@@ -455,6 +456,90 @@ static int radix_sort_positions(uint32_t* keys_a, uint32_t* keys_b, int32_t* val
   }
   *sorted_vals = vin;
   return MGCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge preprocessing that DEFINES the botnet edge order (data_procs/undirected.py:6-35: both directions,
+// sort-unique by row*N+col keeping the first occurrence; loop.py:13-17: (i,i) for every node appended at
+// the END; data_add_degree.py:45-65: out-degree incl. the loop as float32).  Lexicographic (row, col)
+// order = stable sort by col, then stable sort by row, with the same radix machinery as the structure
+// build; duplicates are adjacent afterwards.  Element i of the (virtually) doubled list is
+// (r[i], c[i]) for i < E and (c[i-E], r[i-E]) for i >= E.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t pre_endpoint(const int64_t* __restrict__ ei, int64_t E, int64_t i, int which) {
+  // which: 0 = row (source), 1 = col (target) of doubled element i
+  const bool flip = i >= E;
+  const int64_t e = flip ? i - E : i;
+  return (which == 0) != flip ? ei[e] : ei[E + e];
+}
+
+__global__ void __launch_bounds__(256)
+    k_pre_keys(const int64_t* __restrict__ ei, int64_t E, int64_t M, int64_t N, int which,
+               const int32_t* __restrict__ pos, uint32_t* __restrict__ keys, int32_t* __restrict__ bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += stride) {
+    const int64_t i = pos ? pos[k] : k;
+    int64_t v = pre_endpoint(ei, E, i, which);
+    if (v < 0 || v >= N) {
+      *bad = 1;
+      v = 0;
+    }
+    keys[k] = (uint32_t)v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_pre_flags(const int64_t* __restrict__ ei, int64_t E, int64_t M, const int32_t* __restrict__ pos,
+                int32_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= M; k += stride) {
+    int32_t f = 0;
+    if (k < M) {
+      f = 1;
+      if (k > 0) {
+        const int64_t a = pos[k], b = pos[k - 1];
+        if (pre_endpoint(ei, E, a, 0) == pre_endpoint(ei, E, b, 0) &&
+            pre_endpoint(ei, E, a, 1) == pre_endpoint(ei, E, b, 1))
+          f = 0;
+      }
+    }
+    flags[k] = f;  // entry M is a zero terminator: the scan yields the number of unique edges
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_pre_compact(const int64_t* __restrict__ ei, int64_t E, int64_t M, const int32_t* __restrict__ pos,
+                  const int32_t* __restrict__ flags, const int32_t* __restrict__ idx, int64_t cap,
+                  int64_t N, int64_t* __restrict__ out, int32_t* __restrict__ perm,
+                  int32_t* __restrict__ degi) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M; k += stride) {
+    if (!flags[k]) continue;
+    const int64_t i = pos[k];
+    const int64_t r = pre_endpoint(ei, E, i, 0), c = pre_endpoint(ei, E, i, 1);
+    const int32_t o = idx[k];
+    out[o] = r;
+    out[cap + o] = c;
+    perm[o] = (int32_t)i;
+    if (r >= 0 && r < N) atomicAdd(degi + r, 1);   // integer count: order-independent (bad ids are flagged)
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_pre_finish(const int32_t* __restrict__ idx, int64_t M, int64_t N, int add_loops, int64_t cap,
+                 int64_t* __restrict__ out, int32_t* __restrict__ perm, const int32_t* __restrict__ degi,
+                 float* __restrict__ deg, int64_t* __restrict__ count) {
+  const int64_t unique = idx[M];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    if (add_loops) {
+      out[unique + i] = i;
+      out[cap + unique + i] = i;
+      perm[unique + i] = -1;
+    }
+    deg[i] = (float)(degi[i] + (add_loops ? 1 : 0));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count = unique + (add_loops ? N : 0);
 }
 
 }  // namespace mgcn
@@ -622,5 +707,65 @@ extern "C" int mgcn_permute_edge_values(const mgcn_csr_t* g, const float* vals_i
   MGCN_REQUIRE(E == 0 || vals_in, MGCN_ERR_NULL);
   MGCN_LAUNCH(k_permute_vals, grid_for(g->nnz_cap, 256), 256, 0, stream, g->perm, g->rowptr,
               g->n_rows, g->nnz_cap, vals_in, E, loop_value, vals_out);
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_preprocess_edges(const int64_t* edge_index, int64_t E, int64_t N, int undirected,
+                                     int add_loops, int64_t cap, int64_t* out, int32_t* perm,
+                                     float* deg, int64_t* count, int32_t* bad_index, void* workspace,
+                                     size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
+  const int64_t kMax = (int64_t(1) << 31) - (int64_t(1) << 20);
+  MGCN_REQUIRE(E >= 0 && N >= 0 && N < kMax, MGCN_ERR_RANGE);
+  const int64_t M = undirected ? 2 * E : E;
+  MGCN_REQUIRE(M + (add_loops ? N : 0) < kMax, MGCN_ERR_RANGE);
+  const int64_t items = M > 0 ? M : 1;
+  const int num_blocks = (int)ceil_div(items, kRsTile);
+  const int64_t hist_len = (int64_t)256 * num_blocks;
+  WorkspaceCarver ws(workspace);
+  uint32_t* keys_a = ws.take<uint32_t>(items);
+  uint32_t* keys_b = ws.take<uint32_t>(items);
+  int32_t* vals_a = ws.take<int32_t>(items);
+  int32_t* vals_b = ws.take<int32_t>(items);
+  int32_t* vals_c = ws.take<int32_t>(items);
+  int32_t* block_hist = ws.take<int32_t>(hist_len);
+  const int64_t scan_len = hist_len > M + 1 ? hist_len : M + 1;
+  int32_t* tile_sums = ws.take<int32_t>(scan_tiles(scan_len));
+  int32_t* flags = ws.take<int32_t>(M + 1);
+  int32_t* idx = ws.take<int32_t>(M + 1);
+  int32_t* degi = ws.take<int32_t>(N > 0 ? N : 1);
+  if (workspace == nullptr) {
+    *workspace_bytes = ws.bytes();
+    return MGCN_OK;
+  }
+  MGCN_REQUIRE(*workspace_bytes >= ws.bytes(), MGCN_ERR_WORKSPACE);
+  MGCN_REQUIRE(out && perm && deg && count && bad_index, MGCN_ERR_NULL);
+  MGCN_REQUIRE(cap >= M + (add_loops ? N : 0), MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(E == 0 || edge_index != nullptr, MGCN_ERR_NULL);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MGCN_CHECK_CUDA(cudaMemsetAsync(bad_index, 0, sizeof(int32_t), st));
+  MGCN_CHECK_CUDA(cudaMemsetAsync(degi, 0, sizeof(int32_t) * (N > 0 ? N : 1), st));
+  const int32_t* pos = nullptr;
+  if (M > 0) {
+    // stable by col, then stable by row  =>  lexicographic (row, col), first occurrence first
+    MGCN_LAUNCH(k_pre_keys, grid_for(M, 256), 256, 0, stream, edge_index, E, M, N, 1, nullptr, keys_a, bad_index);
+    int rc = radix_sort_positions(keys_a, keys_b, vals_a, vals_b, M, (uint64_t)(N > 0 ? N - 1 : 0), block_hist,
+                                  tile_sums, &pos, stream);
+    if (rc != MGCN_OK) return rc;
+    MGCN_CHECK_CUDA(cudaMemcpyAsync(vals_c, pos, sizeof(int32_t) * M, cudaMemcpyDeviceToDevice, st));
+    MGCN_LAUNCH(k_pre_keys, grid_for(M, 256), 256, 0, stream, edge_index, E, M, N, 0, vals_c, keys_a, bad_index);
+    rc = radix_sort_positions(keys_a, keys_b, vals_a, vals_b, M, (uint64_t)(N > 0 ? N - 1 : 0), block_hist,
+                              tile_sums, &pos, stream, vals_c);
+    if (rc != MGCN_OK) return rc;
+  }
+  MGCN_LAUNCH(k_pre_flags, grid_for(M + 1, 256), 256, 0, stream, edge_index, E, M, pos, flags);
+  int rc = exclusive_scan_i32(flags, idx, M + 1, tile_sums, stream);
+  if (rc != MGCN_OK) return rc;
+  if (M > 0) {
+    MGCN_LAUNCH(k_pre_compact, grid_for(M, 256), 256, 0, stream, edge_index, E, M, pos, flags, idx, cap, N, out, perm,
+                degi);
+  }
+  MGCN_LAUNCH(k_pre_finish, grid_for(N > 0 ? N : 1, 256), 256, 0, stream, idx, M, N, add_loops, cap, out, perm, degi,
+              deg, count);
   return MGCN_OK;
 }

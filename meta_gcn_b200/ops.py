@@ -117,6 +117,32 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRES
     return csr
 
 
+def preprocess_edges_impl(edge_index, N, undirected=True, add_loops=True):
+    """mgcn_preprocess_edges: returns (edge_index_out int64 [2, count], deg f32 [N], perm int32 [count]);
+    one host sync to read the number of kept edges (as torch.unique does)."""
+    _need_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("edge_index must be int64 [2,E]")
+    ei = edge_index.contiguous()
+    E, N = ei.size(1), int(N)
+    dev = ei.device
+    cap = (2 * E if undirected else E) + (N if add_loops else 0)
+    out = torch.empty(2, max(cap, 1), dtype=torch.int64, device=dev)
+    perm = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    deg = torch.empty(N, dtype=torch.float32, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    args = (_ptr(ei), E, N, int(bool(undirected)), int(bool(add_loops)), out.size(1), _ptr(out), _ptr(perm),
+            _ptr(deg), _ptr(count), _ptr(bad))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_preprocess_edges(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_preprocess_edges(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    n_out, is_bad = int(count.item()), int(bad.item())
+    if is_bad:
+        raise IndexError("edge_index contains node ids outside [0, num_nodes)")
+    return out[:, :n_out], deg, perm[:n_out]
+
+
 def degree_impl(rowptr):
     _need_cuda(rowptr)
     N = rowptr.numel() - 1
