@@ -47,7 +47,7 @@ struct BwdTcArgs {
   int64_t n_rows;
 };
 
-// shared-memory map (bytes from a 1024-aligned base)
+// shared-memory map (bytes from a 1024-aligned base); one operand stage = 10 images = 80 KB
 constexpr int kOffKDh = 0;                 // K-major images of dxw_hi, dxw_lo, gy_hi, gy_lo
 constexpr int kOffKDl = 1 * kTileB;
 constexpr int kOffKGh = 2 * kTileB;
@@ -55,10 +55,21 @@ constexpr int kOffKGl = 3 * kTileB;
 constexpr int kOffMN = 4 * kTileB;         // MN-major images [dxw_hi | gy_hi | dxw_lo | gy_lo]
 constexpr int kOffMXh = 8 * kTileB;        // MN-major x_hi, x_lo
 constexpr int kOffMXl = 9 * kTileB;
-constexpr int kOffB1 = 10 * kTileB;        // [Wt_hi ; Wt_lo]  64 x 32, K-major
+constexpr int kStageB = 10 * kTileB;
+constexpr int kStages = 2;                 // operand stages == TMEM accumulator buffers
+constexpr int kOffB1 = kStages * kStageB;  // [Wt_hi ; Wt_lo]  64 x 32, K-major
 constexpr int kOffB2 = kOffB1 + 8192;      // [R_hi ; R_lo]
-constexpr int kOffMisc = kOffB2 + 8192;    // barrier, tmem slot, xbits[64], dr reduction scratch
-constexpr int kBwdTcSmem = kOffMisc + 64 + 256 + 64 * 32 * 4 + 1024;
+constexpr int kOffMisc = kOffB2 + 8192;    // barriers (full[2], done[2], tfree[2]), tmem slot
+constexpr int kOffXbits = kOffMisc + 64;   // [4][64] words: x > 0 of the tile's rows (4 tiles deep)
+constexpr int kLdo = 36;                   // floats per staged output row (144 bytes)
+constexpr int kOffOut = kOffXbits + 4 * 64 * 4;     // [2 buffers][gy_prev | gs_prev][64 rows][kLdo] staged outputs
+constexpr int kOffDrRed = kOffOut;         // [128 slots][32] dr reduction scratch (after the last tile)
+constexpr int kBwdTcSmem = kOffOut + 2 * 2 * kTRows * kLdo * 4 + 1024;
+constexpr int kTmemBufCols = 256;          // accumulator columns per buffer (160 used)
+
+constexpr int kEpiWarps = 8;               // warps 0..7   TMEM -> registers -> gy_prev / gs_prev, running dW / dR rows
+constexpr int kProdWarps = 16;             // warps 8..23  global -> split -> operand images (two sets of 8, one per stage)
+constexpr int kBwdTcThreads = 32 * (kEpiWarps + kProdWarps + 1);   // warp 24 issues the tcgen05.mma
 
 __device__ __forceinline__ int k_image_off(int r, int q) {      // bytes; 16-byte chunk q of row r, interleaved
   return ((r >> 3) << 10) + (q << 7) + ((r & 7) << 4);
@@ -79,6 +90,17 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   lo = make_float4(l[0], l[1], l[2], l[3]);
 }
 
+struct F8 {
+  float4 lo, hi;
+};
+__device__ __forceinline__ F8 ld_f8_hint(const float* p, uint64_t pol) {   // one LDG.256, streamed
+  F8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -92,19 +114,28 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr));
 }
 
-__global__ void __launch_bounds__(256, 2) k_layer_bwd_tc(const BwdTcArgs a) {
+// Warp-specialised, one persistent CTA per SM.  Tile `it` of a CTA uses operand stage / accumulator buffer
+// s = it & 1 for the (it >> 1)-th time; three mbarriers per stage carry the hand-offs:
+//   full[s]   producers -> MMA warp        the 10 images of the tile are written (8 arrivals, one per warp)
+//   done[s]   tensor core -> everyone      tcgen05.commit: accumulators ready, images free again
+//   tfree[s]  epilogue -> MMA warp         accumulator buffer s has been read (8 arrivals)
+// so the split of tile it+1, the tensor-core work of tile it+1 and the epilogue of tile it overlap.
+__global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment as an offset on the __shared__ array (keeps the shared address space: STS, not ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffMisc);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 16);
-  uint32_t* xbits = reinterpret_cast<uint32_t*>(smem + kOffMisc + 64);
-  float* dr_red = reinterpret_cast<float*>(smem + kOffMisc + 64 + 256);   // [64 slots][32]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffMisc);
+  uint64_t* bar_done = bar_full + 2;
+  uint64_t* bar_tfree = bar_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 48);
+  uint32_t* xbits = reinterpret_cast<uint32_t*>(smem + kOffXbits);
+  float* dr_red = reinterpret_cast<float*>(smem + kOffDrRed);   // [128 slots][32]
+  float* stage_out = reinterpret_cast<float*>(smem + kOffOut);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool want_prev = a.gy_prev != nullptr;
 
   // weight images: B1(n, k) = W[n][k] (hi rows 0..31, lo rows 32..63); B2(n, k) = R[k][n]
-  for (int i = tid; i < 32 * 32; i += 256) {
+  for (int i = tid; i < 32 * 32; i += kBwdTcThreads) {
     const int n = i >> 5, k = i & 31;
     const float w1 = __ldg(a.w + n * 32 + k), w2 = __ldg(a.res_w + k * 32 + n);
     const float h1 = __uint_as_float(round_tf32_bits(__float_as_uint(w1)));
@@ -118,190 +149,263 @@ __global__ void __launch_bounds__(256, 2) k_layer_bwd_tc(const BwdTcArgs a) {
     b2[o_lo] = __uint_as_float(round_tf32_bits(__float_as_uint(w2 - h2)));
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full + s, kProdWarps / 2);
+      mbar_init(bar_done + s, 1);
+      mbar_init(bar_tfree + s, kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight images -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const uint64_t pol = policy_evict_first();
-
-  // this thread's elements of a tile: row r0, 16-byte chunks q0 and q0 + 4 (the four lanes with equal lane % 8
-  // cover one row's 8 chunks)
-  const int r0 = (lane & 7) + 8 * warp, q0 = lane >> 3;
   const int64_t n_tiles = (a.n_rows + kTRows - 1) / kTRows;
-  float4 cur[3][2], nxt[3][2];
-  auto load_tile = [&](float4 (&dst)[3][2], int64_t tile) {
-    const float* src[3] = {a.dxw, a.gy, a.x};
-#pragma unroll
-    for (int arr = 0; arr < 3; ++arr)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int64_t gr = tile * kTRows + r0;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tile < n_tiles && gr < a.n_rows) v = __ldg(reinterpret_cast<const float4*>(src[arr] + gr * kTH + 4 * (q0 + 4 * i)));
-        dst[arr][i] = v;
-      }
-  };
 
-  float acc_t[32];   // warps 4..7: running transposed-product row of this TMEM lane
-#pragma unroll
-  for (int t = 0; t < 32; ++t) acc_t[t] = 0.f;
-  float acc_dr[2][4];
+  float acc_dr[2][4];   // producers: column sums of gy over this thread's rows
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc_dr[i][t] = 0.f;
-
-  const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32), idT = umma_idesc_tf32(128, 64, 1, 1);
-  const uint32_t sbase = smem_u32(smem);
-  // descriptor templates: the start-address field (bits 0..13, 16-byte units) is added per k step
-  const uint64_t dK = umma_desc(sbase, 128, 1024, 0), dM = umma_desc(sbase, kTileB, 512, 1);
-  uint32_t phase = 0;
-  int64_t tile = blockIdx.x;
-  load_tile(cur, tile);
-  for (; tile < n_tiles; tile += gridDim.x) {
-    load_tile(nxt, tile + gridDim.x);
-    // ---- split once, write the operand images ----
-    {
-      const int r = r0;
-      uint32_t b = 0;
+  float acc_t[16];      // epilogue: running transposed-product row of this TMEM lane, 16 of its 32 columns
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int q = q0 + 4 * i;
-        const int ko = k_image_off(r, q), mo = mn_image_off(r, q);
-        float4 hi, lo;
-        split4(cur[0][i], hi, lo);                 // dxw
-        *reinterpret_cast<float4*>(smem + kOffKDh + ko) = hi;
-        *reinterpret_cast<float4*>(smem + kOffKDl + ko) = lo;
-        *reinterpret_cast<float4*>(smem + kOffMN + 0 * kTileB + mo) = hi;
-        *reinterpret_cast<float4*>(smem + kOffMN + 2 * kTileB + mo) = lo;
-        const float4 gv = cur[1][i];               // gy
-        acc_dr[i][0] += gv.x; acc_dr[i][1] += gv.y; acc_dr[i][2] += gv.z; acc_dr[i][3] += gv.w;
-        split4(gv, hi, lo);
-        *reinterpret_cast<float4*>(smem + kOffKGh + ko) = hi;
-        *reinterpret_cast<float4*>(smem + kOffKGl + ko) = lo;
-        *reinterpret_cast<float4*>(smem + kOffMN + 1 * kTileB + mo) = hi;
-        *reinterpret_cast<float4*>(smem + kOffMN + 3 * kTileB + mo) = lo;
-        const float4 xv = cur[2][i];               // x
-        split4(xv, hi, lo);
-        *reinterpret_cast<float4*>(smem + kOffMXh + mo) = hi;
-        *reinterpret_cast<float4*>(smem + kOffMXl + mo) = lo;
-        b |= ((xv.x > 0.f ? 1u : 0u) | (xv.y > 0.f ? 2u : 0u) | (xv.z > 0.f ? 4u : 0u) | (xv.w > 0.f ? 8u : 0u)) << (4 * q);
+  for (int t = 0; t < 16; ++t) acc_t[t] = 0.f;
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // ---------------- producers: global -> registers (one tile ahead) -> hi/lo split -> images ----------------
+    // Two sets of 8 warps: set p produces the tiles with it % 2 == p, i.e. always into stage p, so a set has
+    // two tile periods for one tile.  Lane 8 qq + j of warp w owns row 8 w + j and the 32-byte chunk pair qq
+    // (one LDG.256 per array); the two 16-byte chunks are stored in the order (j >> 2) ? (hi, lo) : (lo, hi) so
+    // that the 8 lanes of a quarter warp hit 8 different 16-byte bank groups in the K-major images (bank group
+    // = row & 7) and in the swizzled MN-major ones (bank group = (((q >> 1) ^ (row & 3)) << 1) | (q & 1)).
+    const int pset = (warp - kEpiWarps) >> 3, pwarp = (warp - kEpiWarps) & 7;
+    const int j = lane & 7, qq = lane >> 3, flip = j >> 2;
+    const int r0 = 8 * pwarp + j;
+    const int qa = 2 * qq + flip, qb = 2 * qq + (flip ^ 1);
+    const int ko_a = k_image_off(r0, qa), ko_b = k_image_off(r0, qb);
+    const int mo_a = mn_image_off(r0, qa), mo_b = mn_image_off(r0, qb);
+    F8 cur[3], nxt[3];
+    auto load_tile = [&](F8 (&dst)[3], int64_t tile) {
+      const float* src[3] = {a.dxw, a.gy, a.x};
+      const int64_t gr = tile * kTRows + r0;
+      const bool ok = tile < n_tiles && gr < a.n_rows;
+#pragma unroll
+      for (int arr = 0; arr < 3; ++arr) {
+        F8 v;
+        v.lo = v.hi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) v = ld_f8_hint(src[arr] + gr * kTH + 8 * qq, pol);
+        dst[arr] = v;
       }
+    };
+    unsigned char* st = smem + pset * kStageB;
+    int it = pset;
+    int64_t tile = blockIdx.x + (int64_t)pset * gridDim.x;
+    load_tile(cur, tile);
+    for (; tile < n_tiles; tile += 2 * (int64_t)gridDim.x, it += 2) {
+      load_tile(nxt, tile + 2 * (int64_t)gridDim.x);
+      const int use = it >> 1;
+      if (use >= 1) mbar_wait(bar_done + pset, (use - 1) & 1);   // the tensor core has consumed this stage's previous tile
+      float4 c0, c1, hi, lo;
+      // dxw
+      c0 = flip ? cur[0].hi : cur[0].lo;
+      c1 = flip ? cur[0].lo : cur[0].hi;
+      split4(c0, hi, lo);
+      *reinterpret_cast<float4*>(st + kOffKDh + ko_a) = hi;
+      *reinterpret_cast<float4*>(st + kOffKDl + ko_a) = lo;
+      *reinterpret_cast<float4*>(st + kOffMN + 0 * kTileB + mo_a) = hi;
+      *reinterpret_cast<float4*>(st + kOffMN + 2 * kTileB + mo_a) = lo;
+      split4(c1, hi, lo);
+      *reinterpret_cast<float4*>(st + kOffKDh + ko_b) = hi;
+      *reinterpret_cast<float4*>(st + kOffKDl + ko_b) = lo;
+      *reinterpret_cast<float4*>(st + kOffMN + 0 * kTileB + mo_b) = hi;
+      *reinterpret_cast<float4*>(st + kOffMN + 2 * kTileB + mo_b) = lo;
+      // gy
+      {
+        const float4 g0 = cur[1].lo, g1 = cur[1].hi;
+        acc_dr[0][0] += g0.x; acc_dr[0][1] += g0.y; acc_dr[0][2] += g0.z; acc_dr[0][3] += g0.w;
+        acc_dr[1][0] += g1.x; acc_dr[1][1] += g1.y; acc_dr[1][2] += g1.z; acc_dr[1][3] += g1.w;
+      }
+      c0 = flip ? cur[1].hi : cur[1].lo;
+      c1 = flip ? cur[1].lo : cur[1].hi;
+      split4(c0, hi, lo);
+      *reinterpret_cast<float4*>(st + kOffKGh + ko_a) = hi;
+      *reinterpret_cast<float4*>(st + kOffKGl + ko_a) = lo;
+      *reinterpret_cast<float4*>(st + kOffMN + 1 * kTileB + mo_a) = hi;
+      *reinterpret_cast<float4*>(st + kOffMN + 3 * kTileB + mo_a) = lo;
+      split4(c1, hi, lo);
+      *reinterpret_cast<float4*>(st + kOffKGh + ko_b) = hi;
+      *reinterpret_cast<float4*>(st + kOffKGl + ko_b) = lo;
+      *reinterpret_cast<float4*>(st + kOffMN + 1 * kTileB + mo_b) = hi;
+      *reinterpret_cast<float4*>(st + kOffMN + 3 * kTileB + mo_b) = lo;
+      // x
+      uint32_t b;
+      {
+        const float4 x0 = cur[2].lo, x1 = cur[2].hi;
+        b = (x0.x > 0.f ? 1u : 0u) | (x0.y > 0.f ? 2u : 0u) | (x0.z > 0.f ? 4u : 0u) | (x0.w > 0.f ? 8u : 0u) |
+            (x1.x > 0.f ? 16u : 0u) | (x1.y > 0.f ? 32u : 0u) | (x1.z > 0.f ? 64u : 0u) | (x1.w > 0.f ? 128u : 0u);
+        b <<= 8 * qq;
+      }
+      c0 = flip ? cur[2].hi : cur[2].lo;
+      c1 = flip ? cur[2].lo : cur[2].hi;
+      split4(c0, hi, lo);
+      *reinterpret_cast<float4*>(st + kOffMXh + mo_a) = hi;
+      *reinterpret_cast<float4*>(st + kOffMXl + mo_a) = lo;
+      split4(c1, hi, lo);
+      *reinterpret_cast<float4*>(st + kOffMXh + mo_b) = hi;
+      *reinterpret_cast<float4*>(st + kOffMXl + mo_b) = lo;
       b |= __shfl_xor_sync(0xffffffffu, b, 8);
       b |= __shfl_xor_sync(0xffffffffu, b, 16);
-      if (q0 == 0) xbits[r] = b;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (want_prev) {
+      if (qq == 0) xbits[(it & 3) * 64 + r0] = b;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + pset);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
-          const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
-          umma_tf32(tmem + 0, dK + ((kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
-          umma_tf32(tmem + 0, dK + ((kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
-          umma_tf32(tmem + 64, dK + ((kOffKDl >> 4) + ko), b1, idG32, k > 0);   // dxw_lo Wt_hi
-          umma_tf32(tmem + 64, dK + ((kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
+      for (int arr = 0; arr < 3; ++arr) cur[arr] = nxt[arr];
+    }
+  } else if (warp == kEpiWarps + kProdWarps) {
+    // ---------------- MMA warp: lane 0 issues 24 tcgen05.mma per tile ----------------
+    const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32), idT = umma_idesc_tf32(128, 64, 1, 1);
+    const uint32_t sbase = smem_u32(smem);
+    // descriptor templates: the start-address field (bits 0..13, 16-byte units) is added per stage and k step
+    const uint64_t dK = umma_desc(sbase, 128, 1024, 0), dM = umma_desc(sbase, kTileB, 512, 1);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1, use = it >> 1;
+      mbar_wait(bar_full + s, use & 1);
+      if (it >= 2) mbar_wait(bar_tfree + s, (use - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t tb = tmem + s * kTmemBufCols;
+        const uint32_t so = (uint32_t)(s * kStageB) >> 4;
+        if (want_prev) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
+            const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
+            umma_tf32(tb + 0, dK + (so + (kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
+            umma_tf32(tb + 0, dK + (so + (kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
+            umma_tf32(tb + 64, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, k > 0);   // dxw_lo Wt_hi
+            umma_tf32(tb + 64, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kTRows / 8; ++k) {
+          const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
+          // B = [x_hi | x_lo]: two 32-column MN atoms one image apart -> D1 | D2 in one N = 64 instruction
+          umma_tf32(tb + 96, dM + (so + (kOffMN >> 4) + ko), dM + (so + (kOffMXh >> 4) + ko), idT, k > 0);
+        }
+        umma_commit(bar_done + s);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue warps: quarter = warp & 3 of the TMEM lanes, column half = warp >> 2 ----------------
+    const int quarter = warp & 3, half = warp >> 2;
+    const int my_row = 16 * quarter + (lane & 15);   // M = 64 accumulators live in lanes 0..15 of each quarter
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1, use = it >> 1;
+      const int64_t g_row = tile * kTRows + my_row;
+      const bool fin = want_prev && lane < 16 && g_row < a.n_rows;
+      uint32_t hbits = 0;
+      float postv = 1.f;
+      if (fin) {
+        hbits = __ldg(a.hmask_prev + g_row);
+        if (a.post) postv = __ldg(a.post + g_row);
+      }
+      mbar_wait(bar_done + s, use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t lane_addr = tmem + s * kTmemBufCols + ((uint32_t)(32 * quarter) << 16);
+      {
+        // transposed products of this tile -> running fp32 sums (RN)
+        uint32_t d1[16], d2[16];
+        tmem_ld16(lane_addr + 96 + 16 * half, d1);
+        tmem_ld16(lane_addr + 128 + 16 * half, d2);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc_t[t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
+      }
+      if (want_prev) {
+        // G row of this lane, columns [16 half, 16 half + 16) -> staging tile in shared memory (rows padded to 144
+        // bytes: the 8 rows of a quarter warp land in 8 different 16-byte bank groups)
+        const uint32_t xb = xbits[(it & 3) * 64 + my_row];
+        float* sg = stage_out + (it & 1) * (2 * kTRows * kLdo);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = 16 * half + 8 * h;
+          uint32_t m[8], c1[8], c2[8];
+          tmem_ld8(lane_addr + 0 + c0, m);
+          tmem_ld8(lane_addr + 32 + c0, c1);
+          tmem_ld8(lane_addr + 64 + c0, c2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (lane < 16) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              float g[4], sv[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int c = c0 + 4 * q + t;
+                const float gv = __uint_as_float(m[4 * q + t]) + (__uint_as_float(c1[4 * q + t]) + __uint_as_float(c2[4 * q + t]));
+                g[t] = ((xb >> c) & 1u) ? gv : 0.f;
+                sv[t] = ((hbits >> c) & 1u) ? g[t] * postv : 0.f;
+              }
+              *reinterpret_cast<float4*>(sg + my_row * kLdo + c0 + 4 * q) = make_float4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<float4*>(sg + (kTRows + my_row) * kLdo + c0 + 4 * q) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            }
+          }
         }
       }
+      // accumulator buffer s is free for the tile after next
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tfree + s);
+      if (want_prev) {
+        // staged rows -> global, 4 whole rows (512 contiguous bytes) per store instruction; warp w owns rows 8w..8w+7
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        const float* sg = stage_out + (it & 1) * (2 * kTRows * kLdo);
 #pragma unroll
-      for (int k = 0; k < kTRows / 8; ++k) {
-        const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
-        // B = [x_hi | x_lo]: two 32-column MN atoms one image apart -> D1 | D2 in one N = 64 instruction
-        umma_tf32(tmem + 96, dM + ((kOffMN >> 4) + ko), dM + ((kOffMXh >> 4) + ko), idT, k > 0);
-      }
-      umma_commit(bar);
-    }
-    // scalars of the row this thread finishes below (warps 0..3, lanes 0..15: M = 64 accumulators live in
-    // lanes 0..15 of every 32-lane TMEM quarter)
-    const int my_row = 16 * (warp & 3) + (lane & 15);
-    const int64_t g_row = tile * kTRows + my_row;
-    const bool fin = want_prev && warp < 4 && lane < 16 && g_row < a.n_rows;
-    uint32_t hbits = 0;
-    float postv = 1.f;
-    if (fin) {
-      hbits = __ldg(a.hmask_prev + g_row);
-      if (a.post) postv = __ldg(a.post + g_row);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    if (warp >= 4) {
-      // transposed products of this tile -> running fp32 sums (RN)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t d1[16], d2[16];
-        tmem_ld16(lane_addr + 96 + 16 * h, d1);
-        tmem_ld16(lane_addr + 128 + 16 * h, d2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int t = 0; t < 16; ++t) acc_t[16 * h + t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
-      }
-    } else if (want_prev) {
-      // G row of this lane -> gy_prev, gs_prev rows, 8 columns at a time
-      const uint32_t xb = xbits[my_row];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        uint32_t m[8], c1[8], c2[8];
-        tmem_ld8(lane_addr + 0 + 8 * h, m);
-        tmem_ld8(lane_addr + 32 + 8 * h, c1);
-        tmem_ld8(lane_addr + 64 + 8 * h, c2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (fin) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float g[4], s[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int c = 8 * h + 4 * q + t;
-              const float gv = __uint_as_float(m[4 * q + t]) + (__uint_as_float(c1[4 * q + t]) + __uint_as_float(c2[4 * q + t]));
-              g[t] = ((xb >> c) & 1u) ? gv : 0.f;
-              s[t] = ((hbits >> c) & 1u) ? g[t] * postv : 0.f;
-            }
-            st_f4_hint(a.gy_prev + g_row * kTH + 8 * h + 4 * q, make_float4(g[0], g[1], g[2], g[3]), pol);
-            st_f4_hint(a.gs_prev + g_row * kTH + 8 * h + 4 * q, make_float4(s[0], s[1], s[2], s[3]), pol);
+        for (int i = 0; i < 2; ++i) {
+          const int r = 8 * warp + 4 * i + (lane >> 3), q = lane & 7;
+          const int64_t gr = tile * kTRows + r;
+          if (gr < a.n_rows) {
+            st_f4_hint(a.gy_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sg + r * kLdo + 4 * q), pol);
+            st_f4_hint(a.gs_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sg + (kTRows + r) * kLdo + 4 * q), pol);
           }
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();   // TMEM and xbits reads done; images may be rewritten
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // per-CTA partials of the transposed products: row = TMEM lane, this warp's 16 columns
+    float* p = a.part_t + ((int64_t)blockIdx.x * 128 + 32 * quarter + lane) * 32 + 16 * half;
 #pragma unroll
-    for (int arr = 0; arr < 3; ++arr)
-#pragma unroll
-      for (int i = 0; i < 2; ++i) cur[arr][i] = nxt[arr][i];
+    for (int t = 0; t < 16; t += 4) *reinterpret_cast<float4*>(p + t) = make_float4(acc_t[t], acc_t[t + 1], acc_t[t + 2], acc_t[t + 3]);
   }
-  // ---- per-CTA partials ----
-  if (warp >= 4) {
-    float* p = a.part_t + ((int64_t)blockIdx.x * 128 + 32 * (warp & 3) + lane) * 32;
+  __syncthreads();   // the staging tiles (aliased by dr_red) are no longer read
+  // dr[c]: a producer thread holds columns 8 qq + 4 i + t summed over its rows; fixed-order sum over the 128 row slots
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    const int slot = (warp - kEpiWarps) * 8 + (lane & 7), qq = lane >> 3;
 #pragma unroll
-    for (int t = 0; t < 32; t += 4) *reinterpret_cast<float4*>(p + t) = make_float4(acc_t[t], acc_t[t + 1], acc_t[t + 2], acc_t[t + 3]);
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dr_red[slot * 32 + 8 * qq + 4 * i + t] = acc_dr[i][t];
   }
-  // dr[c]: this thread holds columns 4*(q0 + 4i) + t summed over its rows; fixed-order sum over the 64 row slots
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) dr_red[((warp * 8 + (lane & 7)) * 8 + (q0 + 4 * i)) * 4 + t] = acc_dr[i][t];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < 32) {
     float s = 0.f;
-    for (int slot = 0; slot < 64; ++slot) s += dr_red[slot * 32 + tid];
+    for (int slot = 0; slot < 8 * kProdWarps; ++slot) s += dr_red[slot * 32 + tid];
     a.part_b[(int64_t)blockIdx.x * 32 + tid] = s;
   }
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
 }
 
 // dW[j][c] = sum_p part[p][c][j] + part[p][64 + c][j];   dR[c][j] = sum_p part[p][32 + c][j] + part[p][96 + c][j]
@@ -331,7 +435,7 @@ __global__ void __launch_bounds__(256) k_bwd_tc_reduce(const float* __restrict__
 
 int bwd_tc_grid(int64_t N) {
   const int64_t tiles = ceil_div(N > 0 ? N : 1, kTRows);
-  return (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  return (int)(tiles < kNumSMs ? tiles : kNumSMs);
 }
 
 size_t bwd_tc_workspace_floats(int64_t N) { return (size_t)bwd_tc_grid(N) * (128 * 32 + 32); }
@@ -352,7 +456,7 @@ int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const
     attr_err = cudaFuncSetAttribute(k_layer_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
   });
   MGCN_CHECK_CUDA(attr_err);
-  MGCN_LAUNCH(k_layer_bwd_tc, P, 256, kBwdTcSmem, stream, a);
+  MGCN_LAUNCH(k_layer_bwd_tc, P, kBwdTcThreads, kBwdTcSmem, stream, a);
   MGCN_LAUNCH(k_bwd_tc_reduce, 64, 256, 0, stream, a.part_t, P, dw, d_res_w);
   return launch_reduce_partials(a.part_b, P, 32, 32, d_res_b, 0, 1, stream);
 }

@@ -180,6 +180,29 @@ def case_preprocess():
                         deg=deg.numpy(), num_nodes=np.array(n))
 
 
+def case_metrics():
+    """binary metrics of src/gcn_meta/optim/metrics.py on seeded logits / labels (train_botnet.py:296-305)"""
+    met = load_file("ref_metrics", os.path.join(REF, "src", "gcn_meta", "optim", "metrics.py"))
+    out = {}
+    for k, (n, p1, seed) in enumerate([(5000, 0.07, 0), (300, 0.5, 1), (64, 0.0, 2)]):
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.randn(n, 2, generator=g)
+        y = (torch.rand(n, generator=g) < p1).long()
+        logits[:, 1] += 2.0 * y.float() - 1.0
+        pred = logits.max(1)[1]
+        vals = [met.accuracy(pred, y), met.true_positive(pred, y), met.false_positive(pred, y),
+                met.true_negative(pred, y), met.false_negative(pred, y)]
+        for fn in (met.recall, met.precision, met.f1_score, met.false_positive_rate, met.false_negative_rate):
+            try:
+                vals.append(float(fn(pred, y)))
+            except ZeroDivisionError:
+                vals.append(float("nan"))
+        out[f"logits{k}"] = logits.numpy()
+        out[f"y{k}"] = y.numpy()
+        out[f"vals{k}"] = np.array(vals, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -199,6 +222,7 @@ def main():
                   graph_slices=[0, 160])  # multi-graph batches hit a shape bug in gcn_model.py:123 unless B == C
     case_primitives()
     case_preprocess()
+    case_metrics()
     case_kernel_net("kernel_gcn", "gcn", "GCN", 10)
     case_kernel_net("kernel_gcn_jk", "gcn", "GCNWithJK", 11)
     case_kernel_net("kernel_gin0", "gin", "GIN0", 12)
