@@ -63,13 +63,13 @@ constexpr int kOffMisc = kOffB2 + 8192;    // barriers (full[2], done[2], tfree[
 constexpr int kOffXbits = kOffMisc + 64;   // [4][64] words: x > 0 of the tile's rows (4 tiles deep)
 constexpr int kLdo = 36;                   // floats per staged output row (144 bytes)
 constexpr int kOffOut = kOffXbits + 4 * 64 * 4;     // [2 buffers][gy_prev | gs_prev][64 rows][kLdo] staged outputs
-constexpr int kOffDrRed = kOffOut;         // [128 slots][32] dr reduction scratch (after the last tile)
-constexpr int kBwdTcSmem = kOffOut + 2 * 2 * kTRows * kLdo * 4 + 1024;
+constexpr int kOffDrRed = kOffOut + 2 * 2 * kTRows * kLdo * 4;   // [16 producer warps][32] dr partials
+constexpr int kBwdTcSmem = kOffDrRed + 16 * 32 * 4 + 1024;
 constexpr int kTmemBufCols = 256;          // accumulator columns per buffer (160 used)
 
 constexpr int kEpiWarps = 8;               // warps 0..7   TMEM -> registers -> gy_prev / gs_prev, running dW / dR rows
 constexpr int kProdWarps = 16;             // warps 8..23  global -> split -> operand images (two sets of 8, one per stage)
-constexpr int kBwdTcThreads = 32 * (kEpiWarps + kProdWarps + 1);   // warp 24 issues the tcgen05.mma
+constexpr int kBwdTcThreads = 32 * (kEpiWarps + kProdWarps);       // warp 0 of a producer set issues its tcgen05.mma
 
 __device__ __forceinline__ int k_image_off(int r, int q) {      // bytes; 16-byte chunk q of row r, interleaved
   return ((r >> 3) << 10) + (q << 7) + ((r & 7) << 4);
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
   uint64_t* bar_tfree = bar_full + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 48);
   uint32_t* xbits = reinterpret_cast<uint32_t*>(smem + kOffXbits);
-  float* dr_red = reinterpret_cast<float*>(smem + kOffDrRed);   // [128 slots][32]
+  float* dr_red = reinterpret_cast<float*>(smem + kOffDrRed);   // [16 warps][32]
   float* stage_out = reinterpret_cast<float*>(smem + kOffOut);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool want_prev = a.gy_prev != nullptr;
@@ -169,15 +169,6 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
   const uint64_t pol = policy_evict_first();
   const int64_t n_tiles = (a.n_rows + kTRows - 1) / kTRows;
 
-  float acc_dr[2][4];   // producers: column sums of gy over this thread's rows
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) acc_dr[i][t] = 0.f;
-  float acc_t[16];      // epilogue: running transposed-product row of this TMEM lane, 16 of its 32 columns
-#pragma unroll
-  for (int t = 0; t < 16; ++t) acc_t[t] = 0.f;
-
   if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
     // ---------------- producers: global -> registers (one tile ahead) -> hi/lo split -> images ----------------
     // Two sets of 8 warps: set p produces the tiles with it % 2 == p, i.e. always into stage p, so a set has
@@ -191,6 +182,11 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
     const int qa = 2 * qq + flip, qb = 2 * qq + (flip ^ 1);
     const int ko_a = k_image_off(r0, qa), ko_b = k_image_off(r0, qb);
     const int mo_a = mn_image_off(r0, qa), mo_b = mn_image_off(r0, qb);
+    float acc_dr[2][4];   // column sums of gy over this thread's rows
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc_dr[i][t] = 0.f;
     F8 cur[3], nxt[3];
     auto load_tile = [&](F8 (&dst)[3], int64_t tile) {
       const float* src[3] = {a.dxw, a.gy, a.x};
@@ -205,6 +201,9 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       }
     };
     unsigned char* st = smem + pset * kStageB;
+    const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32), idT = umma_idesc_tf32(128, 64, 1, 1);
+    // descriptor templates: the start-address field (bits 0..13, 16-byte units) is added per stage and k step
+    const uint64_t dK = umma_desc(smem_u32(smem), 128, 1024, 0), dM = umma_desc(smem_u32(smem), kTileB, 512, 1);
     int it = pset;
     int64_t tile = blockIdx.x + (int64_t)pset * gridDim.x;
     load_tile(cur, tile);
@@ -266,48 +265,57 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + pset);
+      if (pwarp == 0) {
+        // this warp also issues the tile's 24 tcgen05.mma (lane 0) once the other 7 warps of the set have arrived
+        // and the epilogue has drained accumulator buffer pset
+        mbar_wait(bar_full + pset, use & 1);
+        if (use >= 1) mbar_wait(bar_tfree + pset, (use - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t tb = tmem + pset * kTmemBufCols;
+          const uint32_t so = (uint32_t)(pset * kStageB) >> 4;
+          if (want_prev) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
+              const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
+              umma_tf32(tb + 0, dK + (so + (kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
+              umma_tf32(tb + 0, dK + (so + (kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
+              umma_tf32(tb + 64, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, k > 0);   // dxw_lo Wt_hi
+              umma_tf32(tb + 64, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kTRows / 8; ++k) {
+            const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
+            // B = [x_hi | x_lo]: two 32-column MN atoms one image apart -> D1 | D2 in one N = 64 instruction
+            umma_tf32(tb + 96, dM + (so + (kOffMN >> 4) + ko), dM + (so + (kOffMXh >> 4) + ko), idT, k > 0);
+          }
+          umma_commit(bar_done + pset);
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int arr = 0; arr < 3; ++arr) cur[arr] = nxt[arr];
     }
-  } else if (warp == kEpiWarps + kProdWarps) {
-    // ---------------- MMA warp: lane 0 issues 24 tcgen05.mma per tile ----------------
-    const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32), idT = umma_idesc_tf32(128, 64, 1, 1);
-    const uint32_t sbase = smem_u32(smem);
-    // descriptor templates: the start-address field (bits 0..13, 16-byte units) is added per stage and k step
-    const uint64_t dK = umma_desc(sbase, 128, 1024, 0), dM = umma_desc(sbase, kTileB, 512, 1);
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1, use = it >> 1;
-      mbar_wait(bar_full + s, use & 1);
-      if (it >= 2) mbar_wait(bar_tfree + s, (use - 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t tb = tmem + s * kTmemBufCols;
-        const uint32_t so = (uint32_t)(s * kStageB) >> 4;
-        if (want_prev) {
+    // dr[c]: this thread holds columns 8 qq + 4 i + t summed over its rows; rows of the warp are added in a fixed
+    // butterfly order, the 16 warps by one thread per column below
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
-            const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
-            umma_tf32(tb + 0, dK + (so + (kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
-            umma_tf32(tb + 0, dK + (so + (kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
-            umma_tf32(tb + 64, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, k > 0);   // dxw_lo Wt_hi
-            umma_tf32(tb + 64, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
-          }
-        }
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int k = 0; k < kTRows / 8; ++k) {
-          const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
-          // B = [x_hi | x_lo]: two 32-column MN atoms one image apart -> D1 | D2 in one N = 64 instruction
-          umma_tf32(tb + 96, dM + (so + (kOffMN >> 4) + ko), dM + (so + (kOffMXh >> 4) + ko), idT, k > 0);
-        }
-        umma_commit(bar_done + s);
+      for (int t = 0; t < 4; ++t) {
+        float v = acc_dr[i][t];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (j == 0) dr_red[(warp - kEpiWarps) * 32 + 8 * qq + 4 * i + t] = v;
       }
-      __syncwarp();
-    }
   } else {
     // ---------------- epilogue warps: quarter = warp & 3 of the TMEM lanes, column half = warp >> 2 ----------------
     const int quarter = warp & 3, half = warp >> 2;
+    float acc_t[16];      // running transposed-product row of this TMEM lane, 16 of its 32 columns
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc_t[t] = 0.f;
     const int my_row = 16 * quarter + (lane & 15);   // M = 64 accumulators live in lanes 0..15 of each quarter
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -386,20 +394,11 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
 #pragma unroll
     for (int t = 0; t < 16; t += 4) *reinterpret_cast<float4*>(p + t) = make_float4(acc_t[t], acc_t[t + 1], acc_t[t + 2], acc_t[t + 3]);
   }
-  __syncthreads();   // the staging tiles (aliased by dr_red) are no longer read
-  // dr[c]: a producer thread holds columns 8 qq + 4 i + t summed over its rows; fixed-order sum over the 128 row slots
-  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
-    const int slot = (warp - kEpiWarps) * 8 + (lane & 7), qq = lane >> 3;
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) dr_red[slot * 32 + 8 * qq + 4 * i + t] = acc_dr[i][t];
-  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < 32) {
     float s = 0.f;
-    for (int slot = 0; slot < 8 * kProdWarps; ++slot) s += dr_red[slot * 32 + tid];
+    for (int w = 0; w < kProdWarps; ++w) s += dr_red[w * 32 + tid];
     a.part_b[(int64_t)blockIdx.x * 32 + tid] = s;
   }
   if (warp == 0) {

@@ -14,6 +14,9 @@ import torch
 from . import ops
 
 FUSED_WIDTHS = (16, 32, 64, 128)
+# row-local backward of the hidden-32 stack: tcgen05 / TMEM pipeline (0.64 ms per layer at the botnet batch)
+# or the mma.sync kernel (0.81 ms); both pass the same parity tests
+BWD_TENSOR_MEMORY = True
 
 
 class _ResidualGCNStack(torch.autograd.Function):
@@ -129,7 +132,7 @@ class _ResidualGCNStack32(torch.autograd.Function):
         for n in range(L - 1, 0, -1):
             dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
             gy_prev, gs_prev, dw, drw, drb = ops.gcn_layer_bwd_impl(
-                dxw, gy, xs[n], layers[n][0], layers[n][1], hmasks[n - 1], post, True)
+                dxw, gy, xs[n], layers[n][0], layers[n][1], hmasks[n - 1], post, True, BWD_TENSOR_MEMORY)
             grads[3 * n], grads[3 * n + 1], grads[3 * n + 2] = dw, drw, drb
             gy, gs = gy_prev, gs_prev
         grads[1], grads[2] = ops.linear_wgrad_impl(xs[0], gy, True, True)
