@@ -211,23 +211,71 @@ __device__ __forceinline__ void store_partial(float* __restrict__ partial, int s
   *reinterpret_cast<float4*>(p + 4) = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
 }
 
-// partial rows of a hub's segments, added left to right
+// partial rows of a hub's segments, added left to right (after k_hub_reduce: one row)
+__device__ __forceinline__ Row8 ld_partial(const float* p) {
+  const float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+  Row8 r;
+  r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+  r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+  return r;
+}
 __device__ __forceinline__ Row8 sum_partials(const float* __restrict__ partial, int s0, int ns, int col) {
-  Row8 tot;
   const float* p = partial + (int64_t)s0 * kH + col;
-  float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
-  tot.v[0] = lo.x; tot.v[1] = lo.y; tot.v[2] = lo.z; tot.v[3] = lo.w;
-  tot.v[4] = hi.x; tot.v[5] = hi.y; tot.v[6] = hi.z; tot.v[7] = hi.w;
+  Row8 tot = ld_partial(p);
   for (int q = 1; q < ns; ++q) {
-    Row8 b;
-    p += kH;
-    lo = *reinterpret_cast<const float4*>(p);
-    hi = *reinterpret_cast<const float4*>(p + 4);
-    b.v[0] = lo.x; b.v[1] = lo.y; b.v[2] = lo.z; b.v[3] = lo.w;
-    b.v[4] = hi.x; b.v[5] = hi.y; b.v[6] = hi.z; b.v[7] = hi.w;
+    const Row8 b = ld_partial(p + (int64_t)q * kH);
     row8_add(tot, b);
   }
   return tot;
+}
+
+// One warp per hub row: the row's segment partials -> one row, in place in the hub's first slot.  The biggest
+// hub of a botnet graph has ~230 segments; summed by one lane group with dependent loads it alone took 60 us
+// per aggregation.  Here the 8 lane groups sum 8 contiguous runs of segments concurrently and the 8 run sums
+// are added left to right (a fixed order: deterministic).
+__global__ void __launch_bounds__(256) k_hub_reduce(const int32_t* __restrict__ hub_rows,
+                                                    const int32_t* __restrict__ hub_seg0,
+                                                    const int32_t* __restrict__ hub_count,
+                                                    const int32_t* __restrict__ rowptr, int64_t hub_cap,
+                                                    int hub_threshold, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2, col = sub * 8;
+  int64_t nh = *hub_count;
+  if (nh > hub_cap) nh = hub_cap;
+  const int64_t W = (int64_t)gridDim.x * 8;
+  for (int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); k < nh; k += W) {
+    const int64_t row = __ldg(hub_rows + k);
+    const int s0 = __ldg(hub_seg0 + k);
+    const int len = __ldg(rowptr + row + 1) - __ldg(rowptr + row);
+    const int ns = (len + hub_threshold - 1) / hub_threshold;
+    if (ns <= 1) continue;
+    const int per = (ns + 7) >> 3;
+    const int q0 = grp * per, q1 = min(ns, q0 + per);
+    Row8 run;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) run.v[q] = 0.f;
+    if (q0 < q1) run = sum_partials(partial, s0 + q0, q1 - q0, col);
+    Row8 tot = run;   // group 0: its own run; then runs 1..7 in order
+#pragma unroll
+    for (int g = 1; g < 8; ++g) {
+      Row8 other;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) other.v[q] = __shfl_sync(0xffffffffu, run.v[q], 4 * g + sub);
+      if (g * per < ns) row8_add(tot, other);
+    }
+    if (grp == 0) {
+      float* o = partial + (int64_t)s0 * kH + col;
+      *reinterpret_cast<float4*>(o) = make_float4(tot.v[0], tot.v[1], tot.v[2], tot.v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(tot.v[4], tot.v[5], tot.v[6], tot.v[7]);
+    }
+  }
+}
+
+static inline int launch_hub_reduce(const mgcn_csr_t* g, float* partial, void* stream) {
+  int64_t hb = ceil_div(g->hub_cap, 8);
+  if (hb > (int64_t)kNumSMs * 8) hb = (int64_t)kNumSMs * 8;
+  MGCN_LAUNCH(k_hub_reduce, (unsigned)hb, 256, 0, stream, g->hub_rows, g->hub_seg0, g->hub_count, g->rowptr,
+              g->hub_cap, g->hub_threshold, partial);
+  return MGCN_OK;
 }
 
 // residual operand rows (x, or the finished residual term) of a 16-row tile -> Xs, asynchronously
@@ -445,7 +493,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd_hubs(const Laye
       const int ns = __shfl_sync(0xffffffffu, mynseg, 8 * p + grp);
       const float postp = __shfl_sync(0xffffffffu, mypost, 8 * p + grp);
       if (rowp >= 0) {
-        Row8 tot = sum_partials(a.partial, s0, ns, col);
+        Row8 tot = sum_partials(a.partial, s0, 1, col);   // reduced by k_hub_reduce
         finish_h(a, tot, postp, rowp, &Hs[8 * p + grp][0], sub, gmask, col);
       }
     }
@@ -553,7 +601,7 @@ __global__ void __launch_bounds__(256) k_agg_flat_hubs(const AggFlatArgs a) {
     const int s0 = __ldg(a.hub_seg0 + k);
     const int len = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
     const int nseg = (len + a.hub_threshold - 1) / a.hub_threshold;
-    const Row8 tot = sum_partials(a.partial, s0, nseg, col);
+    const Row8 tot = sum_partials(a.partial, s0, 1, col);   // reduced by k_hub_reduce
     agg_finish_row(a, tot, a.post ? __ldg(a.post + row) : 1.f, row, col, pol);
   }
 }
@@ -583,6 +631,8 @@ int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, in
   if (blocks > (int64_t)kNumSMs * MGCN_AGG_MINB) blocks = (int64_t)kNumSMs * MGCN_AGG_MINB;
   MGCN_LAUNCH(k_agg_flat, (unsigned)blocks, 256, 0, stream, a);
   if (hubs) {
+    const int rc = launch_hub_reduce(g, partial, stream);
+    if (rc != MGCN_OK) return rc;
     int64_t hb = ceil_div(a.hub_cap, 64);
     if (hb > (int64_t)kNumSMs * 2) hb = (int64_t)kNumSMs * 2;
     MGCN_LAUNCH(k_agg_flat_hubs, (unsigned)hb, 256, 0, stream, a);
@@ -863,6 +913,8 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
   if (blocks > (int64_t)kNumSMs * MGCN_FWD_MINB) blocks = (int64_t)kNumSMs * MGCN_FWD_MINB;
   MGCN_LAUNCH(k_layer_fwd, (unsigned)blocks, kFwdWarps * 32, smem, stream, a);
   if (hubs) {
+    const int rc = launch_hub_reduce(g, partial, stream);
+    if (rc != MGCN_OK) return rc;
     int64_t hb = ceil_div(ceil_div(a.hub_cap, 16), kFwdWarps);
     if (hb > (int64_t)kNumSMs) hb = kNumSMs;
     MGCN_LAUNCH(k_layer_fwd_hubs, (unsigned)hb, kFwdWarps * 32, smem, stream, a);

@@ -5,7 +5,7 @@
 // Every operand element is split ONCE into hi/lo tf32 images in shared memory and one thread issues 24
 // tcgen05.mma per 64-row tile:
 //   row-local   D[64 x 64|32] (+)= A_K[64 x 8] * B_K[64|32 x 8]^T        K-major, un-swizzled interleaved images
-//               TMEM cols [0,32) main = dxw_hi Wt_hi + gy_hi R_hi; [32,64) = hi * B_lo; [64,96) = lo * B_hi
+//               TMEM cols [0,32) main = dxw_hi Wt_hi + gy_hi R_hi; [32,64) = hi * B_lo + lo * B_hi (both corrections)
 //               (M = 64 accumulators live in lanes 0..15 of each 32-lane TMEM quarter)
 //   transposed  [D1 | D2][128 x 64] (+)= [dxw_hi|gy_hi|dxw_lo|gy_lo]^T[128 x 8 rows] * [x_hi | x_lo][8 rows x 64]
 //               MN-major, SWIZZLE_128B_BASE32B images, TMEM cols [96,160)
@@ -60,7 +60,7 @@ constexpr int kStages = 2;                 // operand stages == TMEM accumulator
 constexpr int kOffB1 = kStages * kStageB;  // [Wt_hi ; Wt_lo]  64 x 32, K-major
 constexpr int kOffB2 = kOffB1 + 8192;      // [R_hi ; R_lo]
 constexpr int kOffMisc = kOffB2 + 8192;    // barriers (full[2], done[2], tfree[2]), tmem slot
-constexpr int kOffXbits = kOffMisc + 64;   // [4][64] words: x > 0 of the tile's rows (4 tiles deep)
+constexpr int kOffXbits = kOffMisc + 128;   // [4][64] words: x > 0 of the tile's rows (4 tiles deep)
 constexpr int kLdo = 36;                   // floats per staged output row (144 bytes)
 constexpr int kOffOut = kOffXbits + 4 * 64 * 4;     // [2 buffers][gy_prev | gs_prev][64 rows][kLdo] staged outputs
 constexpr int kOffDrRed = kOffOut + 2 * 2 * kTRows * kLdo * 4;   // [16 producer warps][32] dr partials
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffMisc);
   uint64_t* bar_done = bar_full + 2;
   uint64_t* bar_tfree = bar_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 48);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 80);
   uint32_t* xbits = reinterpret_cast<uint32_t*>(smem + kOffXbits);
   float* dr_red = reinterpret_cast<float*>(smem + kOffDrRed);   // [16 warps][32]
   float* stage_out = reinterpret_cast<float*>(smem + kOffOut);
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
               const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
               umma_tf32(tb + 0, dK + (so + (kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
               umma_tf32(tb + 0, dK + (so + (kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
-              umma_tf32(tb + 64, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, k > 0);   // dxw_lo Wt_hi
-              umma_tf32(tb + 64, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
+              umma_tf32(tb + 32, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, 1);       // dxw_lo Wt_hi  (joins hi * B_lo)
+              umma_tf32(tb + 32, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
             }
           }
 #pragma unroll
@@ -317,17 +317,25 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc_t[t] = 0.f;
     const int my_row = 16 * quarter + (lane & 15);   // M = 64 accumulators live in lanes 0..15 of each quarter
+    // mask word and per-target factor of this lane's row, fetched one tile ahead
+    uint32_t hbits_n = 0;
+    float post_n = 1.f;
+    auto load_row_scalars = [&](int64_t tile) {
+      const int64_t gr = tile * kTRows + my_row;
+      hbits_n = 0;
+      post_n = 1.f;
+      if (want_prev && lane < 16 && tile < n_tiles && gr < a.n_rows) {
+        hbits_n = __ldg(a.hmask_prev + gr);
+        if (a.post) post_n = __ldg(a.post + gr);
+      }
+    };
+    load_row_scalars(blockIdx.x);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1, use = it >> 1;
-      const int64_t g_row = tile * kTRows + my_row;
-      const bool fin = want_prev && lane < 16 && g_row < a.n_rows;
-      uint32_t hbits = 0;
-      float postv = 1.f;
-      if (fin) {
-        hbits = __ldg(a.hmask_prev + g_row);
-        if (a.post) postv = __ldg(a.post + g_row);
-      }
+      const uint32_t hbits = hbits_n;
+      const float postv = post_n;
+      load_row_scalars(tile + gridDim.x);
       mbar_wait(bar_done + s, use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t lane_addr = tmem + s * kTmemBufCols + ((uint32_t)(32 * quarter) << 16);
@@ -344,14 +352,14 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
         // G row of this lane, columns [16 half, 16 half + 16) -> staging tile in shared memory (rows padded to 144
         // bytes: the 8 rows of a quarter warp land in 8 different 16-byte bank groups)
         const uint32_t xb = xbits[(it & 3) * 64 + my_row];
-        float* sg = stage_out + (it & 1) * (2 * kTRows * kLdo);
+        float* sg = stage_out + s * (2 * kTRows * kLdo);
+
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = 16 * half + 8 * h;
-          uint32_t m[8], c1[8], c2[8];
+          uint32_t m[8], c1[8];
           tmem_ld8(lane_addr + 0 + c0, m);
           tmem_ld8(lane_addr + 32 + c0, c1);
-          tmem_ld8(lane_addr + 64 + c0, c2);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (lane < 16) {
 #pragma unroll
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const int c = c0 + 4 * q + t;
-                const float gv = __uint_as_float(m[4 * q + t]) + (__uint_as_float(c1[4 * q + t]) + __uint_as_float(c2[4 * q + t]));
+                const float gv = __uint_as_float(m[4 * q + t]) + __uint_as_float(c1[4 * q + t]);
                 g[t] = ((xb >> c) & 1u) ? gv : 0.f;
                 sv[t] = ((hbits >> c) & 1u) ? g[t] * postv : 0.f;
               }
@@ -377,14 +385,14 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       if (want_prev) {
         // staged rows -> global, 4 whole rows (512 contiguous bytes) per store instruction; warp w owns rows 8w..8w+7
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        const float* sg = stage_out + (it & 1) * (2 * kTRows * kLdo);
+        const float* sgo = stage_out + s * (2 * kTRows * kLdo);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int r = 8 * warp + 4 * i + (lane >> 3), q = lane & 7;
           const int64_t gr = tile * kTRows + r;
           if (gr < a.n_rows) {
-            st_f4_hint(a.gy_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sg + r * kLdo + 4 * q), pol);
-            st_f4_hint(a.gs_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sg + (kTRows + r) * kLdo + 4 * q), pol);
+            st_f4_hint(a.gy_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sgo + r * kLdo + 4 * q), pol);
+            st_f4_hint(a.gs_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sgo + (kTRows + r) * kLdo + 4 * q), pol);
           }
         }
       }
