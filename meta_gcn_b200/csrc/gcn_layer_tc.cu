@@ -60,12 +60,14 @@ constexpr int kStages = 2;                 // operand stages == TMEM accumulator
 constexpr int kOffB1 = kStages * kStageB;  // [Wt_hi ; Wt_lo]  64 x 32, K-major
 constexpr int kOffB2 = kOffB1 + 8192;      // [R_hi ; R_lo]
 constexpr int kOffMisc = kOffB2 + 8192;    // barriers (full[2], done[2], tfree[2]), tmem slot
-constexpr int kOffXbits = kOffMisc + 128;   // [4][64] words: x > 0 of the tile's rows (4 tiles deep)
+constexpr int kOffXbits = kOffMisc + 128;   // [8][64] words: x > 0 of the tile's rows (8 tiles deep)
 constexpr int kLdo = 36;                   // floats per staged output row (144 bytes)
-constexpr int kOffOut = kOffXbits + 4 * 64 * 4;     // [2 buffers][gy_prev | gs_prev][64 rows][kLdo] staged outputs
+constexpr int kOffOut = kOffXbits + 8 * 64 * 4;     // [2 tiles of a pair][gy_prev | gs_prev][64 rows][kLdo] staged outputs
 constexpr int kOffDrRed = kOffOut + 2 * 2 * kTRows * kLdo * 4;   // [16 producer warps][32] dr partials
 constexpr int kBwdTcSmem = kOffDrRed + 16 * 32 * 4 + 1024;
-constexpr int kTmemBufCols = 256;          // accumulator columns per buffer (160 used)
+constexpr int kTmemBufCols = 256;          // accumulator columns per pair buffer: G main [0,32) and corrections [32,64) of both
+                                           // tiles (tile 2j in lanes 0..15, tile 2j+1 in lanes 16..31 of every quarter),
+                                           // transposed products of tile 2j [64,128) and of tile 2j+1 [128,192)
 
 constexpr int kEpiWarps = 8;               // warps 0..7   TMEM -> registers -> gy_prev / gs_prev, running dW / dR rows
 constexpr int kProdWarps = 16;             // warps 8..23  global -> split -> operand images (two sets of 8, one per stage)
@@ -126,12 +128,13 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + kOffMisc);
   uint64_t* bar_done = bar_full + 2;
-  uint64_t* bar_tfree = bar_full + 4;
+  uint64_t* bar_tfree = bar_full + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 80);
   uint32_t* xbits = reinterpret_cast<uint32_t*>(smem + kOffXbits);
   float* dr_red = reinterpret_cast<float*>(smem + kOffDrRed);   // [16 warps][32]
   float* stage_out = reinterpret_cast<float*>(smem + kOffOut);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (roles, descriptors)
   const bool want_prev = a.gy_prev != nullptr;
 
   // weight images: B1(n, k) = W[n][k] (hi rows 0..31, lo rows 32..63); B2(n, k) = R[k][n]
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + s, kProdWarps / 2);
       mbar_init(bar_done + s, 1);
+      mbar_init(bar_done + 2 + s, 1);
       mbar_init(bar_tfree + s, kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -210,7 +214,8 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
     for (; tile < n_tiles; tile += 2 * (int64_t)gridDim.x, it += 2) {
       load_tile(nxt, tile + 2 * (int64_t)gridDim.x);
       const int use = it >> 1;
-      if (use >= 1) mbar_wait(bar_done + pset, (use - 1) & 1);   // the tensor core has consumed this stage's previous tile
+      // the tensor core has consumed this stage's previous tile (done barriers: [pair buffer][set])
+      if (use >= 1) mbar_wait(bar_done + 2 * ((use - 1) & 1) + pset, ((use - 1) >> 1) & 1);
       float4 c0, c1, hi, lo;
       // dxw
       c0 = flip ? cur[0].hi : cur[0].lo;
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       *reinterpret_cast<float4*>(st + kOffMXl + mo_b) = lo;
       b |= __shfl_xor_sync(0xffffffffu, b, 8);
       b |= __shfl_xor_sync(0xffffffffu, b, 16);
-      if (qq == 0) xbits[(it & 3) * 64 + r0] = b;
+      if (qq == 0) xbits[(it & 7) * 64 + r0] = b;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + pset);
@@ -269,29 +274,33 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
         // this warp also issues the tile's 24 tcgen05.mma (lane 0) once the other 7 warps of the set have arrived
         // and the epilogue has drained accumulator buffer pset
         mbar_wait(bar_full + pset, use & 1);
-        if (use >= 1) mbar_wait(bar_tfree + pset, (use - 1) & 1);
+        // pair buffer of tiles (2 use, 2 use + 1): read by the epilogue two pairs ago
+        const int pb = use & 1;
+        if (use >= 2) mbar_wait(bar_tfree + pb, ((use >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
-          const uint32_t tb = tmem + pset * kTmemBufCols;
+          const uint32_t tb = tmem + pb * kTmemBufCols;
+          const uint32_t tg = tb + ((uint32_t)(16 * pset) << 16);   // M = 64 accumulators of this set's tile: lanes 16 pset ..
+          const uint32_t tt = tb + 64 + 64 * pset;
           const uint32_t so = (uint32_t)(pset * kStageB) >> 4;
           if (want_prev) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
               const uint64_t b1 = dK + ((kOffB1 >> 4) + ko), b2 = dK + ((kOffB2 >> 4) + ko);
-              umma_tf32(tb + 0, dK + (so + (kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
-              umma_tf32(tb + 0, dK + (so + (kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
-              umma_tf32(tb + 32, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, 1);       // dxw_lo Wt_hi  (joins hi * B_lo)
-              umma_tf32(tb + 32, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
+              umma_tf32(tg + 0, dK + (so + (kOffKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
+              umma_tf32(tg + 0, dK + (so + (kOffKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
+              umma_tf32(tg + 32, dK + (so + (kOffKDl >> 4) + ko), b1, idG32, 1);       // dxw_lo Wt_hi  (joins hi * B_lo)
+              umma_tf32(tg + 32, dK + (so + (kOffKGl >> 4) + ko), b2, idG32, 1);       // gy_lo  R_hi
             }
           }
 #pragma unroll
           for (int k = 0; k < kTRows / 8; ++k) {
             const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
             // B = [x_hi | x_lo]: two 32-column MN atoms one image apart -> D1 | D2 in one N = 64 instruction
-            umma_tf32(tb + 96, dM + (so + (kOffMN >> 4) + ko), dM + (so + (kOffMXh >> 4) + ko), idT, k > 0);
+            umma_tf32(tt, dM + (so + (kOffMN >> 4) + ko), dM + (so + (kOffMXh >> 4) + ko), idT, k > 0);
           }
-          umma_commit(bar_done + pset);
+          umma_commit(bar_done + 2 * pb + pset);
         }
         __syncwarp();
       }
@@ -316,44 +325,50 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
     float acc_t[16];      // running transposed-product row of this TMEM lane, 16 of its 32 columns
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc_t[t] = 0.f;
-    const int my_row = 16 * quarter + (lane & 15);   // M = 64 accumulators live in lanes 0..15 of each quarter
-    // mask word and per-target factor of this lane's row, fetched one tile ahead
+    // tile 2j of a pair lives in lanes 0..15, tile 2j + 1 in lanes 16..31 of every quarter (M = 64 accumulators)
+    const int my_row = 16 * quarter + (lane & 15), sel = lane >> 4;
+    // mask word and per-target factor of this lane's row, fetched one pair ahead
     uint32_t hbits_n = 0;
     float post_n = 1.f;
     auto load_row_scalars = [&](int64_t tile) {
       const int64_t gr = tile * kTRows + my_row;
       hbits_n = 0;
       post_n = 1.f;
-      if (want_prev && lane < 16 && tile < n_tiles && gr < a.n_rows) {
+      if (want_prev && tile < n_tiles && gr < a.n_rows) {
         hbits_n = __ldg(a.hmask_prev + gr);
         if (a.post) post_n = __ldg(a.post + gr);
       }
     };
-    load_row_scalars(blockIdx.x);
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int s = it & 1, use = it >> 1;
+    load_row_scalars(blockIdx.x + (int64_t)sel * gridDim.x);
+    int j = 0;
+    for (int64_t tile_a = blockIdx.x; tile_a < n_tiles; tile_a += 2 * (int64_t)gridDim.x, ++j) {
+      const int pb = j & 1;
+      const int64_t tile_b = tile_a + gridDim.x;
+      const bool has_b = tile_b < n_tiles;
       const uint32_t hbits = hbits_n;
       const float postv = post_n;
-      load_row_scalars(tile + gridDim.x);
-      mbar_wait(bar_done + s, use & 1);
+      load_row_scalars(tile_a + (int64_t)(2 + sel) * gridDim.x);
+      mbar_wait(bar_done + 2 * pb + 0, (j >> 1) & 1);
+      if (has_b) mbar_wait(bar_done + 2 * pb + 1, (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t lane_addr = tmem + s * kTmemBufCols + ((uint32_t)(32 * quarter) << 16);
-      {
-        // transposed products of this tile -> running fp32 sums (RN)
-        uint32_t d1[16], d2[16];
-        tmem_ld16(lane_addr + 96 + 16 * half, d1);
-        tmem_ld16(lane_addr + 128 + 16 * half, d2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const uint32_t lane_addr = tmem + pb * kTmemBufCols + ((uint32_t)(32 * quarter) << 16);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) acc_t[t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
+      for (int t2 = 0; t2 < 2; ++t2) {
+        if (t2 == 0 || has_b) {
+          // transposed products of one tile -> running fp32 sums (RN)
+          uint32_t d1[16], d2[16];
+          tmem_ld16(lane_addr + 64 + 64 * t2 + 16 * half, d1);
+          tmem_ld16(lane_addr + 96 + 64 * t2 + 16 * half, d2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int t = 0; t < 16; ++t) acc_t[t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
+        }
       }
       if (want_prev) {
         // G row of this lane, columns [16 half, 16 half + 16) -> staging tile in shared memory (rows padded to 144
         // bytes: the 8 rows of a quarter warp land in 8 different 16-byte bank groups)
-        const uint32_t xb = xbits[(it & 3) * 64 + my_row];
-        float* sg = stage_out + s * (2 * kTRows * kLdo);
-
+        const uint32_t xb = xbits[((2 * j + sel) & 7) * 64 + my_row];
+        float* sg = stage_out + sel * (2 * kTRows * kLdo);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = 16 * half + 8 * h;
@@ -361,40 +376,46 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
           tmem_ld8(lane_addr + 0 + c0, m);
           tmem_ld8(lane_addr + 32 + c0, c1);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (lane < 16) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              float g[4], sv[4];
+          for (int q = 0; q < 2; ++q) {
+            float g[4], sv[4];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int c = c0 + 4 * q + t;
-                const float gv = __uint_as_float(m[4 * q + t]) + __uint_as_float(c1[4 * q + t]);
-                g[t] = ((xb >> c) & 1u) ? gv : 0.f;
-                sv[t] = ((hbits >> c) & 1u) ? g[t] * postv : 0.f;
-              }
-              *reinterpret_cast<float4*>(sg + my_row * kLdo + c0 + 4 * q) = make_float4(g[0], g[1], g[2], g[3]);
-              *reinterpret_cast<float4*>(sg + (kTRows + my_row) * kLdo + c0 + 4 * q) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            for (int t = 0; t < 4; ++t) {
+              const int c = c0 + 4 * q + t;
+              const float gv = __uint_as_float(m[4 * q + t]) + __uint_as_float(c1[4 * q + t]);
+              g[t] = ((xb >> c) & 1u) ? gv : 0.f;
+              sv[t] = ((hbits >> c) & 1u) ? g[t] * postv : 0.f;
             }
+            *reinterpret_cast<float4*>(sg + my_row * kLdo + c0 + 4 * q) = make_float4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<float4*>(sg + (kTRows + my_row) * kLdo + c0 + 4 * q) = make_float4(sv[0], sv[1], sv[2], sv[3]);
           }
         }
       }
-      // accumulator buffer s is free for the tile after next
+      // pair buffer pb is free for the pair after next
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tfree + s);
+      if (lane == 0) mbar_arrive(bar_tfree + pb);
       if (want_prev) {
-        // staged rows -> global, 4 whole rows (512 contiguous bytes) per store instruction; warp w owns rows 8w..8w+7
+        // staged rows -> global, 4 whole rows (512 contiguous bytes) per store instruction; warp w owns rows
+        // 8w..8w+7 of both tiles
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        const float* sgo = stage_out + s * (2 * kTRows * kLdo);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int r = 8 * warp + 4 * i + (lane >> 3), q = lane & 7;
-          const int64_t gr = tile * kTRows + r;
-          if (gr < a.n_rows) {
-            st_f4_hint(a.gy_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sgo + r * kLdo + 4 * q), pol);
-            st_f4_hint(a.gs_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sgo + (kTRows + r) * kLdo + 4 * q), pol);
+        for (int t2 = 0; t2 < 2; ++t2) {
+          if (t2 == 0 || has_b) {
+            const float* sgo = stage_out + t2 * (2 * kTRows * kLdo);
+            const int64_t tile = t2 == 0 ? tile_a : tile_b;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r = 8 * warp + 4 * i + (lane >> 3), q = lane & 7;
+              const int64_t gr = tile * kTRows + r;
+              if (gr < a.n_rows) {
+                st_f4_hint(a.gy_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sgo + r * kLdo + 4 * q), pol);
+                st_f4_hint(a.gs_prev + gr * kTH + 4 * q, *reinterpret_cast<const float4*>(sgo + (kTRows + r) * kLdo + 4 * q), pol);
+              }
+            }
           }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");   // staging tile may be rewritten
       }
     }
     // per-CTA partials of the transposed products: row = TMEM lane, this warp's 16 columns

@@ -96,7 +96,7 @@ def test_layer_fwd_is_deterministic_and_order_exact():
 
 
 @pytest.mark.parametrize("tensor_memory", [False, True])
-@pytest.mark.parametrize("n,want_prev", [(1000, True), (1003, True), (131, False), (7, True), (40000, True)])
+@pytest.mark.parametrize("n,want_prev", [(1000, True), (1003, True), (131, False), (7, True), (40000, True), (300001, True), (151617, False)])
 def test_layer_bwd(n, want_prev, tensor_memory):
     gen = torch.Generator().manual_seed(n)
     dxw = torch.randn(n, H, generator=gen)
