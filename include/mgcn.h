@@ -131,6 +131,13 @@ int mgcn_degree_from_rowptr(const int32_t* rowptr, int64_t N, float* deg, void* 
 int mgcn_weighted_degree(const mgcn_csr_t* g, const float* edge_weight, int64_t E,
                          float loop_weight, float* deg, void* stream);
 
+/* out4[0..3] = two independent 64-bit multiset fingerprints of the directed edge list, interleaved with the
+ * same two of its transpose: out4[0] == out4[1] && out4[2] == out4[3] <=> every (u,v) occurs as often as (v,u).
+ * The botnet data of the reference are symmetric by construction (data_procs/undirected.py:6-35); for such an
+ * edge_index the structure by source (the transposed aggregation of the autograd, train_botnet.py:293) holds
+ * the same neighbour multisets per row as the structure by target and is not built a second time. */
+int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint64_t* out4, void* stream);
+
 /* dis = deg^-1/2 (mode 0, 'sm') or deg^-1 (mode 1, 'rw') with inf -> 0:
  * gcn_base_models.py:128-135.  Computed as correctly rounded 1/sqrt(d) resp. 1/d. */
 int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream);

@@ -690,6 +690,59 @@ extern "C" int mgcn_weighted_degree(const mgcn_csr_t* g, const float* edge_weigh
   return MGCN_OK;
 }
 
+namespace mgcn {
+// Multiset fingerprint of the edge list and of its transpose: sums (mod 2^64) of two independent 64-bit mixes
+// of (src, dst) resp. (dst, src).  Equal fingerprints <=> the directed edge multiset is symmetric (up to a
+// 2^-128 collision chance), in which case the structure by source lists, row by row, the same neighbour
+// multisets as the structure by target and need not be built.  Integer sums: independent of scheduling.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) k_edge_fingerprint(const int64_t* __restrict__ ei, int64_t E,
+                                                          unsigned long long* __restrict__ out) {
+  unsigned long long f[4] = {0ull, 0ull, 0ull, 0ull};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    const uint64_t a = (uint64_t)ei[e], b = (uint64_t)ei[E + e];
+    const uint64_t ab = a * 0x9e3779b97f4a7c15ull + b, ba = b * 0x9e3779b97f4a7c15ull + a;
+    f[0] += mix64(ab);
+    f[1] += mix64(ba);
+    f[2] += mix64(ab ^ 0xd6e8feb86659fd93ull);
+    f[3] += mix64(ba ^ 0xd6e8feb86659fd93ull);
+  }
+  __shared__ unsigned long long red[8][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    unsigned long long v = f[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long v = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    atomicAdd(out + threadIdx.x, v);
+  }
+}
+}  // namespace mgcn
+
+extern "C" int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint64_t* out4, void* stream) {
+  MGCN_REQUIRE(out4 != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(E >= 0 && E < (int64_t(1) << 31), MGCN_ERR_RANGE);
+  MGCN_CHECK_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
+  if (E == 0) return MGCN_OK;
+  MGCN_REQUIRE(edge_index != nullptr, MGCN_ERR_NULL);
+  int64_t blocks = ceil_div(E, 256 * 8);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  MGCN_LAUNCH(k_edge_fingerprint, (unsigned)blocks, 256, 0, stream, edge_index, E,
+              reinterpret_cast<unsigned long long*>(out4));
+  return MGCN_OK;
+}
+
 extern "C" int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream) {
   MGCN_REQUIRE(N >= 0, MGCN_ERR_RANGE);
   MGCN_REQUIRE(mode == 0 || mode == 1, MGCN_ERR_SHAPE);

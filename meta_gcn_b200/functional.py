@@ -40,7 +40,7 @@ class _Aggregate(torch.autograd.Function):
                 gg = g / graph.in_degree().clamp(min=1).unsqueeze(1)
             # transpose: rows = sources; the per-target factor is now gathered, the per-source
             # factor scales the row
-            dx = ops.spmm_impl(graph.bwd, gg, False, ev_bwd, row_scale, nbr_scale, 0, None,
+            dx = ops.spmm_impl(graph.bwd if ev_bwd is not None else graph.bwd_plain, gg, False, ev_bwd, row_scale, nbr_scale, 0, None,
                                None, 0)
         return dx, d_bias, d_res, None, None, None, None, None, None, None
 

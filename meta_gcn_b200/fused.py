@@ -49,7 +49,7 @@ class _ResidualGCNStack(torch.autograd.Function):
         saved = ctx.saved_tensors
         xs, hs, params = saved[:L + 1], saved[L + 1:2 * L + 1], saved[2 * L + 1:]
         layers = [params[i * per:(i + 1) * per] for i in range(L)]
-        pre, post, bwd = ctx.pre, ctx.post, ctx.graph.bwd
+        pre, post, bwd = ctx.pre, ctx.post, ctx.graph.bwd_plain
         grads = [None] * len(params)
         g = g.contiguous()
         need_x = ctx.needs_input_grad[0]
@@ -123,7 +123,7 @@ class _ResidualGCNStack32(torch.autograd.Function):
         saved = ctx.saved_tensors
         xs, hmasks, params = saved[:L + 1], saved[L + 1:2 * L + 1], saved[2 * L + 1:]
         layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
-        pre, post, bwd = ctx.pre, ctx.post, ctx.graph.bwd
+        pre, post, bwd = ctx.pre, ctx.post, ctx.graph.bwd_plain
         grads = [None] * len(params)
         gy = g.contiguous()
         if last_relu:

@@ -18,6 +18,10 @@ LOOPS_REMOVE = 1    # PyG remove_self_loops (GINConv)
 LOOPS_ADD_REMAINING = 2  # PyG add_remaining_self_loops (GCNConv.norm, SAGEConv)
 
 
+# set False to always build the by-source structure (tests compare both)
+USE_SYMMETRY = True
+
+
 class GraphStructure:
     """Lazily built forward (by target) and backward (by source) structures of an edge_index."""
 
@@ -32,6 +36,7 @@ class GraphStructure:
         self.hub_threshold = int(hub_threshold)
         self._fwd = None
         self._bwd = None
+        self._symmetric = None
         self._deg = {}
 
     def _build(self, by):
@@ -52,10 +57,28 @@ class GraphStructure:
             self._bwd = self._build(0)
         return self._bwd
 
+    @property
+    def symmetric(self):
+        """every (u, v) occurs as often as (v, u) — true for the reference's botnet data
+        (data_procs/undirected.py:6-35).  Checked once per edge_index on the device (ops.edge_symmetry_impl)."""
+        if self._symmetric is None:
+            self._symmetric = USE_SYMMETRY and ops.edge_symmetry_impl(self.edge_index)
+        return self._symmetric
+
+    @property
+    def bwd_plain(self):
+        """Structure for transposed aggregations WITHOUT per-edge values: rows = sources, neighbour multisets
+        only.  For a symmetric edge list that is the forward structure (same multisets per row, another order
+        inside a row), so the second sort is skipped; `bwd` keeps the exact by-source structure with `perm`."""
+        if self._bwd is not None:
+            return self._bwd
+        return self.fwd if self.symmetric else self.bwd
+
     def out_degree(self):
         """float degree over edge_index[0] (after loop handling): gcn_base_models.py:126"""
         if "out" not in self._deg:
-            self._deg["out"] = ops.degree_impl(self.bwd.rowptr)
+            rowptr = self.bwd.rowptr if (self._bwd is not None or not self.symmetric) else self.fwd.rowptr
+            self._deg["out"] = ops.degree_impl(rowptr)
         return self._deg["out"]
 
     def in_degree(self):

@@ -160,6 +160,19 @@ def weighted_degree_impl(csr, edge_weight, loop_weight):
     return deg
 
 
+def edge_symmetry_impl(edge_index):
+    """True iff the directed edge multiset equals its transpose (mgcn_edge_fingerprint).  Reads four words
+    back from the device: one host synchronisation per edge_index."""
+    _need_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("edge_index must be int64 [2, E]")
+    ei = edge_index.contiguous()
+    out = torch.empty(4, dtype=torch.int64, device=ei.device)
+    _lib.check(_lib.load().mgcn_edge_fingerprint(_ptr(ei), ei.size(1), _ptr(out), _stream()))
+    f = out.tolist()
+    return f[0] == f[1] and f[2] == f[3]
+
+
 def gcn_norm_impl(deg, mode):
     _need_cuda(deg)
     d = _f32c(deg, "deg")

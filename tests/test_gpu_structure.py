@@ -190,3 +190,29 @@ def test_batch_to_offsets():
     batch = torch.cat([torch.full((s,), i, dtype=torch.long) for i, s in enumerate(sizes)]).to(DEV)
     off = ops.batch_to_offsets_impl(batch, len(sizes))
     assert off.cpu().tolist() == np.concatenate([[0], np.cumsum(sizes)]).tolist()
+
+
+def test_edge_symmetry_fingerprint_and_structure_reuse():
+    """mgcn_edge_fingerprint: symmetric edge multisets (the reference's undirected botnet data,
+    data_procs/undirected.py:6-35) are recognised, any asymmetry is not; for a symmetric list the plain
+    transposed structure is the forward one and the aggregation results agree with the by-source build."""
+    from meta_gcn_b200 import graph as G
+    g = synth_botnet_graph(seed=3, num_nodes=5000, edge_entries=40000, evil=300)
+    ei = torch.from_numpy(np.ascontiguousarray(g["edge_index"])).long().to(DEV)
+    assert ops.edge_symmetry_impl(ei) is True
+    ei2 = ei.clone()
+    ei2[1, 17] = (ei2[1, 17] + 1) % 5000            # one endpoint changed
+    assert ops.edge_symmetry_impl(ei2) is False
+    dup = torch.cat([ei, ei[:, :1]], 1)             # one direction duplicated: multiplicities differ
+    assert ops.edge_symmetry_impl(dup) is (bool(ei[0, 0] == ei[1, 0]))
+    assert ops.edge_symmetry_impl(torch.zeros(2, 0, dtype=torch.int64, device=DEV)) is True
+    gs = G.GraphStructure(ei, 5000)
+    assert gs.symmetric and gs.bwd_plain is gs.fwd
+    x = torch.randn(5000, 32, device=DEV)
+    a = ops.aggregate_prescaled_impl(gs.bwd_plain, x, None, 0, None, None, 0)
+    b = ops.aggregate_prescaled_impl(gs.bwd, x, None, 0, None, None, 0)
+    assert gs.bwd_plain is gs.bwd                   # once built, the exact by-source structure is used
+    torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+    assert_bitexact(gs.out_degree().cpu().numpy(), np.diff(gs.bwd.rowptr.cpu().numpy()).astype(np.float32), "deg")
+    gs2 = G.GraphStructure(ei2, 5000)
+    assert not gs2.symmetric and gs2.bwd_plain is gs2.bwd
