@@ -172,7 +172,7 @@ def run_reference(args):
         "e2e": {"value": gedges, "unit": "GEdges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -392,13 +392,26 @@ def run_ours(args):
             "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"1 of the {args.graphs} graphs (N={graphs[0]['x'].shape[0]}, E={e1g}), best of "
                       f"{args.cpu_steps} steps after 1 warm-up, oracle port on torch CPU fp32"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else this process (or NCCL, which prints its
+    version banner on fd 1 when NCCL_DEBUG is set) writes to fd 1 is diverted to stderr"""
+    os.write(_JSON_OUT if _JSON_OUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -166,15 +166,24 @@ __global__ void __launch_bounds__(256) k_radix_hist(const uint32_t* __restrict__
   block_hist[(int64_t)threadIdx.x * num_blocks + blockIdx.x] = s;
 }
 
+// Scatter pass.  The tile is first ordered by digit in shared memory (stable: digit, then warp, round, lane)
+// and then written out run by run, so the items of one digit leave as one contiguous, coalesced run per
+// array (measured at 37.5 M pairs: 0.70 ms with direct 4-byte scatters from registers, each its own sector).
 __global__ void __launch_bounds__(256)
     k_radix_scatter(const uint32_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                     uint32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n,
                     int shift, const int32_t* __restrict__ block_off, int num_blocks) {
-  __shared__ int32_t wh[kRsWarps][256];
+  __shared__ int32_t wh[kRsWarps][256];     // per-warp digit counts, then tile-local start of (digit, warp)
+  __shared__ int32_t dig_start[256];        // tile-local start of the digit's run
+  __shared__ int32_t dig_gbase[256];        // global position of the run's first item
+  __shared__ int32_t scan_w[8];
+  __shared__ uint32_t s_key[kRsTile];
+  __shared__ int32_t s_val[kRsTile];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < kRsWarps * 256; i += 256) (&wh[0][0])[i] = 0;
   __syncthreads();
-  const int64_t wbase = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (32 * kRsRounds);
+  const int64_t tbase = (int64_t)blockIdx.x * kRsTile;
+  const int64_t wbase = tbase + (int64_t)warp * (32 * kRsRounds);
   const unsigned lt = (1u << lane) - 1u;
   uint32_t key[kRsRounds];
 #pragma unroll
@@ -188,12 +197,30 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   {
-    int32_t base = block_off[(int64_t)threadIdx.x * num_blocks + blockIdx.x];
+    // thread d: total of digit d in the tile -> exclusive scan over the 256 digits -> starts per (digit, warp)
+    const int d = threadIdx.x;
+    int32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) tot += wh[w][d];
+    int32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) scan_w[warp] = inc;
+    __syncthreads();
+    int32_t wpre = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) wpre += (w < warp) ? scan_w[w] : 0;
+    int32_t start = wpre + inc - tot;
+    dig_start[d] = start;
+    dig_gbase[d] = block_off[(int64_t)d * num_blocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w) {
-      const int32_t c = wh[w][threadIdx.x];
-      wh[w][threadIdx.x] = base;
-      base += c;
+      const int32_t c = wh[w][d];
+      wh[w][d] = start;
+      start += c;
     }
   }
   __syncthreads();
@@ -204,15 +231,25 @@ __global__ void __launch_bounds__(256)
     const uint32_t d = valid ? ((key[r] >> shift) & 255u) : 256u;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & lt);
-    int32_t dst = 0;
-    if (valid) dst = wh[warp][d] + rank;
+    int32_t lp = 0;
+    if (valid) lp = wh[warp][d] + rank;
     __syncwarp();
     if (valid && rank == 0) wh[warp][d] += __popc(peers);
     __syncwarp();
     if (valid) {
-      keys_out[dst] = key[r];
-      vals_out[dst] = vals_in ? vals_in[idx] : (int32_t)idx;
+      s_key[lp] = key[r];
+      s_val[lp] = vals_in ? vals_in[idx] : (int32_t)idx;
     }
+  }
+  __syncthreads();
+  const int64_t rem = n - tbase;
+  const int cnt = rem < kRsTile ? (int)rem : kRsTile;
+  for (int k = threadIdx.x; k < cnt; k += 256) {
+    const uint32_t kk = s_key[k];
+    const uint32_t d = (kk >> shift) & 255u;
+    const int32_t dst = dig_gbase[d] + (k - dig_start[d]);
+    keys_out[dst] = kk;
+    vals_out[dst] = s_val[k];
   }
 }
 

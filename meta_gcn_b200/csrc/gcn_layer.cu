@@ -104,7 +104,7 @@ struct LayerFwdArgs {
 #define MGCN_GATHER_U 4   // row gathers in flight per lane group
 #endif
 #ifndef MGCN_FWD_MINB
-#define MGCN_FWD_MINB 2   // resident CTAs per SM the forward kernel is compiled for
+#define MGCN_FWD_MINB 5   // resident CTAs per SM the forward kernel is compiled for
 #endif
 #ifndef MGCN_AGG_MINB
 #define MGCN_AGG_MINB 3
@@ -359,7 +359,10 @@ __device__ __forceinline__ void fwd_tile_tail(const LayerFwdArgs& a, float (*Xs)
   __syncwarp();  // tile buffers are free for the next tile
 }
 
-constexpr int kFwdWarps = 8;
+#ifndef MGCN_FWD_WARPS
+#define MGCN_FWD_WARPS 4   // 4 warps x 5 CTAs/SM at 96 registers: 20 resident warps (0.84 ms vs 0.86 for 8 x 2)
+#endif
+constexpr int kFwdWarps = MGCN_FWD_WARPS;
 constexpr int kFwdSmemFloats = 4 * kPlane + kFwdWarps * 2 * 16 * kLda;
 
 __device__ __forceinline__ void fwd_fill_planes(const LayerFwdArgs& a, float* planes, int tid, int nthreads) {
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, MGCN_FWD_MINB) k_layer_fwd(con
 }
 
 // hub rows: partial sums of the row's segments added left to right, then the same tile tail
-__global__ void __launch_bounds__(kFwdWarps * 32, 3) k_layer_fwd_hubs(const LayerFwdArgs a) {
+__global__ void __launch_bounds__(kFwdWarps * 32, 2) k_layer_fwd_hubs(const LayerFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* planes = smem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -543,6 +546,7 @@ __device__ __forceinline__ void agg_finish_row(const AggFlatArgs& a, Row8 acc, f
 
 __global__ void __launch_bounds__(256, MGCN_AGG_MINB) k_agg_flat(const AggFlatArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
   const int sub = lane & 3, grp = lane >> 2, grp_lane0 = grp * 4;
   const unsigned gmask = 0xfu << grp_lane0;
   const int col = sub * 8;
@@ -599,8 +603,6 @@ __global__ void __launch_bounds__(256) k_agg_flat_hubs(const AggFlatArgs a) {
   for (int64_t k = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 8 + grp; k < nh; k += G) {
     const int64_t row = __ldg(a.hub_rows + k);
     const int s0 = __ldg(a.hub_seg0 + k);
-    const int len = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
-    const int nseg = (len + a.hub_threshold - 1) / a.hub_threshold;
     const Row8 tot = sum_partials(a.partial, s0, 1, col);   // reduced by k_hub_reduce
     agg_finish_row(a, tot, a.post ? __ldg(a.post + row) : 1.f, row, col, pol);
   }
