@@ -298,6 +298,13 @@ int mgcn_cross_entropy_fwd(const float* logits, const int64_t* target, int64_t N
 int mgcn_cross_entropy_bwd(const float* logits, const int64_t* target, int64_t N, int64_t C, int mean,
                            const float* upstream, float* dlogits, void* stream);
 
+/* Binary-classification counters of src/gcn_meta/optim/metrics.py:8-24 as used at train_botnet.py:296-305:
+ * counts5 = {TP, FP, TN, FN, correct} (int64) with pred = argmax(logits[n,:]) (first maximal class; logits
+ * float [N,C]) or the given pred int64[N] (exactly one of logits / pred is non-NULL); target int64[N].
+ * One pass, integer sums (exact); the reference makes one boolean-mask pass and one host sync per counter. */
+int mgcn_binary_confusion(const float* logits, const int64_t* pred, int64_t N, int64_t C,
+                          const int64_t* target, int64_t* counts5, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

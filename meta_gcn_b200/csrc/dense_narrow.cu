@@ -49,6 +49,78 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Same contract when 256 % (Ho/4) == 0: a thread keeps one 4-column chunk for all its rows, so its Hi x 4
+// weights and the bias sit in registers, there is no per-element division, and 4 rows are in flight per
+// thread (the generic kernel above ran at 1.9 TB/s of stores at the botnet batch).
+__global__ void __launch_bounds__(256)
+    k_linear_small_in_fixed(const float* __restrict__ x, const float* __restrict__ xmask, int64_t N, int Hi,
+                            const float* __restrict__ w, int64_t w_sk, int64_t w_sc, int Ho,
+                            const float* __restrict__ bias, const float* __restrict__ add, int act,
+                            const float* __restrict__ row_scale, float* __restrict__ y) {
+  const int q4 = Ho >> 2, rpb = 256 / q4;
+  const int c = (threadIdx.x % q4) * 4, rl = threadIdx.x / q4;
+  float wv[4][4], bv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wv[k][j] = k < Hi ? __ldg(w + k * w_sk + (c + j) * w_sc) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bv[j] = bias ? __ldg(bias + c + j) : 0.f;
+  const uint64_t pol = policy_evict_first();
+  const int64_t step = (int64_t)gridDim.x * rpb;
+  for (int64_t n0 = (int64_t)blockIdx.x * rpb + rl; n0 < N; n0 += 4 * step) {
+    float xv[4][4], rs[4];
+    float4 av[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t n = n0 + u * step;
+      rs[u] = 1.f;
+      av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xv[u][k] = 0.f;
+      if (n < N) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < Hi) {
+            xv[u][k] = __ldg(x + n * Hi + k);
+            if (xmask && !(__ldg(xmask + n * Hi + k) > 0.f)) xv[u][k] = 0.f;
+          }
+        }
+        if (add) av[u] = ld_f4_hint(add + n * Ho + c, pol);
+        if (row_scale) rs[u] = __ldg(row_scale + n);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t n = n0 + u * step;
+      if (n < N) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < Hi) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(xv[u][k], wv[k][j], o[j]);
+          }
+        }
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] += bv[j];
+        }
+        if (add) { o[0] += av[u].x; o[1] += av[u].y; o[2] += av[u].z; o[3] += av[u].w; }
+        if (act == 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = o[j] < 0.f ? 0.f : o[j];
+        }
+        if (row_scale) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] *= rs[u];
+        }
+        st_f4_hint(y + n * Ho + c, make_float4(o[0], o[1], o[2], o[3]), pol);
+      }
+    }
+  }
+}
+
 // y[n, c] = rs[n] * act( sum_k x[n,k]*(xmask>0) * W(k,c) + bias[c] + add[n,c] ), Ho <= 4, Hi = 4*L with L a
 // power of two <= 32: L lanes per row, float4 each, butterfly sum (fixed order).
 template <int L>
@@ -119,24 +191,52 @@ __global__ void __launch_bounds__(256)
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
-  for (int64_t n = (int64_t)blockIdx.x * RPB + rl; n < N; n += (int64_t)gridDim.x * RPB) {
-    float4 bv = __ldg(reinterpret_cast<const float4*>(bw + n * Hb + 4 * sub));
-    if (bmask) {
-      const float4 m = __ldg(reinterpret_cast<const float4*>(bmask + n * Hb + 4 * sub));
-      bv.x = m.x > 0.f ? bv.x : 0.f; bv.y = m.y > 0.f ? bv.y : 0.f;
-      bv.z = m.z > 0.f ? bv.z : 0.f; bv.w = m.w > 0.f ? bv.w : 0.f;
-    }
-    bs[0] += bv.x; bs[1] += bv.y; bs[2] += bv.z; bs[3] += bv.w;
+  // 4 rows of this thread are fetched before the first is used (one float4 in flight per thread left the
+  // pass at 2.5 TB/s); rows are still accumulated in increasing order
+  const int64_t step = (int64_t)gridDim.x * RPB;
+  for (int64_t n0 = (int64_t)blockIdx.x * RPB + rl; n0 < N; n0 += 4 * step) {
+    float4 bvs[4], ms[4];
+    float avs[4][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < Ka) {
-        float av = __ldg(a + n * Ka + k);
-        if (amask && !(__ldg(amask + n * Ka + k) > 0.f)) av = 0.f;
-        acc[k][0] = fmaf(av, bv.x, acc[k][0]);
-        acc[k][1] = fmaf(av, bv.y, acc[k][1]);
-        acc[k][2] = fmaf(av, bv.z, acc[k][2]);
-        acc[k][3] = fmaf(av, bv.w, acc[k][3]);
-        if (sub == 0) as[k] += av;
+    for (int u = 0; u < 4; ++u) {
+      const int64_t n = n0 + u * step;
+      bvs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ms[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) avs[u][k] = 0.f;
+      if (n < N) {
+        bvs[u] = __ldg(reinterpret_cast<const float4*>(bw + n * Hb + 4 * sub));
+        if (bmask) ms[u] = __ldg(reinterpret_cast<const float4*>(bmask + n * Hb + 4 * sub));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < Ka) {
+            avs[u][k] = __ldg(a + n * Ka + k);
+            if (amask && !(__ldg(amask + n * Ka + k) > 0.f)) avs[u][k] = 0.f;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (n0 + u * step < N) {
+        float4 bv = bvs[u];
+        if (bmask) {
+          const float4 m = ms[u];
+          bv.x = m.x > 0.f ? bv.x : 0.f; bv.y = m.y > 0.f ? bv.y : 0.f;
+          bv.z = m.z > 0.f ? bv.z : 0.f; bv.w = m.w > 0.f ? bv.w : 0.f;
+        }
+        bs[0] += bv.x; bs[1] += bv.y; bs[2] += bv.z; bs[3] += bv.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < Ka) {
+            const float av = avs[u][k];
+            acc[k][0] = fmaf(av, bv.x, acc[k][0]);
+            acc[k][1] = fmaf(av, bv.y, acc[k][1]);
+            acc[k][2] = fmaf(av, bv.z, acc[k][2]);
+            acc[k][3] = fmaf(av, bv.w, acc[k][3]);
+            if (sub == 0) as[k] += av;
+          }
+        }
       }
     }
   }
@@ -228,6 +328,14 @@ bool narrow_linear_applies(int64_t Hi, int64_t Ho, const float* x, const float* 
 int launch_narrow_linear(const float* x, const float* xmask, int64_t N, int64_t Hi, const float* w,
                          int64_t w_sk, int64_t w_sc, int64_t Ho, const float* bias, const float* add,
                          int act, const float* row_scale, float* y, void* stream) {
+  if (Hi <= 4 && Ho % 4 == 0 && Ho <= 1024 && 256 % (Ho / 4) == 0) {
+    const int rpb = 256 / (int)(Ho / 4);
+    int64_t blocks = ceil_div(N > 0 ? N : 1, (int64_t)rpb * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    MGCN_LAUNCH(k_linear_small_in_fixed, (unsigned)blocks, 256, 0, stream, x, xmask, N, (int)Hi, w, w_sk, w_sc,
+                (int)Ho, bias, add, act, row_scale, y);
+    return MGCN_OK;
+  }
   if (Hi <= 4 && Ho % 4 == 0) {
     MGCN_LAUNCH(k_linear_small_in, stream_grid(N * (Ho / 4), 256), 256, 0, stream, x, xmask, N, (int)Hi,
                 w, w_sk, w_sc, (int)Ho, bias, add, act, row_scale, y);

@@ -253,7 +253,25 @@ __global__ void __launch_bounds__(256) k_hub_reduce(const int32_t* __restrict__ 
     Row8 run;
 #pragma unroll
     for (int q = 0; q < 8; ++q) run.v[q] = 0.f;
-    if (q0 < q1) run = sum_partials(partial, s0 + q0, q1 - q0, col);
+    {
+      // this group's run, 8 loads issued ahead of the (ordered) adds
+      const float* pp = partial + (int64_t)(s0 + q0) * kH + col;
+      int q = q0;
+      for (; q + 8 <= q1; q += 8, pp += 8 * kH) {
+        Row8 b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b[u] = ld_row8(pp + u * kH);
+        // one statement after the 8 loads that every first add depends on: keeps the loads together
+        asm volatile("" : "+f"(b[0].v[0]), "+f"(b[1].v[0]), "+f"(b[2].v[0]), "+f"(b[3].v[0]), "+f"(b[4].v[0]),
+                          "+f"(b[5].v[0]), "+f"(b[6].v[0]), "+f"(b[7].v[0]));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) row8_add(run, b[u]);
+      }
+      for (; q < q1; ++q, pp += kH) {
+        const Row8 b = ld_row8(pp);
+        row8_add(run, b);
+      }
+    }
     Row8 tot = run;   // group 0: its own run; then runs 1..7 in order
 #pragma unroll
     for (int g = 1; g < 8; ++g) {

@@ -123,3 +123,69 @@ extern "C" int mgcn_cross_entropy_bwd(const float* logits, const int64_t* target
               upstream, dlogits);
   return MGCN_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Binary-classification counters of src/gcn_meta/optim/metrics.py:8-24 (train_botnet.py:296-305) in one pass:
+// counts = {TP, FP, TN, FN, correct} over pred = argmax(logits, 1) (first maximal class) or a given pred.
+// The reference makes five boolean-mask passes with a host synchronisation each.  Integer sums: exact and
+// independent of scheduling.
+// -------------------------------------------------------------------------------------------------
+namespace mgcn {
+__global__ void __launch_bounds__(256)
+    k_confusion(const float* __restrict__ logits, const int64_t* __restrict__ pred, int64_t N, int C,
+                const int64_t* __restrict__ target, unsigned long long* __restrict__ counts) {
+  unsigned long long c5[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p;
+    if (logits) {
+      const float* z = logits + n * C;
+      float m = z[0];
+      p = 0;
+      for (int c = 1; c < C; ++c) {
+        if (z[c] > m) {
+          m = z[c];
+          p = c;
+        }
+      }
+    } else {
+      p = pred[n];
+    }
+    const int64_t y = target[n];
+    c5[0] += (p == 1 && y == 1);
+    c5[1] += (p == 1 && y == 0);
+    c5[2] += (p == 0 && y == 0);
+    c5[3] += (p == 0 && y == 1);
+    c5[4] += (p == y);
+  }
+  __shared__ unsigned long long red[8][5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    unsigned long long v = c5[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    unsigned long long v = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (v) atomicAdd(counts + threadIdx.x, v);
+  }
+}
+}  // namespace mgcn
+
+extern "C" int mgcn_binary_confusion(const float* logits, const int64_t* pred, int64_t N, int64_t C,
+                                     const int64_t* target, int64_t* counts5, void* stream) {
+  MGCN_REQUIRE(counts5 != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(N >= 0 && C >= 1 && C < (int64_t(1) << 20), MGCN_ERR_RANGE);
+  MGCN_REQUIRE((logits != nullptr) != (pred != nullptr) || N == 0, MGCN_ERR_NULL);   // exactly one source
+  MGCN_CHECK_CUDA(cudaMemsetAsync(counts5, 0, 5 * sizeof(int64_t), static_cast<cudaStream_t>(stream)));
+  if (N == 0) return MGCN_OK;
+  MGCN_REQUIRE(target != nullptr, MGCN_ERR_NULL);
+  int64_t blocks = ceil_div(N, 256 * 4);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  MGCN_LAUNCH(k_confusion, (unsigned)blocks, 256, 0, stream, logits, pred, N, (int)C, target,
+              reinterpret_cast<unsigned long long*>(counts5));
+  return MGCN_OK;
+}

@@ -160,6 +160,32 @@ def weighted_degree_impl(csr, edge_weight, loop_weight):
     return deg
 
 
+def binary_confusion_impl(target, logits=None, pred=None):
+    """device int64[5] = {TP, FP, TN, FN, correct} (mgcn_binary_confusion); no host synchronisation"""
+    if (logits is None) == (pred is None):
+        raise ValueError("exactly one of logits / pred")
+    src = logits if logits is not None else pred
+    _need_cuda(src, target)
+    if target.dtype != torch.int64:
+        raise TypeError("target must be int64 (batch.y.long())")
+    target = target.contiguous()
+    if logits is not None:
+        logits = _f32c(logits, "logits")
+        N, C = logits.shape
+    else:
+        if pred.dtype != torch.int64:
+            raise TypeError("pred must be int64")
+        pred = pred.contiguous()
+        N, C = pred.numel(), 2
+    if target.numel() != N:
+        raise ValueError("pred / logits and target differ in length")
+    out = torch.empty(5, dtype=torch.int64, device=src.device)
+    _lib.check(_lib.load().mgcn_binary_confusion(_ptr(logits) if logits is not None else None,
+                                                 _ptr(pred) if pred is not None else None, N, C,
+                                                 _ptr(target), _ptr(out), _stream()))
+    return out
+
+
 def edge_symmetry_impl(edge_index):
     """True iff the directed edge multiset equals its transpose (mgcn_edge_fingerprint).  Reads four words
     back from the device: one host synchronisation per edge_index."""

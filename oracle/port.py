@@ -225,3 +225,30 @@ def aggregate_dense_f64(edge_index, num_nodes, x, weights=None):
     w = np.ones(ei.shape[1]) if weights is None else np.asarray(weights, dtype=np.float64)
     np.add.at(A, (ei[1], ei[0]), w)
     return A @ np.asarray(x, dtype=np.float64)
+
+
+def binary_metrics(pred, target):
+    """src/gcn_meta/optim/metrics.py:8-60 restated on numpy integer arrays: returns
+    [accuracy, TP, FP, TN, FN, recall, precision, f1, fpr, fnr] with NaN where the reference raises
+    ZeroDivisionError (recall / fpr / fnr, and f1 through recall), -1 / 0 where it catches it
+    (precision :38-39, f1 :47-48)."""
+    pred = np.asarray(pred).astype(np.int64)
+    target = np.asarray(target).astype(np.int64)
+    tp = int(((pred == 1) & (target == 1)).sum())      # :13
+    fp = int(((pred == 1) & (target == 0)).sum())      # :17
+    tn = int(((pred == 0) & (target == 0)).sum())      # :21
+    fn = int(((pred == 0) & (target == 1)).sum())      # :25
+    acc = int((pred == target).sum()) / target.size    # :9
+    pos, neg, ppos = int((target == 1).sum()), int((target == 0).sum()), int((pred == 1).sum())
+    nan = float("nan")
+    rec = tp / pos if pos else nan                     # :31
+    prec = tp / ppos if ppos else -1                   # :35-39
+    if pos == 0:
+        f1 = nan                                       # recall raises before the try of :46
+    elif prec + rec == 0:
+        f1 = 0                                         # :47-48
+    else:
+        f1 = 2 * (prec * rec) / (prec + rec)
+    fpr = fp / neg if neg else nan                     # :52
+    fnr = fn / pos if pos else nan                     # :59
+    return np.array([acc, tp, fp, tn, fn, rec, prec, f1, fpr, fnr], dtype=np.float64)

@@ -182,3 +182,16 @@ def test_oracle_kernel_nets_match_reference_files(name):
     for k, p in net.named_parameters():
         if "grad." + k in g:
             assert_parity(p.grad, g["grad." + k], f"{name}.grad.{k}", rtol=tol, scale_atol=tol)
+
+
+def test_binary_metrics_restatement_matches_reference_golden():
+    """oracle.port.binary_metrics against the values the UNMODIFIED src/gcn_meta/optim/metrics.py produced
+    (oracle/make_golden.py case_metrics), including its division-by-zero behaviour"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for k in range(3):
+        logits, y = g[f"logits{k}"], g[f"y{k}"]
+        pred = logits.argmax(1)
+        got = port.binary_metrics(pred, y)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(g[f"vals{k}"]))
+        np.testing.assert_allclose(got, g[f"vals{k}"], rtol=0, atol=0, equal_nan=True)
