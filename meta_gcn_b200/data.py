@@ -82,6 +82,70 @@ class GraphBatch:
         return GraphBatch(torch.cat(xs), torch.cat(eis, dim=1), y, torch.cat(ids), sx, se)
 
 
+class DeviceLoader:
+    """Prefetching loader over pinned host GraphBatches (the role of num_workers in
+    src/gcn_meta/data/dataloader.py:6-30 and of `batch.to(device)` at train_botnet.py:282): the H2D copy of
+    batch k+1 runs on a second stream while batch k computes, into `slots` preallocated device slots per field,
+    so the steady state allocates nothing (a fresh 600 MB allocation per step costs a cudaMalloc and its
+    device synchronisation).  A slot is overwritten only after the work enqueued for its previous batch.
+
+        for batch in DeviceLoader(host_batches, "cuda"):      # host_batches: iterable of GraphBatch
+            loss = step(batch)
+    """
+
+    FIELDS = ("x", "edge_index", "y", "batch")
+
+    def __init__(self, batches, device, slots=2):
+        self.batches = batches
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceLoader copies to a CUDA device (no CPU path)")
+        self.slots = [dict() for _ in range(max(2, int(slots)))]
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _copy(self, host, k):
+        """enqueue host -> slot k on the copy stream; returns (device batch, event)"""
+        slot = self.slots[k]
+        cur = torch.cuda.current_stream(self.device)
+        free = torch.cuda.Event()
+        free.record(cur)                       # everything enqueued so far (incl. this slot's previous batch)
+        self.stream.wait_event(free)
+        out = {}
+        with torch.cuda.stream(self.stream):
+            for name in self.FIELDS:
+                src = getattr(host, name)
+                if src is None:
+                    out[name] = None
+                    continue
+                dst = slot.get(name)
+                if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                    dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                    slot[name] = dst
+                dst.copy_(src, non_blocking=True)
+                out[name] = dst
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        b = GraphBatch(out["x"], out["edge_index"], out["y"], out["batch"], host.slices_x, host.slices_e)
+        return b, ev
+
+    def __iter__(self):
+        it = iter(self.batches)
+        try:
+            pending = self._copy(next(it), 0)
+        except StopIteration:
+            return
+        k = 0
+        while pending is not None:
+            b, ev = pending
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            k += 1
+            try:
+                pending = self._copy(next(it), k % len(self.slots))
+            except StopIteration:
+                pending = None
+            yield b
+
+
 # ------------------------------------------------------------------------------------------------
 # edge preprocessing with the reference's ordering (data_procs/undirected.py:6-35, loop.py:13-17,
 # data_add_degree.py:45-65): symmetrise, sort-unique by (src,dst), append loops, out-degree
