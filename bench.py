@@ -30,7 +30,7 @@ LAYERS = 12
 HIDDEN = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of k_layer_fwd per launch at the default workload, from
 # the ncu --set full capture summarised in profiles/ (None until captured for the current kernel)
-TRAFFIC_FWD_BYTES = 2_089_572_000   # profiles/r1_ncu_k_layer_fwd.csv: 1.1997 GB read + 0.8899 GB written
+TRAFFIC_FWD_BYTES = 2_103_522_000   # profiles/r1b_ncu_k_layer_fwd.csv: 1.2161 GB read + 0.8874 GB written
 CFG = dict(in_channels=1, enc_sizes=[HIDDEN] * LAYERS, num_classes=2, non_linear="relu",
            non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj",
            pred_on="node", nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="add", bias=False)
@@ -286,7 +286,10 @@ def run_ours(args):
 
     fwd_ms = time_kernel(lambda: ops.gcn_layer_fwd_impl(gs.fwd, feat, xin, None, w_a, r_b, w_b, None, dis, dis, 1))
     agg_ms = time_kernel(lambda: ops.aggregate_prescaled_impl(gs.bwd, feat, dis, 0, None, None, 0))
-    del feat, xin
+    hbits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n_nodes,), device=dev, dtype=torch.int64).to(torch.int32)
+    gyv = torch.randn(n_nodes, HIDDEN, device=dev)
+    bwd_ms = time_kernel(lambda: ops.gcn_layer_bwd_impl(feat, gyv, xin, w_a, w_b, hbits, dis, True, True))
+    del feat, xin, gyv, hbits
 
     # ---- end to end from pinned host buffers through the public API ----
     e2e_ms = None
@@ -363,6 +366,12 @@ def run_ours(args):
                                        "achieved": agg_bytes / (agg_ms / 1e3) / 1e9,
                                        "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / peak_bw,
                                        "gather_l2_to_sm_gbs": n_edges * HIDDEN * 4 / (agg_ms / 1e3) / 1e9},
+                     "third_kernel": {"kernel": "k_layer_bwd_tc: row-local backward (4 products, both ReLU masks) on "
+                                                "tcgen05.mma / TMEM, warp-specialised",
+                                      "algorithmic_bytes_per_launch": 5 * 4 * n_nodes * HIDDEN + 8 * n_nodes,
+                                      "ms_per_launch": bwd_ms,
+                                      "achieved": (5 * 4 * n_nodes * HIDDEN + 8 * n_nodes) / (bwd_ms / 1e3) / 1e9,
+                                      "frac": (5 * 4 * n_nodes * HIDDEN + 8 * n_nodes) / (bwd_ms / 1e3) / 1e9 / peak_bw},
                      "step_algorithmic_bytes": step_bytes,
                      "step_frac": step_bytes / t / 1e9 / peak_bw,
                      "step_frac_of_nominal_8TBs": step_bytes / t / 1e9 / 8000.0},

@@ -6,20 +6,28 @@
 // tcgen05.mma per 64-row tile:
 //   row-local   D[64 x 64|32] (+)= A_K[64 x 8] * B_K[64|32 x 8]^T        K-major, un-swizzled interleaved images
 //               TMEM cols [0,32) main = dxw_hi Wt_hi + gy_hi R_hi; [32,64) = hi * B_lo + lo * B_hi (both corrections)
-//               (M = 64 accumulators live in lanes 0..15 of each 32-lane TMEM quarter)
+//               (M = 64 accumulators occupy 16 lanes of each 32-lane TMEM quarter; the D address may start at lane 0
+//               or 16, so the two tiles of a pair share one set of columns: tile 2j in lanes 0..15, tile 2j+1 in 16..31)
 //   transposed  [D1 | D2][128 x 64] (+)= [dxw_hi|gy_hi|dxw_lo|gy_lo]^T[128 x 8 rows] * [x_hi | x_lo][8 rows x 64]
-//               MN-major, SWIZZLE_128B_BASE32B images, TMEM cols [96,160)
+//               MN-major, SWIZZLE_128B_BASE32B images, TMEM cols [64,128) (tile 2j) and [128,192) (tile 2j+1)
 //               rows 0-31 -> dW^T, 32-63 -> dR (main terms), 64-127 -> their corrections
 // (a 32-bit MN-major operand is only read correctly from the BASE32B image, a K-major one never from it —
 // scripts/tc_probe.cu — hence dxw and gy are stored in both images.)  Chains through the TMEM accumulator
 // stay short (8 steps) and start from zero in every tile; sums over tiles are RN adds in registers;
-// per-CTA partials are reduced in a fixed order.  Two persistent CTAs per SM (98 KB of images, 256 TMEM
-// columns each); the next tile is prefetched into registers while the current one is processed.
+// per-CTA partials are reduced in a fixed order.
 //
-// Status (profiles/r1_layer_summary.md): parity-green, 0.99 ms per layer at the botnet batch against 0.83 ms
-// for the mma.sync kernel — 23 % of warp time waits on the MMA barrier, 16 % on the end-of-tile barrier
-// (the G epilogue runs on 64 of 256 threads), 14 % on the prefetched loads.  Next step: warp-specialised
-// producer / MMA / epilogue roles over double-buffered images instead of CTA-wide phases.
+// One persistent CTA per SM, 24 warps in three roles (k_layer_bwd_tc below):
+//   producers  2 sets x 8 warps, set p owns operand stage p (80 KB of images) and the tiles with it % 2 == p:
+//              LDG.256 one tile ahead -> split -> 20 conflict-free STS.128 per thread; warp 0 of a set also issues
+//              the tile's tcgen05.mma and commits to the stage's `done` barrier
+//   epilogue   8 warps (TMEM quarter = warp % 4, column half = warp / 4) work on tile PAIRS: all 32 lanes carry a
+//              G row, outputs are staged in shared memory (144-byte rows) and leave as whole 512-byte row groups
+//   barriers   full[stage] producers -> issuer, done[pair buffer][set] tensor core -> producers + epilogue,
+//              tfree[pair buffer] epilogue -> issuers   (done is per pair buffer so that no waiter can be lapped)
+// Measured at the botnet batch (profiles/r1b_layer_summary.md): 0.99 ms as CTA-wide phases -> 0.58 ms, against 0.81 ms
+// for the mma.sync kernel; 4.0 TB/s of algorithmic bytes.  The limiter is now the shared-memory data pipe
+// (l1tex__data_pipe_lsu_wavefronts 83 %: 47 M store wavefronts for the ten images + the tensor core's operand
+// reads), not HBM (48 %) or the tensor pipe (23 %).
 #include <mutex>
 
 #include "common.cuh"
@@ -28,8 +36,7 @@
 namespace mgcn {
 
 constexpr int kTH = 32;
-constexpr int kTRows = 64;                 // rows per tile: two CTAs (98 KB of images each) share an SM, so one
-                                           // CTA's split / epilogue overlaps the other's tensor-core phase
+constexpr int kTRows = 64;                 // rows per tile (M = 64 accumulators; two operand stages of 80 KB fit one SM)
 constexpr int kTileB = kTRows * kTH * 4;   // 8 KB per image
 
 struct BwdTcArgs {
