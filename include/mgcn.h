@@ -248,6 +248,17 @@ int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n_in, const 
                        int act_out, int64_t H, float* x_next, float* m_next, uint32_t* hmask,
                        void* workspace, size_t* workspace_bytes, void* stream);
 
+/* First layer of the stack when its input is narrow (H_in <= 4; the botnet model feeds x = ones[N,1],
+ * train_botnet.py:286): the layer is aggregated BEFORE its transform — s = sum_j pre_j x_j by mgcn_spmm on
+ * [N,H_in] — and this launch forms, reading only s and x,
+ *     h = relu(post * (s W_in)),  y = h + x R^T + r,  x' = act(y),  m' = pre * (x' W_next),  hmask = bits(h > 0)
+ * i.e. NodeModelAdditive.forward (gcn_base_models.py:199-243) + the residual Linear / ReLU of gcn_model.py:96-105
+ * for layer 0 without materialising x W_in or x R^T.  w_in [H_in][32] (in,out), res_w [32][H_in] (out,in). */
+int mgcn_gcn_first_layer_fwd(const float* s, const float* x, int64_t N, int64_t Hin, const float* w_in,
+                             const float* res_w, const float* res_b, const float* w_next, const float* pre,
+                             const float* post, int act_out, int64_t H, float* x_next, float* m_next,
+                             uint32_t* hmask, void* stream);
+
 /* backward, row-local part of layer n (dxw = pre * A^T gs comes from mgcn_aggregate_prescaled on the
  * structure built by source):
  *   G = dxw w^T + gy res_w;  dw = x^T dxw;  d_res_w = gy^T x;  d_res_b = colsum(gy)

@@ -81,6 +81,13 @@ struct LayerFwdArgs {
   const float* bias;        // node-model bias [32] or NULL
   const float* pre;         // per-source factor of the NEXT layer's messages, or NULL
   const float* post;        // per-target factor, or NULL
+  // first layer with a narrow input (row-local mode only): z = npost * (ns W_in), resid = nx R^T + r, formed
+  // in the kernel from [N, nhin] operands instead of being read as two [N, 32] arrays
+  const float* ns;          // [N, nhin]  aggregated narrow input  sum_j pre_j x_j
+  const float* nx;          // [N, nhin]  narrow layer input
+  const float* nw;          // [nhin][32] weight_node of the first layer (in, out)
+  const float* npost;       // [N] per-target factor or NULL
+  int nhin;
   float* x_next;            // [N, 32]
   float* m_next;            // [N, 32] (with w_next)
   uint32_t* hmask;          // [N]
@@ -471,6 +478,69 @@ __global__ void __launch_bounds__(kFwdWarps * 32, MGCN_FWD_MINB) k_layer_fwd(con
       }
     }
     cp_async_wait_all();
+    __syncwarp();
+    fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane, pol);
+  }
+}
+
+// First layer with a narrow input (mgcn_gcn_first_layer_fwd): row-local, z and the residual term are formed in
+// the kernel from the [N, nhin] operands; then the same tile tail.
+__global__ void __launch_bounds__(kFwdWarps * 32, 4) k_first_layer_fwd(const LayerFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* planes = smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float (*Xs)[kLda] = reinterpret_cast<float (*)[kLda]>(smem + 4 * kPlane + warp * 2 * 16 * kLda);
+  float (*Hs)[kLda] = Xs + 16;
+  fwd_fill_planes(a, planes, tid, kFwdWarps * 32);
+  float* nws = planes;   // W_in [k][c] at 0, R^T [k][c] at 128, r at 256 (the residual planes are unused: a.x == NULL)
+  for (int i = tid; i < a.nhin * kH; i += kFwdWarps * 32) {
+    const int k = i / kH, c = i % kH;
+    nws[i] = __ldg(a.nw + i);
+    nws[128 + i] = __ldg(a.res_w + c * a.nhin + k);
+  }
+  if (tid < kH) nws[256 + tid] = a.res_b ? __ldg(a.res_b + tid) : 0.f;
+  __syncthreads();
+  const int sub = lane & 3, grp = lane >> 2;
+  const unsigned gmask = 0xfu << (grp * 4);
+  const int col = sub * 8;
+  const uint64_t pol = policy_evict_first();
+  const int64_t n_loc = (a.n_rows + 15) >> 4;
+  for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < n_loc; tile += (int64_t)gridDim.x * kFwdWarps) {
+    const int64_t r = tile * 16 + lane;
+    const int myrow = (lane < 16 && r < a.n_rows) ? (int)r : -1;
+    float mypre = 1.f;
+    if (myrow >= 0 && a.pre && a.w_next) mypre = __ldg(a.pre + myrow);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const int rowp = __shfl_sync(0xffffffffu, myrow, 8 * p + grp);
+      if (rowp >= 0) {
+        Row8 z, rs;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          z.v[q] = 0.f;
+          rs.v[q] = 0.f;
+        }
+        for (int k = 0; k < a.nhin; ++k) {
+          const float sv = __ldg(a.ns + (int64_t)rowp * a.nhin + k);
+          const float xv = __ldg(a.nx + (int64_t)rowp * a.nhin + k);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            z.v[q] = fmaf(sv, nws[k * kH + col + q], z.v[q]);
+            rs.v[q] = fmaf(xv, nws[128 + k * kH + col + q], rs.v[q]);
+          }
+        }
+        const float ps = a.npost ? __ldg(a.npost + rowp) : 1.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          z.v[q] *= ps;
+          rs.v[q] += nws[256 + col + q];
+        }
+        float* xr = &Xs[8 * p + grp][col];
+        *reinterpret_cast<float4*>(xr) = make_float4(rs.v[0], rs.v[1], rs.v[2], rs.v[3]);
+        *reinterpret_cast<float4*>(xr + 4) = make_float4(rs.v[4], rs.v[5], rs.v[6], rs.v[7]);
+        finish_h(a, z, 1.f, rowp, &Hs[8 * p + grp][0], sub, gmask, col);
+      }
+    }
     __syncwarp();
     fwd_tile_tail(a, Xs, Hs, planes, myrow, mypre, lane, pol);
   }
@@ -939,6 +1009,42 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
     if (hb > (int64_t)kNumSMs) hb = kNumSMs;
     MGCN_LAUNCH(k_layer_fwd_hubs, (unsigned)hb, kFwdWarps * 32, smem, stream, a);
   }
+  return MGCN_OK;
+}
+
+// First layer of a stack whose input is narrow (H_in <= 4; the botnet model has H_in = 1): the layer is
+// aggregated BEFORE its transform, s = sum_j pre_j x_j (mgcn_spmm on [N, H_in]), and this launch forms
+//   h = relu( post * (s W_in) ),  y = h + x R^T + r,  x' = act(y),  m' = pre * (x' W_next)
+// reading only the two [N, H_in] operands (gcn_base_models.py:201-240 + gcn_model.py:96-105 for layer 0).
+extern "C" int mgcn_gcn_first_layer_fwd(const float* s, const float* x, int64_t N, int64_t Hin, const float* w_in,
+                                        const float* res_w, const float* res_b, const float* w_next,
+                                        const float* pre, const float* post, int act_out, int64_t H,
+                                        float* x_next, float* m_next, uint32_t* hmask, void* stream) {
+  MGCN_REQUIRE(H == kH, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(Hin >= 1 && Hin <= 4, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(act_out == 0 || act_out == 1, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
+  if (N == 0) return MGCN_OK;
+  MGCN_REQUIRE(s && x && w_in && res_w && x_next && hmask, MGCN_ERR_NULL);
+  MGCN_REQUIRE(!w_next || m_next, MGCN_ERR_NULL);
+  MGCN_REQUIRE(aligned16(x_next) && (!m_next || aligned16(m_next)), MGCN_ERR_ALIGN);
+  LayerFwdArgs a{};
+  a.ns = s; a.nx = x; a.nw = w_in; a.npost = post; a.nhin = (int)Hin;
+  a.resid = x_next;   // row-local mode with a finished residual term: the tail reads it from the tile, never from here
+  a.res_w = res_w; a.res_b = res_b; a.w_next = w_next; a.pre = pre;
+  a.x_next = x_next; a.m_next = m_next; a.hmask = hmask;
+  a.n_rows = N;
+  a.act_out = act_out;
+  const size_t smem = sizeof(float) * kFwdSmemFloats;
+  static std::once_flag once;
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(k_first_layer_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  MGCN_CHECK_CUDA(attr_err);
+  int64_t blocks = ceil_div(ceil_div(N, 16), kFwdWarps);
+  if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
+  MGCN_LAUNCH(k_first_layer_fwd, (unsigned)blocks, kFwdWarps * 32, smem, stream, a);
   return MGCN_OK;
 }
 

@@ -87,23 +87,24 @@ class _ResidualGCNStack32(torch.autograd.Function):
         fwd = graph.fwd
         x0 = x.contiguous()
         xs, hmasks = [x0], []
-        resid0 = ops.linear_impl(x0, layers[0][1], True, layers[0][2])       # x0 R0^T + r0
         # A first layer of small input width is aggregated BEFORE its transform — (A_hat x) W instead of
         # A_hat (x W): the gather moves H_in instead of 32 floats per entry, and its backward needs no
-        # transposed aggregation at all:  dW_0 = s^T gs_0  with  s = sum_j pre_j x_j  saved here.
+        # transposed aggregation at all:  dW_0 = s^T gs_0  with  s = sum_j pre_j x_j  saved here.  The layer's
+        # two [N,32] operands (s W_0 and x R_0^T + r_0) are formed inside its launch (mgcn_gcn_first_layer_fwd).
         agg_first = x0.size(1) <= 4 and not ctx.needs_input_grad[0]
-        s0 = None
+        s0 = resid0 = None
         if agg_first:
-            s0 = ops.spmm_impl(fwd, x0, nbr_scale=pre)                        # [N, H_in]
-            m = ops.linear_impl(s0, layers[0][0], False, row_scale=post)      # z0 = post * (s0 W0)
+            xs0 = x0 * pre.unsqueeze(1) if pre is not None else x0            # pre_j x_j, one rounding as in the gather
+            s0 = ops.spmm_impl(fwd, xs0)                                      # [N, H_in]
         else:
+            resid0 = ops.linear_impl(x0, layers[0][1], True, layers[0][2])    # x0 R0^T + r0
             m = ops.linear_impl(x0, layers[0][0], False, row_scale=pre)       # messages of layer 0
         for n in range(L):
             w_next = layers[n + 1][0] if n + 1 < L else None
             act_out = 1 if (last_relu or n < L - 1) else 0
             if n == 0 and agg_first:
-                xn, m, hm = ops.gcn_layer_fwd_impl(None, m, None, resid0, layers[0][1], layers[0][2], w_next,
-                                                   None, pre, None, act_out)
+                xn, m, hm = ops.gcn_first_layer_fwd_impl(s0, x0, layers[0][0], layers[0][1], layers[0][2], w_next,
+                                                         pre, post, act_out)
             else:
                 xn, m, hm = ops.gcn_layer_fwd_impl(
                     fwd, m, xs[n] if n > 0 else None, resid0 if n == 0 else None,

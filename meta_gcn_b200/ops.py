@@ -369,6 +369,32 @@ def gcn_layer_fwd_impl(csr, m, x, resid, res_w, res_b, w_next, bias, pre, post, 
     return x_next, m_next, hmask
 
 
+def gcn_first_layer_fwd_impl(s, x, w_in, res_w, res_b, w_next, pre, post, act_out):
+    """first layer with a narrow input (mgcn_gcn_first_layer_fwd): s = aggregated input [N,Hin], x = layer input
+    [N,Hin]; returns (x_next [N,32], m_next | None, hmask int32[N])"""
+    _need_cuda(s, x, w_in, res_w, res_b, w_next, pre, post)
+    s = _f32c(s, "s")
+    x = _f32c(x, "x")
+    w_in = _f32c(w_in, "w_in")
+    res_w = _f32c(res_w, "res_w")
+    res_b = _f32c(res_b, "res_b")
+    w_next = _f32c(w_next, "w_next")
+    pre = _f32c(pre, "pre")
+    post = _f32c(post, "post")
+    N, Hin = x.shape
+    H = w_in.size(1)
+    if s.shape != x.shape or w_in.size(0) != Hin or tuple(res_w.shape) != (H, Hin):
+        raise ValueError("shape mismatch in gcn_first_layer_fwd")
+    dev = x.device
+    x_next = torch.empty(N, H, dtype=torch.float32, device=dev)
+    m_next = torch.empty(N, H, dtype=torch.float32, device=dev) if w_next is not None else None
+    hmask = torch.empty(N, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().mgcn_gcn_first_layer_fwd(
+        _ptr(s), _ptr(x), N, Hin, _ptr(w_in), _ptr(res_w), _ptr(res_b), _ptr(w_next), _ptr(pre), _ptr(post),
+        int(act_out), H, _ptr(x_next), _ptr(m_next), _ptr(hmask), _stream()))
+    return x_next, m_next, hmask
+
+
 def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, tensor_memory=False):
     """row-local backward of one layer at hidden 32 (mgcn_gcn_layer_bwd): returns
     (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b)"""

@@ -142,3 +142,35 @@ def test_layer_fwd_row_local_mode(n):
     bits = hm.cpu().numpy().astype(np.uint32)
     got = ((bits[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(bool)
     assert (got == (z.numpy() > 0)).all()
+
+
+@pytest.mark.parametrize("n,hin,act_out,with_next", [(1000, 1, 1, True), (1003, 2, 0, False), (37, 4, 1, True), (150001, 1, 1, True)])
+def test_first_layer_fwd_narrow_input(n, hin, act_out, with_next):
+    """mgcn_gcn_first_layer_fwd: h = relu(post (s W)), y = h + x R^T + r, x' = act(y), m' = pre (x' W') from the
+    two [N, H_in] operands (gcn_base_models.py:199-243 + gcn_model.py:96-105 for layer 0), fp64 restatement"""
+    gen = torch.Generator().manual_seed(n + hin)
+    s = torch.randn(n, hin, generator=gen)
+    x = torch.randn(n, hin, generator=gen)
+    w_in = torch.randn(hin, H, generator=gen)
+    res_w = torch.randn(H, hin, generator=gen)
+    res_b = torch.randn(H, generator=gen)
+    w_next = torch.randn(H, H, generator=gen) / H ** 0.5
+    pre = torch.rand(n, generator=gen) + 0.1
+    post = torch.rand(n, generator=gen) + 0.1
+    d = lambda t: t.to(DEV)
+    xn, mn, hm = ops.gcn_first_layer_fwd_impl(d(s), d(x), d(w_in), d(res_w), d(res_b), d(w_next) if with_next else None,
+                                              d(pre), d(post), act_out)
+    D = lambda t: t.double()
+    z = D(post).view(-1, 1) * (D(s) @ D(w_in))
+    y = torch.relu(z) + D(x) @ D(res_w).t() + D(res_b)
+    x_ref = torch.relu(y) if act_out else y
+    assert_parity(xn, x_ref, "x_next")
+    if with_next:
+        assert_parity(mn, D(pre).view(-1, 1) * (x_ref @ D(w_next)), "m_next")
+    else:
+        assert mn is None
+    bits = hm.cpu().numpy().astype(np.uint32)
+    got = ((bits[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(bool)
+    zf = (post.view(-1, 1) * (s @ w_in)).numpy()
+    sure = np.abs(z.numpy()) > 1e-5          # sign of z is unambiguous away from zero
+    assert (got == (zf > 0))[sure].all()
