@@ -61,6 +61,8 @@ struct WideArgs {
   int Hi, Ho, n_chunks, act;
 };
 
+constexpr int kWLdo = 36;   // floats per staged output row (144 bytes)
+
 __global__ void __launch_bounds__(kWThreads, 1) k_linear_wide(const WideArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -169,38 +171,51 @@ __global__ void __launch_bounds__(kWThreads, 1) k_linear_wide(const WideArgs a) 
     tile_phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
-      const int64_t row = tile * kWM + 32 * (warp & 3) + lane;
+      // A TMEM lane is an output row, so a thread holds 32 consecutive columns of ITS row: stored directly, a warp
+      // instruction would touch 32 different 128-byte lines (measured in k_layer_bwd_tc: the LSU pays per line).
+      // Each warp therefore transposes its 32 x 32 slab through a private staging tile (144-byte rows:
+      // conflict-free both ways) and stores 4 whole 128-byte row pieces per instruction; `add` is read the same way.
+      const int64_t row0 = tile * kWM + 32 * (warp & 3);
       const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
       const int half = a.Ho / 2;
-      const float rs = (a.row_scale && row < a.n_rows) ? __ldg(a.row_scale + row) : 1.f;
+      // (the staging tiles alias operand stage 0: every MMA of the tile has completed, tile_done)
+      float* stg = reinterpret_cast<float*>(smem) + warp * (32 * kWLdo);
+      const int sr = lane >> 3, sq = lane & 7;          // phase 2: row sr + 4 i of the slab, 16-byte chunk sq
       for (int c0 = (warp >> 2) * half; c0 < (warp >> 2) * half + half; c0 += 32) {
         uint32_t m[32], c[32];
         tmem_ld32(lane_addr + c0, m);
         tmem_ld32(lane_addr + 256 + c0, c);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < a.n_rows) {
-          float* yp = a.y + row * a.Ho + c0;
-          const float* ap = a.add ? a.add + row * a.Ho + c0 : nullptr;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            float o[4];
+        for (int q = 0; q < 32; q += 4) {
+          float o[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              float v = __uint_as_float(m[q + t]) + __uint_as_float(c[q + t]);
-              if (a.bias) v += __ldg(a.bias + c0 + q + t);
-              o[t] = v;
-            }
-            if (ap) {
-              const float4 av = __ldg(reinterpret_cast<const float4*>(ap + q));
-              o[0] += av.x; o[1] += av.y; o[2] += av.z; o[3] += av.w;
+          for (int t = 0; t < 4; ++t) o[t] = __uint_as_float(m[q + t]) + __uint_as_float(c[q + t]);
+          *reinterpret_cast<float4*>(stg + lane * kWLdo + q) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + 4 * sq));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = sr + 4 * i;
+          const int64_t row = row0 + r;
+          if (row < a.n_rows) {
+            float4 v = *reinterpret_cast<const float4*>(stg + r * kWLdo + 4 * sq);
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (a.add) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(a.add + row * a.Ho + c0 + 4 * sq));
+              v.x += av.x; v.y += av.y; v.z += av.z; v.w += av.w;
             }
             if (a.act == 1) {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) o[t] = o[t] < 0.f ? 0.f : o[t];
+              v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+              v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
             }
-            *reinterpret_cast<float4*>(yp + q) = make_float4(o[0] * rs, o[1] * rs, o[2] * rs, o[3] * rs);
+            const float rs = a.row_scale ? __ldg(a.row_scale + row) : 1.f;
+            *reinterpret_cast<float4*>(a.y + row * a.Ho + c0 + 4 * sq) = make_float4(v.x * rs, v.y * rs, v.z * rs, v.w * rs);
           }
         }
+        __syncwarp();   // the staging tile is rewritten by the next slab
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
