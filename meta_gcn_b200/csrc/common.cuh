@@ -99,6 +99,12 @@ size_t narrow_wgrad_blocks(int64_t N);
 int launch_narrow_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, const float* gmask,
                         int64_t Ho, float* dw, int64_t dw_sk, int64_t dw_sc, float* db, float* part,
                         float* part_db, void* stream);
+// wide weight gradient on tcgen05 (wgrad_wide.cu)
+bool wide_wgrad_applies(int64_t N, int64_t Hi, int64_t Ho, const float* x, const float* g, const float* gmask);
+int wide_wgrad_splits(int64_t Hi);
+int launch_wide_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, const float* gmask, int64_t Ho,
+                      float* dw, int64_t dw_sk, int64_t dw_sc, float* db, float* partial, float* partial_b,
+                      void* stream);
 // out[k*sk + c*sc] = sum_p partial[p*count + k*Hc + c], fixed order
 int launch_reduce_partials(const float* partial, int P, int count, int Hc, float* out, int64_t sk,
                            int64_t sc, void* stream);

@@ -373,7 +373,8 @@ extern "C" int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const
   MGCN_REQUIRE(N >= 0 && N < (int64_t(1) << 31), MGCN_ERR_RANGE);
   MGCN_REQUIRE(Hi >= 1 && Ho >= 1 && Hi <= 65536 && Ho <= 65536, MGCN_ERR_SHAPE);
   const int P = wgrad_slabs(N);
-  const size_t p_max = (size_t)P > narrow_wgrad_blocks(N) ? (size_t)P : narrow_wgrad_blocks(N);
+  size_t p_max = (size_t)P > narrow_wgrad_blocks(N) ? (size_t)P : narrow_wgrad_blocks(N);
+  if (Hi <= 256 && (size_t)wide_wgrad_splits(Hi) > p_max) p_max = (size_t)wide_wgrad_splits(Hi);
   WorkspaceCarver ws(workspace);
   float* partial = ws.take<float>(p_max * Hi * Ho);
   float* partial_b = ws.take<float>(p_max * Ho);
@@ -386,6 +387,8 @@ extern "C" int mgcn_linear_wgrad_ex(const float* x, int64_t N, int64_t Hi, const
   MGCN_REQUIRE(N == 0 || (x && g), MGCN_ERR_NULL);
   if (N > 0 && narrow_wgrad_applies(Hi, Ho, x, g, gmask))
     return launch_narrow_wgrad(x, N, Hi, g, gmask, Ho, dw, dw_sk, dw_sc, db, partial, partial_b, stream);
+  if (N > 0 && wide_wgrad_applies(N, Hi, Ho, x, g, gmask))   // tcgen05 transposed product (wgrad_wide.cu)
+    return launch_wide_wgrad(x, N, Hi, g, gmask, Ho, dw, dw_sk, dw_sc, db, partial, partial_b, stream);
   const int64_t rows_per_slab = ceil_div(ceil_div(N > 0 ? N : 1, P), kWgRows) * kWgRows;
   const int x_vec4 = (Hi % 4 == 0) && aligned16(x);
   const int g_vec4 = (Ho % 4 == 0) && aligned16(g) && (!gmask || aligned16(gmask));

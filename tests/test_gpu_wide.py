@@ -37,3 +37,27 @@ def test_linear_wide_is_deterministic():
     a = ops.linear_impl(x, w, False)
     b = ops.linear_impl(x, w, False)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,hi,ho,masked,out_in", [
+    (40000, 256, 256, False, False),
+    (65537, 100, 256, True, True),       # SAGE first layer at C4: 100 -> 256, ragged row count, masked gradient
+    (33000, 64, 64, False, True),
+    (70011, 128, 192, True, False),
+    (150000, 256, 128, False, False),    # several accumulator chains per CTA
+])
+def test_wide_weight_gradient_tcgen05(n, hi, ho, masked, out_in):
+    """dW = x^T (g * (mask > 0)), db = colsum on tcgen05 (csrc/wgrad_wide.cu: both operands MN-major, 3xTF32,
+    chains cut every 16 chunks) against fp64 — autograd of SAGEConv / GCNConv matmul(x, weight) + bias
+    (kernel/graph_sage.py:10,13; kernel/gcn.py:10,13)"""
+    gen = torch.Generator().manual_seed(n + hi)
+    x = torch.randn(n, hi, generator=gen)
+    g = torch.randn(n, ho, generator=gen)
+    m = torch.randn(n, ho, generator=gen) if masked else None
+    dw, db = ops.linear_wgrad_impl(x.to(DEV), g.to(DEV), out_in, True, gmask=m.to(DEV) if masked else None)
+    gm = g.double() * (m > 0) if masked else g.double()
+    ref = x.double().t() @ gm
+    assert_parity(dw, ref.t() if out_in else ref, "dW")
+    assert_parity(db, gm.sum(0), "db")
+    dw2, db2 = ops.linear_wgrad_impl(x.to(DEV), g.to(DEV), out_in, True, gmask=m.to(DEV) if masked else None)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)      # deterministic: no atomics
