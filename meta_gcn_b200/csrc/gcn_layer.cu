@@ -236,49 +236,84 @@ __device__ __forceinline__ Row8 sum_partials(const float* __restrict__ partial, 
   return tot;
 }
 
+// acc += p[0 .. 4 rows) in row order, the four 256-bit loads issued before the first add.  One asm statement: the
+// compiler otherwise sinks each load next to its add, and an in-order warp then waits a full latency per row.
+__device__ __forceinline__ void row8_add4(Row8& acc, const float* p) {
+  asm volatile(
+      "{\n .reg .f32 a<8>, b<8>, c<8>, d<8>;\n .reg .b64 x0, x1, x2, x3, y0, y1, y2, y3;\n"
+      " ld.global.nc.v8.f32 {a0,a1,a2,a3,a4,a5,a6,a7}, [%8];\n"
+      " ld.global.nc.v8.f32 {b0,b1,b2,b3,b4,b5,b6,b7}, [%8+128];\n"
+      " ld.global.nc.v8.f32 {c0,c1,c2,c3,c4,c5,c6,c7}, [%8+256];\n"
+      " ld.global.nc.v8.f32 {d0,d1,d2,d3,d4,d5,d6,d7}, [%8+384];\n"
+      " mov.b64 x0, {%0,%1}; mov.b64 x1, {%2,%3}; mov.b64 x2, {%4,%5}; mov.b64 x3, {%6,%7};\n"
+      " mov.b64 y0, {a0,a1}; mov.b64 y1, {a2,a3}; mov.b64 y2, {a4,a5}; mov.b64 y3, {a6,a7};\n"
+      " add.rn.f32x2 x0, x0, y0; add.rn.f32x2 x1, x1, y1; add.rn.f32x2 x2, x2, y2; add.rn.f32x2 x3, x3, y3;\n"
+      " mov.b64 y0, {b0,b1}; mov.b64 y1, {b2,b3}; mov.b64 y2, {b4,b5}; mov.b64 y3, {b6,b7};\n"
+      " add.rn.f32x2 x0, x0, y0; add.rn.f32x2 x1, x1, y1; add.rn.f32x2 x2, x2, y2; add.rn.f32x2 x3, x3, y3;\n"
+      " mov.b64 y0, {c0,c1}; mov.b64 y1, {c2,c3}; mov.b64 y2, {c4,c5}; mov.b64 y3, {c6,c7};\n"
+      " add.rn.f32x2 x0, x0, y0; add.rn.f32x2 x1, x1, y1; add.rn.f32x2 x2, x2, y2; add.rn.f32x2 x3, x3, y3;\n"
+      " mov.b64 y0, {d0,d1}; mov.b64 y1, {d2,d3}; mov.b64 y2, {d4,d5}; mov.b64 y3, {d6,d7};\n"
+      " add.rn.f32x2 x0, x0, y0; add.rn.f32x2 x1, x1, y1; add.rn.f32x2 x2, x2, y2; add.rn.f32x2 x3, x3, y3;\n"
+      " mov.b64 {%0,%1}, x0; mov.b64 {%2,%3}, x1; mov.b64 {%4,%5}, x2; mov.b64 {%6,%7}, x3;\n}\n"
+      : "+f"(acc.v[0]), "+f"(acc.v[1]), "+f"(acc.v[2]), "+f"(acc.v[3]), "+f"(acc.v[4]), "+f"(acc.v[5]), "+f"(acc.v[6]),
+        "+f"(acc.v[7])
+      : "l"(p)
+      : "memory");
+}
+
 // One warp per hub row: the row's segment partials -> one row, in place in the hub's first slot.  The biggest
 // hub of a botnet graph has ~230 segments; summed by one lane group with dependent loads it alone took 60 us
 // per aggregation.  Here the 8 lane groups sum 8 contiguous runs of segments concurrently and the 8 run sums
 // are added left to right (a fixed order: deterministic).
+__device__ __forceinline__ Row8 hub_run_sum(const float* __restrict__ partial, int s0, int q0, int q1, int col) {
+  Row8 run;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) run.v[q] = 0.f;
+  if (q0 >= q1) return run;
+  const float* pp = partial + (int64_t)(s0 + q0) * kH + col;
+  int q = q0;
+  for (; q + 4 <= q1; q += 4, pp += 4 * kH) row8_add4(run, pp);
+  for (; q < q1; ++q, pp += kH) {
+    const Row8 b = ld_row8(pp);
+    row8_add(run, b);
+  }
+  return run;
+}
+
+constexpr int kGiantSegs = 32;   // hubs with more segments are summed by a whole CTA (64 runs) instead of a warp (8 runs)
+constexpr int kGiantList = 32;
+
 __global__ void __launch_bounds__(256) k_hub_reduce(const int32_t* __restrict__ hub_rows,
                                                     const int32_t* __restrict__ hub_seg0,
                                                     const int32_t* __restrict__ hub_count,
                                                     const int32_t* __restrict__ rowptr, int64_t hub_cap,
                                                     int hub_threshold, float* __restrict__ partial) {
-  const int lane = threadIdx.x & 31, sub = lane & 3, grp = lane >> 2, col = sub * 8;
+  __shared__ int giant_k[kGiantList];
+  __shared__ int n_giant;
+  __shared__ __align__(16) float red[64][kH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3, grp = lane >> 2, col = sub * 8;
+  if (threadIdx.x == 0) n_giant = 0;
+  __syncthreads();
   int64_t nh = *hub_count;
   if (nh > hub_cap) nh = hub_cap;
   const int64_t W = (int64_t)gridDim.x * 8;
-  for (int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); k < nh; k += W) {
+  for (int64_t k = (int64_t)blockIdx.x * 8 + warp; k < nh; k += W) {
     const int64_t row = __ldg(hub_rows + k);
     const int s0 = __ldg(hub_seg0 + k);
     const int len = __ldg(rowptr + row + 1) - __ldg(rowptr + row);
     const int ns = (len + hub_threshold - 1) / hub_threshold;
     if (ns <= 1) continue;
-    const int per = (ns + 7) >> 3;
-    const int q0 = grp * per, q1 = min(ns, q0 + per);
-    Row8 run;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) run.v[q] = 0.f;
-    {
-      // this group's run, 8 loads issued ahead of the (ordered) adds
-      const float* pp = partial + (int64_t)(s0 + q0) * kH + col;
-      int q = q0;
-      for (; q + 8 <= q1; q += 8, pp += 8 * kH) {
-        Row8 b[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) b[u] = ld_row8(pp + u * kH);
-        // one statement after the 8 loads that every first add depends on: keeps the loads together
-        asm volatile("" : "+f"(b[0].v[0]), "+f"(b[1].v[0]), "+f"(b[2].v[0]), "+f"(b[3].v[0]), "+f"(b[4].v[0]),
-                          "+f"(b[5].v[0]), "+f"(b[6].v[0]), "+f"(b[7].v[0]));
-#pragma unroll
-        for (int u = 0; u < 8; ++u) row8_add(run, b[u]);
-      }
-      for (; q < q1; ++q, pp += kH) {
-        const Row8 b = ld_row8(pp);
-        row8_add(run, b);
+    if (ns > kGiantSegs) {   // queue for the CTA-wide pass below (the slot order never reaches the results)
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&n_giant, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot < kGiantList) {
+        if (lane == 0) giant_k[slot] = (int)k;
+        continue;
       }
     }
+    const int per = (ns + 7) >> 3;
+    const Row8 run = hub_run_sum(partial, s0, grp * per, min(ns, grp * per + per), col);
     Row8 tot = run;   // group 0: its own run; then runs 1..7 in order
 #pragma unroll
     for (int g = 1; g < 8; ++g) {
@@ -292,6 +327,35 @@ __global__ void __launch_bounds__(256) k_hub_reduce(const int32_t* __restrict__ 
       *reinterpret_cast<float4*>(o) = make_float4(tot.v[0], tot.v[1], tot.v[2], tot.v[3]);
       *reinterpret_cast<float4*>(o + 4) = make_float4(tot.v[4], tot.v[5], tot.v[6], tot.v[7]);
     }
+  }
+  __syncthreads();
+  // giants: 64 lane groups of the CTA sum 64 contiguous runs concurrently, group 0 adds the 64 run sums in order
+  const int ng = min(n_giant, kGiantList);
+  for (int gi = 0; gi < ng; ++gi) {
+    const int64_t k = giant_k[gi];
+    const int64_t row = __ldg(hub_rows + k);
+    const int s0 = __ldg(hub_seg0 + k);
+    const int len = __ldg(rowptr + row + 1) - __ldg(rowptr + row);
+    const int ns = (len + hub_threshold - 1) / hub_threshold;
+    const int per = (ns + 63) >> 6, gid = warp * 8 + grp;
+    const Row8 run = hub_run_sum(partial, s0, gid * per, min(ns, gid * per + per), col);
+    *reinterpret_cast<float4*>(&red[gid][col]) = make_float4(run.v[0], run.v[1], run.v[2], run.v[3]);
+    *reinterpret_cast<float4*>(&red[gid][col + 4]) = make_float4(run.v[4], run.v[5], run.v[6], run.v[7]);
+    __syncthreads();   // also: every read of the hub's first slot (run 0) has completed
+    if (warp == 0 && grp == 0) {
+      Row8 tot = run;
+      for (int g = 1; g < 64 && g * per < ns; ++g) {
+        const float4 lo = *reinterpret_cast<const float4*>(&red[g][col]), hi = *reinterpret_cast<const float4*>(&red[g][col + 4]);
+        Row8 o;
+        o.v[0] = lo.x; o.v[1] = lo.y; o.v[2] = lo.z; o.v[3] = lo.w;
+        o.v[4] = hi.x; o.v[5] = hi.y; o.v[6] = hi.z; o.v[7] = hi.w;
+        row8_add(tot, o);
+      }
+      float* o = partial + (int64_t)s0 * kH + col;
+      *reinterpret_cast<float4*>(o) = make_float4(tot.v[0], tot.v[1], tot.v[2], tot.v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(tot.v[4], tot.v[5], tot.v[6], tot.v[7]);
+    }
+    __syncthreads();
   }
 }
 
@@ -1006,7 +1070,7 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
     const int rc = launch_hub_reduce(g, partial, stream);
     if (rc != MGCN_OK) return rc;
     int64_t hb = ceil_div(ceil_div(a.hub_cap, 16), kFwdWarps);
-    if (hb > (int64_t)kNumSMs) hb = kNumSMs;
+    if (hb > (int64_t)kNumSMs * 4) hb = (int64_t)kNumSMs * 4;   // one 16-row tile per warp at the botnet batch
     MGCN_LAUNCH(k_layer_fwd_hubs, (unsigned)hb, kFwdWarps * 32, smem, stream, a);
   }
   return MGCN_OK;

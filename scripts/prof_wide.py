@@ -36,3 +36,20 @@ for hi, ho in ((256, 256), (100, 256), (64, 64)):
     print(f"[{N} x {hi}] x [{hi} x {ho}]: tcgen05 3xTF32 {ms_tc:.3f} ms ({flop / ms_tc / 1e9:.0f} TFLOP/s fp32-equivalent, "
           f"{3 * flop / ms_tc / 1e9:.0f} TF32 TFLOP/s issued, {byts / ms_tc / 1e6:.0f} GB/s) | FMA kernel {ms_fma:.3f} ms | "
           f"torch addmm+relu (cuBLAS fp32) {ms_ref:.3f} ms")
+
+# weight gradient x^T g: tcgen05 (dispatch of mgcn_linear_wgrad_ex) at the C4 shapes
+for hi, ho in ((256, 256), (100, 256)):
+    x = torch.randn(N, hi, device=dev)
+    g = torch.randn(N, ho, device=dev)
+    for _ in range(2):
+        ops.linear_wgrad_impl(x, g, False, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.linear_wgrad_impl(x, g, False, True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"wgrad [{N} x {hi}]^T [{N} x {ho}]: {ms:.3f} ms ({2 * N * hi * ho / ms / 1e9:.0f} TFLOP/s fp32-equivalent, "
+          f"{4 * N * (hi + ho) / ms / 1e6:.0f} GB/s)")

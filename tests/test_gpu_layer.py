@@ -174,3 +174,22 @@ def test_first_layer_fwd_narrow_input(n, hin, act_out, with_next):
     zf = (post.view(-1, 1) * (s @ w_in)).numpy()
     sure = np.abs(z.numpy()) > 1e-5          # sign of z is unambiguous away from zero
     assert (got == (zf > 0))[sure].all()
+
+
+def test_giant_hub_rows_cta_wide_reduce():
+    """rows with more than 32 hub segments (k_hub_reduce's CTA-wide path) next to ordinary hubs: the hidden-32
+    aggregation equals the edge-order scatter_add within fp32 rounding and is run-to-run identical"""
+    n = 4000
+    g = np.random.default_rng(7)
+    src = g.integers(0, n, 30000)
+    dst = g.integers(0, n, 30000)
+    dst[:9000] = 11           # 141 segments at threshold 64
+    dst[9000:12500] = 12      # 55 segments
+    dst[12500:13000] = 13     # 8 segments: warp path
+    ei = torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+    x = torch.randn(n, H, generator=torch.Generator().manual_seed(3))
+    gs = GraphStructure(ei.to(DEV), n, hub_threshold=64)
+    outs = [ops.aggregate_prescaled_impl(gs.fwd, x.to(DEV), None, 0, None, None, 0).cpu() for _ in range(2)]
+    assert_bitexact(outs[0], outs[1], "run-to-run")
+    ref = torch.zeros(n, H, dtype=torch.float64).index_add_(0, ei[1], x.double()[ei[0]])
+    assert_parity(outs[0], ref, "aggregation with giant hubs")
