@@ -269,10 +269,11 @@ int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float* x, const 
                        int64_t H, float* gy_prev, float* gs_prev, float* dw, float* d_res_w,
                        float* d_res_b, void* workspace, size_t* workspace_bytes, void* stream);
 
-/* mgcn_gcn_layer_bwd on tcgen05.mma / tensor memory (one split of every operand into tf32 hi/lo images in
- * shared memory, K-major images for the row-local products, SWIZZLE_128B_BASE32B images for the transposed
- * ones).  Same results within rounding; currently slower than the mma.sync kernel (0.99 vs 0.83 ms per
- * layer at the botnet batch), kept as the base of the next round's producer/consumer version. */
+/* mgcn_gcn_layer_bwd on tcgen05.mma / tensor memory — the default of the hidden-32 stack.  Every operand is split
+ * once into tf32 hi/lo images in shared memory (K-major images for the row-local products, SWIZZLE_128B_BASE32B
+ * images for the transposed ones); a persistent CTA per SM runs producer / issuer / epilogue roles over two operand
+ * stages and two accumulator buffers (csrc/gcn_layer_tc.cu).  Same contract and the same results within rounding
+ * as mgcn_gcn_layer_bwd; 0.58 ms against 0.81 ms per layer at the botnet batch (profiles/r1b_layer_summary.md). */
 int mgcn_gcn_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* w,
                           const float* res_w, const uint32_t* hmask_prev, const float* post, int64_t N,
                           int64_t H, float* gy_prev, float* gs_prev, float* dw, float* d_res_w,
