@@ -1,0 +1,37 @@
+"""CUDA-graph replay of a training step's device work for batches of a FIXED shape.
+
+The botnet step is ~120 kernel launches for 23 ms of device time, so the host normally stays ahead — but any host
+jitter (a busy box, the Python GC) shows up as idle gaps, and a single graph (C1, 2.3 ms per step) is plainly
+launch-bound.  Every entry point of libmgcn.so is capture-safe by contract (no allocation, no synchronisation, no
+host reads: include/mgcn.h), so forward + loss + backward can be recorded once and replayed:
+
+    g = GraphedCall(lambda: fwd_loss_bwd(batch))     # zero grads, forward, loss, backward; returns the loss tensor
+    loss = g()                                       # replay; `loss` is the captured output tensor (overwritten per replay)
+
+Inputs are the tensors the closure reads (static addresses: copy new data INTO them); parameter gradients must
+already exist (they are accumulated in place).  Shapes, the edge structure and the set of launches are frozen at
+capture time — a batch of another shape needs its own GraphedCall.
+"""
+import torch
+
+
+class GraphedCall:
+    def __init__(self, fn, warmup=3):
+        self.fn = fn
+        self.graph = None
+        self.out = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # lazy initialisation (cudaFuncSetAttribute, structure cache, allocator)
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.out = fn()
+        self.graph = graph
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out

@@ -267,3 +267,43 @@ def test_device_loader_prefetch_matches_plain_copy():
         torch.cuda._sleep(2_000_000)          # keep the compute stream busy while the next copy runs
     assert k == 4 and len(ptrs) <= 2 + 3      # slots are reused when shapes repeat (here shapes differ per seed)
     assert list(DeviceLoader([], "cuda")) == []
+
+
+def test_graphed_call_replays_the_eager_step_bit_exactly():
+    """meta_gcn_b200.graphed.GraphedCall: forward + loss + backward of the botnet model recorded as one CUDA graph
+    gives the gradients of the eager step bit for bit (every libmgcn entry point is capture-safe and deterministic),
+    also after the inputs were overwritten in place"""
+    from meta_gcn_b200 import functional as F
+    from meta_gcn_b200.data import GraphBatch, synth_botnet_graph
+    from meta_gcn_b200.gcn_meta.models import GCNModel
+    from meta_gcn_b200.graphed import GraphedCall
+    torch.manual_seed(0)
+    cfg = dict(in_channels=1, enc_sizes=[32] * 4, num_classes=2, non_linear="relu", non_linear_layer_wise="relu",
+               residual_hop=1, dropout=0.0, final_type="proj", pred_on="node", nodemodel="additive", deg_norm="sm",
+               edge_gate=None, aggr="add", bias=False)
+    model = GCNModel(**cfg).to("cuda")
+    b = GraphBatch.from_data_list([synth_botnet_graph(seed=5, num_nodes=6000, edge_entries=50000, evil=400)]).to("cuda")
+    x0, deg, y = b.x[:, 0].contiguous().view(-1, 1), b.x[:, 1].contiguous(), b.y.long()
+    params = [p for p in model.parameters()]
+    for p in params:
+        p.grad = torch.zeros_like(p)
+
+    def fwd_loss_bwd():
+        for p in params:
+            p.grad.zero_()
+        loss = F.cross_entropy(model(x0, b.edge_index, deg_K=deg), y, "sum")
+        loss.backward()
+        return loss
+
+    loss_e = float(fwd_loss_bwd())
+    grads_e = [p.grad.clone() for p in params]
+    g = GraphedCall(fwd_loss_bwd)
+    assert float(g()) == loss_e
+    for p, ge in zip(params, grads_e):
+        assert torch.equal(p.grad, ge)
+    x0.mul_(2.0)                       # new data in the static input buffer
+    loss_g2 = float(g())
+    grads_g2 = [p.grad.clone() for p in params]
+    assert float(fwd_loss_bwd()) == loss_g2 and loss_g2 != loss_e
+    for p, gg in zip(params, grads_g2):
+        assert torch.equal(p.grad, gg)
