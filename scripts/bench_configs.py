@@ -75,6 +75,25 @@ if C1:
          graphs_per_s=1e3 / ms, gedges_per_s=b.num_edges * 24 / ms / 1e6, launches=launches,
          n=b.num_nodes, e=b.num_edges)
 
+    # the same step replayed as one CUDA graph (meta_gcn_b200/graphed.py): C1 is launch-bound
+    from meta_gcn_b200.graphed import GraphedCall  # noqa: E402
+    for p_ in model.parameters():
+        p_.grad = torch.zeros_like(p_)
+
+
+    def c1_fwd_loss_bwd():
+        for p_ in model.parameters():
+            p_.grad.zero_()
+        loss = F_mgcn.cross_entropy(model(x0, b.edge_index, deg_K=deg), y, "mean")
+        loss.backward()
+        return loss
+
+
+    graphed = GraphedCall(c1_fwd_loss_bwd)
+    ms_g = timeit(graphed, reps=20, warm=3)
+    emit(config="C1", what="the same step replayed as one CUDA graph", ms=ms_g, graphs_per_s=1e3 / ms_g,
+         gedges_per_s=b.num_edges * 24 / ms_g / 1e6, n=b.num_nodes, e=b.num_edges)
+
 # ---- C3: TU-shaped batches of 128 small graphs, 3 layers, hidden 64 ----
 if C3:
     tb = D.synth_tu_batch(seed=0, num_graphs=128).to(dev)
