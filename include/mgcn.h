@@ -310,6 +310,23 @@ int mgcn_cross_entropy_fwd(const float* logits, const int64_t* target, int64_t N
 int mgcn_cross_entropy_bwd(const float* logits, const int64_t* target, int64_t N, int64_t C, int mean,
                            const float* upstream, float* dlogits, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * 'max' aggregation: scatter_('max', src, index, dim_size) (common.py:54-64 — torch_scatter scatter_max with fill
+ * -1e38, untouched rows set to 0) and NodeModelAdditive(aggr='max') (gcn_base_models.py:223-237), with
+ * torch_scatter's gradient rule (the first entry that attains the maximum receives the gradient).
+ * out[i,c] = max over the row's entries, in row order, of edge_val[k] * x[idx_k, c] (idx = perm when gather_perm:
+ * primitive seam, else nbr: layer seam; edge_val in row order or NULL); arg[i,c] = edge id (perm) of the first
+ * maximal entry, -1 (and out = 0) for a row without entries.  Deterministic, no atomics. */
+int mgcn_segment_max(const mgcn_csr_t* g, const float* x, int64_t n_in, int64_t H, int gather_perm,
+                     const float* edge_val, float* out, int32_t* arg, void* stream);
+/* layer seam, gt = the structure grouped by the OTHER endpoint (by source):
+ * dx[j,c] = sum over row j's entries k of [arg[nbr_k, c] == perm_k] * edge_val[k] * grad[nbr_k, c] */
+int mgcn_segment_max_bwd(const mgcn_csr_t* gt, const float* grad, const int32_t* arg, const float* edge_val,
+                         int64_t H, float* dx, void* stream);
+/* primitive seam: dsrc [n_src,H] = 0, then dsrc[arg[i,c], c] = grad[i,c] */
+int mgcn_scatter_max_bwd(const int32_t* arg, const float* grad, int64_t N, int64_t H, int64_t n_src, float* dsrc,
+                         void* stream);
+
 /* Binary-classification counters of src/gcn_meta/optim/metrics.py:8-24 as used at train_botnet.py:296-305:
  * counts5 = {TP, FP, TN, FN, correct} (int64) with pred = argmax(logits[n,:]) (first maximal class; logits
  * float [N,C]) or the given pred int64[N] (exactly one of logits / pred is non-NULL); target int64[N].

@@ -27,5 +27,17 @@ def scatter_mean(src, index, dim=-1, out=None, dim_size=None, fill_value=0):
     return F_mgcn.scatter_rows(src, index, dim_size, "mean")
 
 
-def scatter_max(*args, **kwargs):
-    raise NotImplementedError("scatter_max belongs to the attention models (SURVEY.md §2.2 K6): out of scope")
+def scatter_max(src, index, dim=-1, out=None, dim_size=None, fill_value=None):
+    """torch_scatter 1.x scatter_max along dim 0 -> (out, argmax): rows without entries hold fill_value / -1
+    (common.py:56-57 passes -1e38 and zeroes those rows afterwards)"""
+    import torch
+    if src.dim() == 1 and dim == -1:
+        dim = 0
+    if dim != 0:
+        raise NotImplementedError("mgcn scatter ops aggregate along dim 0 only")
+    if out is not None:
+        raise NotImplementedError("scatter_max(out=...) is not used by the reference")
+    if fill_value is None:
+        fill_value = torch.finfo(src.dtype).min
+    res, arg = F_mgcn.scatter_rows_max(src, index, dim_size)
+    return torch.where(arg < 0, torch.full_like(res, fill_value), res), arg

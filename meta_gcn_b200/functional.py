@@ -57,6 +57,35 @@ def aggregate(x, graph, nbr_scale=None, row_scale=None, edge_weight=None, reduce
                             _REDUCE[reduce], _ACT[act])
 
 
+class _AggregateMax(torch.autograd.Function):
+    """out_i = max_e x[source(e)] * w_e over the edges into i (0 for a node without edges); gradient to the first
+    maximal edge (torch_scatter scatter_max), accumulated per source by a row-owned pass over the by-source
+    structure"""
+
+    @staticmethod
+    def forward(ctx, x, graph, ev_fwd, ev_bwd):
+        out, arg = ops.segment_max_impl(graph.fwd, x, False, ev_fwd)
+        ctx.graph = graph
+        ctx.save_for_backward(arg, ev_bwd)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, g, _garg):
+        arg, ev_bwd = ctx.saved_tensors
+        dx = ops.segment_max_bwd_impl(ctx.graph.bwd, g.contiguous(), arg, ev_bwd) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None
+
+
+def aggregate_max(x, graph, edge_weight=None, loop_value=1.0):
+    """NodeModelAdditive(aggr='max') (gcn_base_models.py:223-237): max over incoming edges of x[row] * norm_e;
+    edge_weight = the per-edge factor norm[E] in edge_index order (or None)"""
+    ev_fwd = ev_bwd = None
+    if edge_weight is not None:
+        ev_fwd, ev_bwd = graph.edge_values(edge_weight, loop_value)
+    return _AggregateMax.apply(x, graph, ev_fwd, ev_bwd)[0]
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, add, w_out_in, act):
@@ -132,6 +161,34 @@ class _ScatterRows(torch.autograd.Function):
         if ctx.reduce == 1:
             g = g / ctx.graph.in_degree().clamp(min=1).unsqueeze(1)
         return g.index_select(0, index), None, None, None
+
+
+class _ScatterRowsMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, graph):
+        out, arg = ops.segment_max_impl(graph.fwd, src, True, None)
+        ctx.n_src = src.size(0)
+        ctx.save_for_backward(arg)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, g, _garg):
+        (arg,) = ctx.saved_tensors
+        return ops.scatter_max_bwd_impl(arg, g.contiguous(), ctx.n_src), None
+
+
+def scatter_rows_max(src, index, dim_size=None):
+    """scatter_('max', src, index, dim_size) (common.py:54-64) -> (out, argmax); rows without entries are 0 / -1"""
+    squeeze = src.dim() == 1
+    src2 = src.unsqueeze(1) if squeeze else src.reshape(src.size(0), -1)
+    if dim_size is None:
+        dim_size = int(index.max().item()) + 1 if index.numel() else 0
+    graph = structure_of_index(index, dim_size)
+    out, arg = _ScatterRowsMax.apply(src2, graph)
+    if squeeze:
+        return out.squeeze(1), arg.squeeze(1).long()
+    return out.reshape(dim_size, *src.shape[1:]), arg.reshape(dim_size, *src.shape[1:]).long()
 
 
 def scatter_rows(src, index, dim_size=None, reduce="add"):

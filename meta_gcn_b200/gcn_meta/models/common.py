@@ -1,5 +1,6 @@
 """Mirror of src/gcn_meta/models/common.py for the hot path: the ``scatter_`` primitive seam
 (common.py:37-66) and the activation factory (common.py:27-34), backed by libmgcn kernels."""
+import torch
 import torch.nn as nn
 
 from ... import functional as F_mgcn
@@ -26,16 +27,18 @@ def activation(act, negative_slope=0.2):
 
 
 def scatter_(name, src, index, dim_size=None, out=None):
-    """Row-wise aggregation of ``src`` by ``index`` along dim 0 ('add' | 'mean').
+    """Row-wise aggregation of ``src`` by ``index`` along dim 0 ('add' | 'mean' | 'max').
 
     Same call shape as the reference (common.py:37); computed by the row-owned gather-sum kernel
     over a stable sort of ``index`` — deterministic, and for rows below the hub threshold the same
-    fp32 summation order as the reference's CPU scatter_add.  'max' belongs to the attention models
-    and is outside this hot path."""
+    fp32 summation order as the reference's CPU scatter_add.  'max' (common.py:57,63-64: fill -1e38, untouched
+    rows set to 0) is a row-owned first-maximum pass with torch_scatter's gradient rule."""
+    assert name in ["add", "mean", "max"]
     if name == "max":
-        raise NotImplementedError("scatter_('max') (attention / hard-attention models) is out of scope")
-    if name not in ("add", "mean"):
-        raise AssertionError(name)
+        res = F_mgcn.scatter_rows_max(src, index, dim_size)[0]
+        if out is not None:
+            res = torch.maximum(out, res)
+        return res
     res = F_mgcn.scatter_rows(src, index, dim_size, name)
     if out is not None:
         res = out + res if name == "add" else res

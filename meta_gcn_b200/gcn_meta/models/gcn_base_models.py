@@ -27,8 +27,6 @@ class NodeModelBase(nn.Module):
         super().__init__()
         if edge_gate is not None:
             raise NotImplementedError("edge gates are outside the B200 hot path (SURVEY.md §2.1 #1)")
-        if aggr == "max":
-            raise NotImplementedError("aggr='max' is outside the B200 hot path (SURVEY.md §2.2 K6)")
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.in_edgedim = in_edgedim
@@ -112,6 +110,24 @@ class NodeModelAdditive(NodeModelBase):
                 dis = self.degree_factors(edge_index, n, deg, edge_weight, self.deg_norm)
             nbr_scale = dis
             row_scale = dis if self.deg_norm == "sm" else None
+        if self.aggr == "max":
+            # gcn_base_models.py:209-237 with scatter_('max'): max over the incoming edges of (x W)[row] * norm_e,
+            # norm_e formed exactly as degnorm_const does (one factor per edge, same roundings)
+            if edge_attr is not None:
+                raise NotImplementedError("aggr='max' with edge attributes is not built (the max is taken over the "
+                                          "SUM of node and edge messages: not separable)")
+            norm_e = None
+            if self.deg_norm is not None:
+                dis = nbr_scale
+                row, col = edge_index
+                if self.deg_norm == "sm":
+                    norm_e = dis[row] * dis[col] if edge_weight is None else dis[row] * edge_weight.view(-1) * dis[col]
+                else:
+                    norm_e = dis[row] if edge_weight is None else dis[row] * edge_weight.view(-1)
+            out = F_mgcn.aggregate_max(xw, graph, norm_e)
+            if self.bias is not None:
+                out = out + self.bias
+            return torch.relu(out) if act == "relu" else out
         ew = edge_weight.view(-1) if (edge_weight is not None and self.deg_norm is not None) else None
         if edge_attr is None:
             return F_mgcn.aggregate(xw, graph, nbr_scale, row_scale, ew, self.aggr, self.bias, None, act)

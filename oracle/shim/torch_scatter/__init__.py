@@ -37,19 +37,40 @@ def scatter_mean(src, index, dim=-1, out=None, dim_size=None, fill_value=0):
     return out / count.clamp(min=1)
 
 
+class _ScatterMax(torch.autograd.Function):
+    """torch_scatter 1.x ScatterMax: forward (out, arg) by a custom kernel, backward
+    grad_src = 0; grad_src[arg[valid]] = grad_out[valid]  (the first maximal entry receives the gradient).
+    `out` is not saved, so the caller may modify it in place (common.py:63-64 does)."""
+
+    @staticmethod
+    def forward(ctx, out, src, index, dim):
+        out = out.scatter_reduce(dim, index, src, reduce="amax", include_self=True)
+        # argmax: first position attaining the max, -1 for untouched rows (torch_scatter 1.x)
+        hit = src == out.gather(dim, index)
+        pos_shape = [1] * src.dim()
+        pos_shape[dim] = src.size(dim)
+        pos = torch.arange(src.size(dim), device=src.device).view(pos_shape).expand_as(src)
+        big = src.size(dim)
+        cand = torch.where(hit, pos, torch.full_like(pos, big))
+        first = index.new_full(out.size(), big).scatter_reduce(dim, index, cand, reduce="amin", include_self=True)
+        arg = torch.where(first < big, first, index.new_full(out.size(), -1))
+        ctx.mark_non_differentiable(arg)
+        ctx.dim, ctx.src_size = dim, src.size()
+        ctx.save_for_backward(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        (arg,) = ctx.saved_tensors
+        valid = arg >= 0
+        grad_src = grad_out.new_zeros(ctx.src_size)
+        grad_src.scatter_(ctx.dim, torch.where(valid, arg, torch.zeros_like(arg)),
+                          torch.where(valid, grad_out, torch.zeros_like(grad_out)), reduce="add")
+        return None, grad_src, None, None
+
+
 def scatter_max(src, index, dim=-1, out=None, dim_size=None, fill_value=None):
     if fill_value is None:
         fill_value = torch.finfo(src.dtype).min if src.is_floating_point() else torch.iinfo(src.dtype).min
     src, out, index, dim = _gen(src, index, dim, out, dim_size, fill_value)
-    out = out.scatter_reduce(dim, index, src, reduce="amax", include_self=True)
-    # argmax: first position attaining the max, -1 for untouched rows (torch_scatter 1.x)
-    arg = index.new_full(out.size(), -1)
-    hit = src == out.gather(dim, index)
-    pos_shape = [1] * src.dim()
-    pos_shape[dim] = src.size(dim)
-    pos = torch.arange(src.size(dim), device=src.device).view(pos_shape).expand_as(src)
-    big = src.size(dim)
-    cand = torch.where(hit, pos, torch.full_like(pos, big))
-    first = index.new_full(out.size(), big).scatter_reduce(dim, index, cand, reduce="amin", include_self=True)
-    arg = torch.where(first < big, first, arg)
-    return out, arg
+    return _ScatterMax.apply(out, src, index, dim)

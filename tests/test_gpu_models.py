@@ -28,6 +28,8 @@ CASES = {
     "gcn_meta_edgeweight": (dict(V, in_channels=5), {"edge_weight": True}),
     "gcn_meta_nodeg": (dict(V, in_channels=5), {"use_deg": False}),
     "gcn_meta_graphpred": (dict(V, in_channels=5, pred_on="graph"), {"graph": True}),
+    "gcn_meta_max": (dict(V, aggr="max"), {}),
+    "gcn_meta_max_ew_rw": (dict(V, in_channels=5, deg_norm="rw", aggr="max"), {"edge_weight": True}),
 }
 
 
@@ -100,6 +102,25 @@ def test_primitive_seam_matches_reference_golden():
     dis = ops.gcn_norm_impl(gs.out_degree(), 0).cpu()
     li = torch.from_numpy(g["legacy_edge_index"])
     assert_bitexact(dis[li[0]] * dis[li[1]], g["legacy_norm"], "legacy GCN.norm")
+
+
+def test_scatter_max_primitive_matches_reference_golden():
+    """scatter_('max', src, index, dim_size) (common.py:37-66) and its autograd against the unmodified reference:
+    values bit-exact, gradient to the first maximal entry (ties and empty rows included), also through the
+    torch_scatter-shaped compat call"""
+    from meta_gcn_b200.compat.torch_scatter import scatter_max
+    from meta_gcn_b200.gcn_meta.models import scatter_
+    g = golden("primitive_max")
+    n = int(g["num_nodes"])
+    index = torch.from_numpy(g["index"]).to(DEV)
+    src = torch.from_numpy(g["src"]).to(DEV).requires_grad_(True)
+    out = scatter_("max", src, index, dim_size=n)
+    assert_bitexact(out, g["out"], "scatter_max")
+    (out * torch.from_numpy(g["wout"]).to(DEV)).sum().backward()
+    assert_bitexact(src.grad, g["grad_src"], "grad_src")
+    o2, arg = scatter_max(src.detach(), index, 0, None, n, -1e38)
+    assert (arg[-7:] == -1).all() and (o2[-7:] == -1e38).all()
+    assert_bitexact(torch.where(arg < 0, torch.zeros_like(o2), o2), g["out"], "compat scatter_max")
 
 
 KNETS = {"kernel_gcn": ("GCN", "gcn", None), "kernel_gcn_jk": ("GCNWithJK", "gcn", "cat"),

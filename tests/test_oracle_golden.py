@@ -19,6 +19,8 @@ CASES = {
     "gcn_meta_edgeweight": (dict(V, in_channels=5), {"edge_weight": True}),
     "gcn_meta_nodeg": (dict(V, in_channels=5), {"use_deg": False}),
     "gcn_meta_graphpred": (dict(V, in_channels=5, pred_on="graph"), {"graph": True}),
+    "gcn_meta_max": (dict(V, aggr="max"), {}),
+    "gcn_meta_max_ew_rw": (dict(V, in_channels=5, deg_norm="rw", aggr="max"), {"edge_weight": True}),
 }
 
 
@@ -195,3 +197,18 @@ def test_binary_metrics_restatement_matches_reference_golden():
         got = port.binary_metrics(pred, y)
         np.testing.assert_array_equal(np.isnan(got), np.isnan(g[f"vals{k}"]))
         np.testing.assert_allclose(got, g[f"vals{k}"], rtol=0, atol=0, equal_nan=True)
+
+
+def test_oracle_scatter_max_matches_reference_golden():
+    """scatter_('max') of common.py:37-66 over the shim's torch_scatter-1.x scatter_max: forward through
+    port.scatter_rows, argmax / gradient rule (first maximal entry) through port.segment_max_first"""
+    g = golden("primitive_max")
+    src, index, n = torch.from_numpy(g["src"]), torch.from_numpy(g["index"]), int(g["num_nodes"])
+    assert_bitexact(port.scatter_rows("max", src, index, n), g["out"], "scatter_max out")
+    out, arg = port.segment_max_first(src, index, n)
+    out = np.where(arg < 0, 0.0, out).astype(np.float32)
+    assert_bitexact(out, g["out"], "first-argmax out")
+    grad = np.zeros_like(g["src"])
+    rows, cols = np.nonzero(arg >= 0)
+    grad[arg[rows, cols], cols] = g["wout"][rows, cols]
+    assert_bitexact(grad, g["grad_src"], "gradient to the first maximal entry")
