@@ -327,6 +327,12 @@ int mgcn_segment_max_bwd(const mgcn_csr_t* gt, const float* grad, const int32_t*
 int mgcn_scatter_max_bwd(const int32_t* arg, const float* grad, int64_t N, int64_t H, int64_t n_src, float* dsrc,
                          void* stream);
 
+/* out[e] = scale_src[row_e] * scale_tgt[col_e] * sum_c a[col_e,c] * b[row_e,c]   (row = edge_index[0], col =
+ * edge_index[1]; scales may be NULL): the gradient of an aggregation w.r.t. a per-edge weight, used by the edge gates
+ * (gcn_base_models.py:230-232, 322-369: x_j = sigmoid(...)_e * x_j before scatter_).  Deterministic. */
+int mgcn_edge_dot(const int64_t* edge_index, int64_t E, const float* a, const float* b, int64_t H,
+                  const float* scale_src, const float* scale_tgt, float* out, void* stream);
+
 /* Binary-classification counters of src/gcn_meta/optim/metrics.py:8-24 as used at train_botnet.py:296-305:
  * counts5 = {TP, FP, TN, FN, correct} (int64) with pred = argmax(logits[n,:]) (first maximal class; logits
  * float [N,C]) or the given pred int64[N] (exactly one of logits / pred is non-NULL); target int64[N].

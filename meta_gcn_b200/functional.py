@@ -15,17 +15,21 @@ _REDUCE = {"add": 0, "sum": 0, "mean": 1}
 
 class _Aggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd, reduce, act):
+    def forward(ctx, x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd, reduce, act, edge_weight=None):
+        # edge_weight (edge_index order) is passed only when its gradient is wanted (edge gates); ev_fwd / ev_bwd are
+        # its row-order copies for the two structures
         out = ops.spmm_impl(graph.fwd, x, False, ev_fwd, nbr_scale, row_scale, reduce, bias,
                             residual, act)
         ctx.graph = graph
         ctx.cfg = (reduce, act, bias is not None, residual is not None)
-        ctx.save_for_backward(out if act else None, nbr_scale, row_scale, ev_bwd)
+        want_dw = edge_weight is not None and edge_weight.requires_grad
+        ctx.want_dw = want_dw
+        ctx.save_for_backward(out if act else None, nbr_scale, row_scale, ev_bwd, x if want_dw else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        out, nbr_scale, row_scale, ev_bwd = ctx.saved_tensors
+        out, nbr_scale, row_scale, ev_bwd, x = ctx.saved_tensors
         reduce, act, has_bias, has_res = ctx.cfg
         graph = ctx.graph
         g = g.contiguous()
@@ -33,28 +37,33 @@ class _Aggregate(torch.autograd.Function):
             g = ops.relu_backward_impl(g, out)
         d_bias = g.sum(0) if (has_bias and ctx.needs_input_grad[1]) else None
         d_res = g if (has_res and ctx.needs_input_grad[2]) else None
-        dx = None
+        dx = d_ew = None
+        gg = g
+        if reduce == 1 and (ctx.needs_input_grad[0] or ctx.want_dw):
+            gg = g / graph.in_degree().clamp(min=1).unsqueeze(1)
         if ctx.needs_input_grad[0]:
-            gg = g
-            if reduce == 1:
-                gg = g / graph.in_degree().clamp(min=1).unsqueeze(1)
             # transpose: rows = sources; the per-target factor is now gathered, the per-source
             # factor scales the row
             dx = ops.spmm_impl(graph.bwd if ev_bwd is not None else graph.bwd_plain, gg, False, ev_bwd, row_scale, nbr_scale, 0, None,
                                None, 0)
-        return dx, d_bias, d_res, None, None, None, None, None, None, None
+        if ctx.want_dw:
+            # d w_e = nbr_scale[row_e] * row_scale[col_e] * <g[col_e], x[row_e]>
+            d_ew = ops.edge_dot_impl(graph.edge_index, gg, x, nbr_scale, row_scale)
+        return dx, d_bias, d_res, None, None, None, None, None, None, None, d_ew
 
 
 def aggregate(x, graph, nbr_scale=None, row_scale=None, edge_weight=None, reduce="add", bias=None,
               residual=None, act=None, loop_value=1.0):
     """out_i = act( reduce_{e: target(e)=i}  x[source(e)] * w_e  + bias + residual_i ),
     w_e = nbr_scale[source] * edge_weight[e] * row_scale[target]   (gcn_base_models.py:138-139,
-    223-240).  ``graph`` is a GraphStructure; edge_weight is in edge_index order."""
+    223-240).  ``graph`` is a GraphStructure; edge_weight is in edge_index order and may require grad (edge
+    gates, gcn_base_models.py:230-232)."""
     ev_fwd = ev_bwd = None
     if edge_weight is not None:
-        ev_fwd, ev_bwd = graph.edge_values(edge_weight, loop_value)
+        ev_fwd, ev_bwd = graph.edge_values(edge_weight.detach(), loop_value)
     return _Aggregate.apply(x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd,
-                            _REDUCE[reduce], _ACT[act])
+                            _REDUCE[reduce], _ACT[act],
+                            edge_weight if (edge_weight is not None and edge_weight.requires_grad) else None)
 
 
 class _AggregateMax(torch.autograd.Function):

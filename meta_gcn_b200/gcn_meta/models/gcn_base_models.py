@@ -5,7 +5,8 @@ Same constructor arguments and parameter names (``weight_node``, ``weight_edge``
 reference, so pickled reference models load.  The forward never materialises [E,H]: X·W runs in the
 narrow FMA transform, and gather * norm -> scatter_add is one row-owned aggregation whose per-edge
 weight dis[row]*edge_weight*dis[col] is formed in the reference's rounding order inside the kernel.
-Edge gates (EdgeGateProj / EdgeGateFree) and NodeModelMLP are outside the hot path."""
+Edge gates (EdgeGateProj / EdgeGateFree, gcn_base_models.py:322-397) multiply that per-edge weight and receive their
+gradient through a per-edge dot product (mgcn_edge_dot).  NodeModelMLP is outside the hot path."""
 import torch
 import torch.nn as nn
 from torch.nn import Parameter
@@ -25,14 +26,20 @@ class NodeModelBase(nn.Module):
         assert edge_gate in [None, "proj", "free"]
         assert aggr in ["add", "mean", "max"]
         super().__init__()
-        if edge_gate is not None:
-            raise NotImplementedError("edge gates are outside the B200 hot path (SURVEY.md §2.1 #1)")
         self.in_channels = in_channels
         self.out_channels = out_channels
         self.in_edgedim = in_edgedim
         self.deg_norm = deg_norm
         self.aggr = aggr
-        self.register_parameter("edge_gate", None)
+        if edge_gate is not None and aggr == "max":
+            raise NotImplementedError("edge gates together with aggr='max' are not built")
+        if edge_gate == "proj":                                           # gcn_base_models.py:57-63
+            self.edge_gate = EdgeGateProj(out_channels, in_edgedim=in_edgedim, bias=True)
+        elif edge_gate == "free":
+            assert "num_edges" in kwargs
+            self.edge_gate = EdgeGateFree(kwargs["num_edges"])
+        else:
+            self.register_parameter("edge_gate", None)
 
     @staticmethod
     def degree_factors(edge_index, num_nodes, deg=None, edge_weight=None, method="sm"):
@@ -110,6 +117,11 @@ class NodeModelAdditive(NodeModelBase):
                 dis = self.degree_factors(edge_index, n, deg, edge_weight, self.deg_norm)
             nbr_scale = dis
             row_scale = dis if self.deg_norm == "sm" else None
+        eg = None
+        if self.edge_gate is not None:                                    # gcn_base_models.py:230-232
+            if self.aggr == "max":
+                raise NotImplementedError("edge gates together with aggr='max' are not built")
+            eg = self.edge_gate(xw, edge_index, edge_attr=edge_attr, edge_weight=edge_weight).view(-1)
         if self.aggr == "max":
             # gcn_base_models.py:209-237 with scatter_('max'): max over the incoming edges of (x W)[row] * norm_e,
             # norm_e formed exactly as degnorm_const does (one factor per edge, same roundings)
@@ -129,13 +141,71 @@ class NodeModelAdditive(NodeModelBase):
                 out = out + self.bias
             return torch.relu(out) if act == "relu" else out
         ew = edge_weight.view(-1) if (edge_weight is not None and self.deg_norm is not None) else None
+        if eg is not None:
+            ew = eg if ew is None else ew * eg                            # gate_e * norm_e: one weight per edge
         if edge_attr is None:
             return F_mgcn.aggregate(xw, graph, nbr_scale, row_scale, ew, self.aggr, self.bias, None, act)
         # per-edge feature messages (gcn_base_models.py:204-206,227): summed by the primitive seam
         assert self.in_edgedim is not None
         x_je = F_mgcn.linear(edge_attr, self.weight_edge)
+        if eg is not None:
+            x_je = x_je * eg.view(-1, 1)
         out = F_mgcn.aggregate(xw, graph, nbr_scale, row_scale, ew, self.aggr)
         out = out + F_mgcn.scatter_rows(x_je, edge_index[1], n, self.aggr)
         if self.bias is not None:
             out = out + self.bias
         return torch.relu(out) if act == "relu" else out
+
+
+class EdgeGateProj(nn.Module):
+    """gcn_base_models.py:322-369: gate_e = sigmoid(linsrc(x)[row_e] + lintgt(x)[col_e] (+ linedge(edge_attr)_e) + bias);
+    the two node projections are [N,1] transforms on libmgcn, the per-edge part is elementwise on [E,1]"""
+
+    def __init__(self, in_channels, in_edgedim=None, bias=False):
+        super().__init__()
+        self.in_channels = in_channels
+        self.in_edgedim = in_edgedim
+        self.linsrc = nn.Linear(in_channels, 1, bias=False)
+        self.lintgt = nn.Linear(in_channels, 1, bias=False)
+        if in_edgedim is not None:
+            self.linedge = nn.Linear(in_edgedim, 1, bias=False)
+        if bias:
+            self.bias = Parameter(torch.Tensor(1))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self, initrange=0.1):
+        nn.init.uniform_(self.linsrc.weight, -initrange, initrange)
+        nn.init.uniform_(self.lintgt.weight, -initrange, initrange)
+        if self.in_edgedim is not None:
+            nn.init.uniform_(self.linedge.weight, -initrange, initrange)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+
+    def forward(self, x, edge_index, edge_attr=None, edge_weight=None):
+        a_src = F_mgcn.linear(x, self.linsrc.weight, weight_layout="out_in")      # [N,1]
+        a_tgt = F_mgcn.linear(x, self.lintgt.weight, weight_layout="out_in")
+        gate = a_src.index_select(0, edge_index[0]) + a_tgt.index_select(0, edge_index[1])
+        if edge_attr is not None:
+            assert self.linedge is not None
+            gate = gate + F_mgcn.linear(edge_attr, self.linedge.weight, weight_layout="out_in")
+        if self.bias is not None:
+            gate = gate + self.bias.view(-1, 1)
+        return torch.sigmoid(gate)
+
+
+class EdgeGateFree(nn.Module):
+    """gcn_base_models.py:372-397: one free gate parameter per edge (fixed edge count)"""
+
+    def __init__(self, num_edges):
+        super().__init__()
+        self.num_edges = num_edges
+        self.edge_gates = Parameter(torch.Tensor(num_edges, 1))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.constant_(self.edge_gates, 1)
+
+    def forward(self, *args, **kwargs):
+        return torch.sigmoid(self.edge_gates)

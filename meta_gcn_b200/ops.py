@@ -255,6 +255,21 @@ def spmm_impl(csr, x, gather_perm=False, edge_val=None, nbr_scale=None, row_scal
     return out
 
 
+def edge_dot_impl(edge_index, a, b, scale_src=None, scale_tgt=None):
+    """out[e] = scale_src[row_e] * scale_tgt[col_e] * <a[col_e], b[row_e]>   (mgcn_edge_dot)"""
+    _need_cuda(edge_index, a, b, scale_src, scale_tgt)
+    a = _f32c(a, "a")
+    b = _f32c(b, "b")
+    scale_src = _f32c(scale_src, "scale_src")
+    scale_tgt = _f32c(scale_tgt, "scale_tgt")
+    ei = edge_index.contiguous()
+    E = ei.size(1)
+    out = torch.empty(E, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().mgcn_edge_dot(_ptr(ei), E, _ptr(a), _ptr(b), a.size(1), _ptr(scale_src), _ptr(scale_tgt),
+                                         _ptr(out), _stream()))
+    return out
+
+
 def segment_max_impl(csr, x, gather_perm=False, edge_val=None):
     """(out [n_rows,H], arg int32 [n_rows,H]) of mgcn_segment_max"""
     _need_cuda(csr.rowptr, x, edge_val)

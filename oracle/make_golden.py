@@ -232,6 +232,14 @@ def main():
         case_gcn_meta("gcn_meta_max_ew_rw", 8, 150, 500, dict(v_, in_channels=5, deg_norm="rw"), edge_weight=True)
         case_primitive_max()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "gate":  # edge-gate cases (added later)
+        v_ = dict(in_channels=1, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",
+                  non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj", pred_on="node",
+                  nodemodel="additive", deg_norm="sm", edge_gate="proj", aggr="add", bias=True)
+        case_gcn_meta("gcn_meta_gate_proj", 9, 150, 500, v_)
+        case_gcn_meta("gcn_meta_gate_proj_mean_ew", 10, 150, 500, dict(v_, in_channels=5, aggr="mean", deg_norm="rw"),
+                      edge_weight=True)
+        return
     botnet = dict(in_channels=1, enc_sizes=[32] * 12, num_classes=2, non_linear="relu",
                   non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj",
                   pred_on="node", nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="add",

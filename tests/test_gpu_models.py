@@ -30,6 +30,10 @@ CASES = {
     "gcn_meta_graphpred": (dict(V, in_channels=5, pred_on="graph"), {"graph": True}),
     "gcn_meta_max": (dict(V, aggr="max"), {}),
     "gcn_meta_max_ew_rw": (dict(V, in_channels=5, deg_norm="rw", aggr="max"), {"edge_weight": True}),
+    # edge gates (EdgeGateProj, gcn_base_models.py:322-369): goldens straight from the unmodified reference
+    "gcn_meta_gate_proj": (dict(V, edge_gate="proj"), {}),
+    "gcn_meta_gate_proj_mean_ew": (dict(V, in_channels=5, aggr="mean", deg_norm="rw", edge_gate="proj"),
+                                   {"edge_weight": True}),
 }
 
 

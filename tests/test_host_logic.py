@@ -85,9 +85,10 @@ def test_unsupported_reference_options_fail_loudly():
     from meta_gcn_b200.gcn_meta.models import GCNModel, scatter_
     with pytest.raises(NotImplementedError):
         GCNModel(1, [8], 2, nodemodel="attention")
+    assert GCNModel(1, [8], 2, edge_gate="proj") is not None    # edge gates and 'max' are built (csrc/segmax.cu)
+    assert GCNModel(1, [8], 2, aggr="max") is not None
     with pytest.raises(NotImplementedError):
-        GCNModel(1, [8], 2, edge_gate="proj")
-    assert GCNModel(1, [8], 2, aggr="max") is not None          # 'max' is built (csrc/segmax.cu)
+        GCNModel(1, [8], 2, aggr="max", edge_gate="proj")
     with pytest.raises(RuntimeError):                           # ... and, like every op, refuses CPU tensors
         scatter_("max", torch.ones(3, 2), torch.zeros(3, dtype=torch.long))
 
