@@ -43,3 +43,15 @@ def scatter_(name, src, index, dim_size=None, out=None):
     if out is not None:
         res = out + res if name == "add" else res
     return res
+
+
+def softmax(src, index, num_nodes=None):
+    """Sparsely evaluated softmax over the groups of ``index`` (common.py:69-92): segment max for stability
+    (fill -1e16 as in the reference), exp, segment sum + 1e-16 — on the libmgcn scatter kernels"""
+    from ...compat.torch_scatter import scatter_add, scatter_max
+    if num_nodes is None:
+        num_nodes = int(index.max().item()) + 1
+    out = src - scatter_max(src, index, dim=0, dim_size=num_nodes, fill_value=-1e16)[0][index]
+    out = out.exp()
+    out = out / (scatter_add(out, index, dim=0, dim_size=num_nodes)[index] + 1e-16)
+    return out

@@ -120,7 +120,7 @@ class GCNModel(nn.Module):
         if any(len(m) != 1 or layer.gcn.kernel_combine != "add" for m, layer in zip(nms, self.gcn_net)):
             return False
         first = nms[0][0]
-        return all(m[0].aggr == "add" and m[0].edge_gate is None and m[0].deg_norm == first.deg_norm and m[0].in_edgedim is None
+        return all(type(m[0]).__name__ == "NodeModelAdditive" and m[0].aggr == "add" and m[0].edge_gate is None and m[0].deg_norm == first.deg_norm and m[0].in_edgedim is None
                    and (m[0].bias is None) == (first.bias is None) for m in nms)
 
     def _forward_stack(self, x, edge_index, dis):

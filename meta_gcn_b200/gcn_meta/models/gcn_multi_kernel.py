@@ -1,18 +1,19 @@
 """Mirror of src/gcn_meta/models/gcn_multi_kernel.py: K node models over K edge sets, combined by
-add / cat / mean (gcn_multi_kernel.py:76-114).  Only the additive node model is on the hot path."""
+add / cat / mean (gcn_multi_kernel.py:76-114): the additive node model (the hot path) and the soft-attention one."""
 import torch
 import torch.nn as nn
 
 from .gcn_base_models import NodeModelAdditive
+from .graph_attention import NodeModelAttention
 
 
 class GCNMultiKernel(nn.Module):
-    nodemodel_dict = {"additive": NodeModelAdditive}
+    nodemodel_dict = {"additive": NodeModelAdditive, "attention": NodeModelAttention}
 
     def __init__(self, *args, num_kernel=1, nodemodel="additive", kernel_combine="add", **kwargs):
         assert kernel_combine in ["add", "cat", "mean"]
         if nodemodel not in self.nodemodel_dict:
-            raise NotImplementedError(f"nodemodel={nodemodel!r} (attention models) is outside the hot path")
+            raise NotImplementedError(f"nodemodel={nodemodel!r} (MLP / hard-attention node models) is outside the hot path")
         super().__init__()
         self.kernel_combine = kernel_combine
         self.node_models = nn.ModuleList(

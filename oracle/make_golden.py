@@ -232,6 +232,15 @@ def main():
         case_gcn_meta("gcn_meta_max_ew_rw", 8, 150, 500, dict(v_, in_channels=5, deg_norm="rw"), edge_weight=True)
         case_primitive_max()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "attention":   # soft-attention node model (added later)
+        v_ = dict(in_channels=5, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",
+                  non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj", pred_on="node",
+                  nodemodel="attention", nheads=2, att_act="lrelu", att_dropout=0, att_combine="cat", att_dir="in",
+                  bias=True)
+        case_gcn_meta("gcn_meta_attention", 11, 150, 500, v_, use_deg=False)
+        case_gcn_meta("gcn_meta_attention_out_mean", 12, 150, 500,
+                      dict(v_, nheads=[2, 4, 1], att_combine="mean", att_dir="out", att_act="relu"), use_deg=False)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "gate":  # edge-gate cases (added later)
         v_ = dict(in_channels=1, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",
                   non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj", pred_on="node",

@@ -31,6 +31,11 @@ CASES = {
     "gcn_meta_max": (dict(V, aggr="max"), {}),
     "gcn_meta_max_ew_rw": (dict(V, in_channels=5, deg_norm="rw", aggr="max"), {"edge_weight": True}),
     # edge gates (EdgeGateProj, gcn_base_models.py:322-369): goldens straight from the unmodified reference
+    # soft attention (NodeModelAttention, graph_attention.py:11-117)
+    "gcn_meta_attention": (dict(V, in_channels=5, nodemodel="attention", nheads=2, att_act="lrelu", att_dropout=0,
+                                att_combine="cat", att_dir="in"), {"use_deg": False}),
+    "gcn_meta_attention_out_mean": (dict(V, in_channels=5, nodemodel="attention", nheads=[2, 4, 1], att_act="relu",
+                                         att_dropout=0, att_combine="mean", att_dir="out"), {"use_deg": False}),
     "gcn_meta_gate_proj": (dict(V, edge_gate="proj"), {}),
     "gcn_meta_gate_proj_mean_ew": (dict(V, in_channels=5, aggr="mean", deg_norm="rw", edge_gate="proj"),
                                    {"edge_weight": True}),

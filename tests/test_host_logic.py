@@ -84,7 +84,8 @@ def test_kernel_mirrors_have_reference_parameter_layout(name, cls, kw):
 def test_unsupported_reference_options_fail_loudly():
     from meta_gcn_b200.gcn_meta.models import GCNModel, scatter_
     with pytest.raises(NotImplementedError):
-        GCNModel(1, [8], 2, nodemodel="attention")
+        GCNModel(1, [8], 2, nodemodel="hardattention")
+    assert GCNModel(1, [8], 2, nodemodel="attention", nheads=2) is not None
     assert GCNModel(1, [8], 2, edge_gate="proj") is not None    # edge gates and 'max' are built (csrc/segmax.cu)
     assert GCNModel(1, [8], 2, aggr="max") is not None
     with pytest.raises(NotImplementedError):
