@@ -116,6 +116,9 @@ struct LayerFwdArgs {
 #ifndef MGCN_AGG_MINB
 #define MGCN_AGG_MINB 3
 #endif
+#ifndef MGCN_AGG_WARPS
+#define MGCN_AGG_WARPS 8   // warps per CTA of the plain aggregation
+#endif
 
 struct Row8 {
   float v[8];
@@ -696,7 +699,7 @@ __device__ __forceinline__ void agg_finish_row(const AggFlatArgs& a, Row8 acc, f
   st_f4_hint(o + 4, make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]), pol);
 }
 
-__global__ void __launch_bounds__(256, MGCN_AGG_MINB) k_agg_flat(const AggFlatArgs a) {
+__global__ void __launch_bounds__(MGCN_AGG_WARPS * 32, MGCN_AGG_MINB) k_agg_flat(const AggFlatArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   const int sub = lane & 3, grp = lane >> 2, grp_lane0 = grp * 4;
@@ -709,9 +712,9 @@ __global__ void __launch_bounds__(256, MGCN_AGG_MINB) k_agg_flat(const AggFlatAr
   }
   const int64_t limit = a.n_rows + nseg;
   const int64_t n_tiles = (limit + 15) >> 4;
-  const int64_t stride = (int64_t)gridDim.x * 8;
+  const int64_t stride = (int64_t)gridDim.x * MGCN_AGG_WARPS;
   const uint64_t pol = policy_evict_first();
-  int64_t tile = (int64_t)blockIdx.x * 8 + warp;
+  int64_t tile = (int64_t)blockIdx.x * MGCN_AGG_WARPS + warp;
   int4 dn = make_int4(-1, 0, 0, 0);
   if (tile < n_tiles) dn = load_tile_desc(a.tasks, tile * 16, limit, lane, pol);
   for (; tile < n_tiles; tile += stride) {
@@ -781,9 +784,9 @@ int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, in
   a.act = act;
   a.hub_threshold = g->hub_threshold;
   const int64_t max_tiles = ceil_div(g->n_rows + a.seg_cap, 16);
-  int64_t blocks = ceil_div(max_tiles, 8);
+  int64_t blocks = ceil_div(max_tiles, MGCN_AGG_WARPS);
   if (blocks > (int64_t)kNumSMs * MGCN_AGG_MINB) blocks = (int64_t)kNumSMs * MGCN_AGG_MINB;
-  MGCN_LAUNCH(k_agg_flat, (unsigned)blocks, 256, 0, stream, a);
+  MGCN_LAUNCH(k_agg_flat, (unsigned)blocks, MGCN_AGG_WARPS * 32, 0, stream, a);
   if (hubs) {
     const int rc = launch_hub_reduce(g, partial, stream);
     if (rc != MGCN_OK) return rc;
