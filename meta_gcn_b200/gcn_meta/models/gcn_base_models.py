@@ -163,49 +163,41 @@ class EdgeGateProj(nn.Module):
 
     def __init__(self, in_channels, in_edgedim=None, bias=False):
         super().__init__()
-        self.in_channels = in_channels
-        self.in_edgedim = in_edgedim
-        self.linsrc = nn.Linear(in_channels, 1, bias=False)
-        self.lintgt = nn.Linear(in_channels, 1, bias=False)
+        self.in_channels, self.in_edgedim = in_channels, in_edgedim
+        proj = lambda width: nn.Linear(width, 1, bias=False)     # noqa: E731  one scalar score per node / edge
+        self.linsrc, self.lintgt = proj(in_channels), proj(in_channels)
         if in_edgedim is not None:
-            self.linedge = nn.Linear(in_edgedim, 1, bias=False)
-        if bias:
-            self.bias = Parameter(torch.Tensor(1))
-        else:
-            self.register_parameter("bias", None)
+            self.linedge = proj(in_edgedim)
+        self.register_parameter("bias", Parameter(torch.empty(1)) if bias else None)   # one scalar for all edges
         self.reset_parameters()
 
     def reset_parameters(self, initrange=0.1):
-        nn.init.uniform_(self.linsrc.weight, -initrange, initrange)
-        nn.init.uniform_(self.lintgt.weight, -initrange, initrange)
-        if self.in_edgedim is not None:
-            nn.init.uniform_(self.linedge.weight, -initrange, initrange)
+        scored = [self.linsrc, self.lintgt] + ([self.linedge] if self.in_edgedim is not None else [])
+        for lin in scored:
+            nn.init.uniform_(lin.weight, -initrange, initrange)
         if self.bias is not None:
-            nn.init.constant_(self.bias, 0)
+            nn.init.zeros_(self.bias)
 
     def forward(self, x, edge_index, edge_attr=None, edge_weight=None):
-        a_src = F_mgcn.linear(x, self.linsrc.weight, weight_layout="out_in")      # [N,1]
-        a_tgt = F_mgcn.linear(x, self.lintgt.weight, weight_layout="out_in")
-        gate = a_src.index_select(0, edge_index[0]) + a_tgt.index_select(0, edge_index[1])
+        score = lambda lin, t: F_mgcn.linear(t, lin.weight, weight_layout="out_in")   # noqa: E731  [*, 1]
+        gate = score(self.linsrc, x).index_select(0, edge_index[0]) + score(self.lintgt, x).index_select(0, edge_index[1])
         if edge_attr is not None:
-            assert self.linedge is not None
-            gate = gate + F_mgcn.linear(edge_attr, self.linedge.weight, weight_layout="out_in")
+            gate = gate + score(self.linedge, edge_attr)
         if self.bias is not None:
             gate = gate + self.bias.view(-1, 1)
         return torch.sigmoid(gate)
 
 
 class EdgeGateFree(nn.Module):
-    """gcn_base_models.py:372-397: one free gate parameter per edge (fixed edge count)"""
+    """gcn_base_models.py:372-397: one free gate parameter per edge (fixed edge count), initialised to 1"""
 
     def __init__(self, num_edges):
         super().__init__()
         self.num_edges = num_edges
-        self.edge_gates = Parameter(torch.Tensor(num_edges, 1))
-        self.reset_parameters()
+        self.edge_gates = Parameter(torch.ones(num_edges, 1))
 
     def reset_parameters(self):
-        nn.init.constant_(self.edge_gates, 1)
+        nn.init.ones_(self.edge_gates)
 
     def forward(self, *args, **kwargs):
         return torch.sigmoid(self.edge_gates)

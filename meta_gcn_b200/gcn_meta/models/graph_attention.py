@@ -23,36 +23,31 @@ from .gcn_base_models import NodeModelBase
 
 
 class NodeModelAttention(NodeModelBase):
+    _ACTS = ("none", "lrelu", "relu")
+    _COMBINE = ("cat", "add", "mean")
+
     def __init__(self, in_channels, out_channels, in_edgedim=None, nheads=1, att_act="none", att_dropout=0,
                  att_combine="cat", att_dir="in", bias=False, **kwargs):
-        assert att_act in ["none", "lrelu", "relu"]
-        assert att_combine in ["cat", "add", "mean"]
-        assert att_dir in ["in", "out"]
-        super().__init__(in_channels, out_channels, in_edgedim)
-        self.nheads = nheads
-        if att_combine == "cat":
-            self.out_channels_1head = out_channels // nheads
-            assert self.out_channels_1head * nheads == out_channels, "out_channels should be divisible by nheads"
-        else:
-            self.out_channels_1head = out_channels
-        self.att_combine = att_combine
-        self.att_dir = att_dir
-        if att_combine == "cat":
-            self.weight = Parameter(torch.Tensor(in_channels, out_channels))
-        else:
-            self.weight = Parameter(torch.Tensor(in_channels, out_channels * nheads))
-        self.att_weight = Parameter(torch.Tensor(1, nheads, 2 * self.out_channels_1head))
+        if att_act not in self._ACTS or att_combine not in self._COMBINE or att_dir not in ("in", "out"):
+            raise AssertionError((att_act, att_combine, att_dir))
+        super().__init__(in_channels, out_channels, in_edgedim)     # deg_norm / edge_gate / aggr keep their defaults
+        self.nheads, self.att_combine, self.att_dir = nheads, att_combine, att_dir
+        concat = att_combine == "cat"
+        # 'cat': the heads share out_channels; 'add' / 'mean': every head is out_channels wide (graph_attention.py:31-45)
+        self.out_channels_1head = out_channels // nheads if concat else out_channels
+        if concat and self.out_channels_1head * nheads != out_channels:
+            raise AssertionError("out_channels should be divisible by nheads")
+        # parameters in the reference's creation order (same RNG stream -> same initial values)
+        self.weight = Parameter(torch.empty(in_channels, self.out_channels_1head * nheads))
+        self.att_weight = Parameter(torch.empty(1, nheads, 2 * self.out_channels_1head))
         self.att_act = activation(att_act)
         self.att_dropout = nn.Dropout(p=att_dropout)
-        if bias:
-            self.bias = Parameter(torch.Tensor(out_channels))
-        else:
-            self.register_parameter("bias", None)
+        self.register_parameter("bias", Parameter(torch.empty(out_channels)) if bias else None)
         self.reset_parameters()
 
     def reset_parameters(self):
-        glorot(self.weight)
-        glorot(self.att_weight)
+        for t in (self.weight, self.att_weight):
+            glorot(t)
         zeros(self.bias)
 
     def forward(self, x, edge_index, edge_attr=None, deg=None, edge_weight=None, attn_store=None, **kwargs):
@@ -84,8 +79,6 @@ class NodeModelAttention(NodeModelBase):
             attn_store.append(alpha)
         return torch.relu(out) if act == "relu" else out
 
-    def __repr__(self):
-        return ("{} (in_channels: {}, out_channels: {}, in_edgedim: {}, nheads: {}, att_activation: {},"
-                "att_dropout: {}, att_combine: {}, att_dir: {} | number of parameters: {}").format(
-                    self.__class__.__name__, self.in_channels, self.out_channels, self.in_edgedim, self.nheads,
-                    self.att_act, self.att_dropout.p, self.att_combine, self.att_dir, self.num_parameters())
+    def extra_repr(self):
+        return (f"{self.in_channels} -> {self.out_channels}, heads={self.nheads}, combine={self.att_combine}, "
+                f"dir={self.att_dir}, att_dropout={self.att_dropout.p}")
