@@ -157,10 +157,17 @@ __global__ void __launch_bounds__(kGThreads, 1) k_wgrad_wide(const WgradWideArgs
 
   int64_t chunk = split;
   Chunk cur = load_chunk(chunk);
+#ifdef MGCN_WGRAD_DEEP
+  Chunk nxt = load_chunk(chunk + a.S);     // two chunks of look-ahead: 96 KB of loads in flight per SM
+#endif
   int it = 0, n_flushed = 0;
   uint32_t chain_phase = 0;
   for (; chunk < n_chunks; chunk += a.S, ++it) {
+#ifdef MGCN_WGRAD_DEEP
+    Chunk nxt2 = load_chunk(chunk + 2 * (int64_t)a.S);
+#else
     Chunk nxt = load_chunk(chunk + a.S);
+#endif
     const int s = it & 1;
     if (it >= 2) mbar_wait(bar_done + s, ((it >> 1) - 1) & 1);   // the tensor core has consumed this stage
     unsigned char* st = smem + s * kGStage;
@@ -223,6 +230,9 @@ __global__ void __launch_bounds__(kGThreads, 1) k_wgrad_wide(const WgradWideArgs
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     cur = nxt;
+#ifdef MGCN_WGRAD_DEEP
+    nxt = nxt2;
+#endif
   }
   if (n_flushed == 0 && m_row < a.Hi) {   // a CTA without chunks still owns its slice of the partial
     for (int c0 = col_w0; c0 < col_w0 + ncol_w; c0 += 4) *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
