@@ -126,12 +126,12 @@ struct Row8 {
 
 __device__ __forceinline__ Row8 ld_row8(const float* p) {
   Row8 r;
-#ifdef MGCN_GATHER_NOL1
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#elif defined(MGCN_GATHER_L1LAST)
-  asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#else
+  // gathered rows do not allocate in L1: its hit rate on them is 8 % (ncu), and skipping the allocation is worth
+  // 1 - 2 % of the gather kernels (L1::evict_last was slower, plain allocation the previous default)
+#ifdef MGCN_GATHER_L1ALLOC
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 #endif
                : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]),
                  "=f"(r.v[6]), "=f"(r.v[7])
