@@ -61,25 +61,33 @@ class GraphBatch:
 
     @staticmethod
     def from_data_list(graphs):
-        """graphs: list of dicts / objects with x, edge_index, y (numpy arrays or tensors)."""
-        xs, eis, ys, ids, sx, se = [], [], [], [], [0], [0]
-        off = 0
-        for g, item in enumerate(graphs):
+        """graphs: list of dicts / objects with x, edge_index, y (numpy arrays or tensors, on the host or all on one
+        CUDA device).  Batch.from_data_list of data/dataloader.py:11: node-wise concatenation, edge indices shifted by
+        the node offset, graph-id vector, cumulative boundaries.  Device inputs are collated on the device (one
+        cat per field, offsets added by a broadcast) — no host round trip."""
+        xs, eis, ys, sx, se = [], [], [], [0], [0]
+        for item in graphs:
             get = item.get if isinstance(item, dict) else (lambda k, it=item: getattr(it, k, None))
             x = torch.as_tensor(get("x"))
             ei = torch.as_tensor(get("edge_index")).long()
-            n = x.size(0)
             xs.append(x)
-            eis.append(ei + off)
+            eis.append(ei)
             y = get("y")
             if y is not None:
                 ys.append(torch.as_tensor(y).reshape(-1) if np.ndim(y) <= 1 else torch.as_tensor(y))
-            ids.append(torch.full((n,), g, dtype=torch.long))
-            off += n
-            sx.append(off)
+            sx.append(sx[-1] + x.size(0))
             se.append(se[-1] + ei.size(1))
+        dev = xs[0].device if xs else torch.device("cpu")
+        counts_n = torch.tensor([b - a for a, b in zip(sx, sx[1:])], dtype=torch.long, device=dev)
+        counts_e = torch.tensor([b - a for a, b in zip(se, se[1:])], dtype=torch.long, device=dev)
+        gid = torch.arange(len(xs), dtype=torch.long, device=dev)
+        batch = torch.repeat_interleave(gid, counts_n)                                   # graph id per node, sorted
+        node_off = torch.tensor(sx[:-1], dtype=torch.long, device=dev)
+        edge_off = torch.repeat_interleave(node_off, counts_e)                           # node offset per edge entry
+        edge_index = (torch.cat(eis, dim=1) + edge_off.unsqueeze(0)) if eis else torch.zeros(2, 0, dtype=torch.long)
         y = torch.cat(ys) if ys else None
-        return GraphBatch(torch.cat(xs), torch.cat(eis, dim=1), y, torch.cat(ids), sx, se)
+        x = torch.cat(xs) if xs else torch.zeros(0, 0)
+        return GraphBatch(x, edge_index, y, batch, sx, se)
 
 
 class DeviceLoader:

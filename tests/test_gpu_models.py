@@ -337,3 +337,18 @@ def test_graphed_call_replays_the_eager_step_bit_exactly():
     assert float(fwd_loss_bwd()) == loss_g2 and loss_g2 != loss_e
     for p, gg in zip(params, grads_g2):
         assert torch.equal(p.grad, gg)
+
+
+def test_from_data_list_collates_on_the_device():
+    """GraphBatch.from_data_list with CUDA inputs (Batch.from_data_list of data/dataloader.py:11): same batch as the
+    host collation, built on the device"""
+    from meta_gcn_b200.data import GraphBatch, synth_tu_graph
+    rng = np.random.default_rng(1)
+    graphs = [synth_tu_graph(rng) for _ in range(7)]
+    host = GraphBatch.from_data_list(graphs)
+    dev_graphs = [{k: torch.as_tensor(v).to(DEV) for k, v in g.items()} for g in graphs]
+    devb = GraphBatch.from_data_list(dev_graphs)
+    assert devb.x.is_cuda and devb.edge_index.is_cuda and devb.batch.is_cuda
+    for name in ("x", "edge_index", "y", "batch"):
+        assert torch.equal(getattr(devb, name).cpu(), getattr(host, name)), name
+    assert devb.slices_x == host.slices_x and devb.num_graphs == 7
