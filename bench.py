@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=12)   # the first copy of a loop cannot be overlapped
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-graphs", default="24,25",
+                    help="global batch sizes of the strong-scaling measurement (configs[1]: 25 graphs sharded over "
+                         "the GPUs by edge count; 24 divides evenly); empty = skip")
     return ap.parse_args()
 
 
@@ -167,7 +170,9 @@ def run_reference(args):
         "graphs_per_s": 1.0 / t, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": dict(workload_config(args, args.gpus), graphs_in_step=1,
+                       note="the CPU arm steps ONE of the batch's graphs per step (bounded sample) and is normalised "
+                            "to edges/s; the GPU arm steps all graphs_per_gpu graphs"),
         "cpu_baseline": {"value": gedges, "unit": "GEdges/s", "cores": torch.get_num_threads(),
                          "kind": "port", "sample": sample},
         "e2e": {"value": gedges, "unit": "GEdges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,7 +198,14 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     seeds = [rank * args.graphs + i for i in range(args.graphs)]
-    graphs = make_graphs(seeds, args.nodes, args.edges)   # before CUDA init (fork-safe)
+    # strong scaling (configs[1] as written: ONE global batch of 25 graphs sharded over the GPUs; 24 divides evenly):
+    # graph i of the global batch goes to rank i % world — the greedy balance by edge count (dist.shard_by_weight) of
+    # graphs whose nominal sizes are equal
+    strong_sizes = [int(v) for v in args.strong_graphs.split(",") if v.strip()]
+    strong_seeds = sorted({i for g_ in strong_sizes for i in range(g_) if i % world == rank})
+    all_seeds = sorted(set(seeds) | set(strong_seeds))
+    by_seed = dict(zip(all_seeds, make_graphs(all_seeds, args.nodes, args.edges)))   # before CUDA init (fork-safe)
+    graphs = [by_seed[s_] for s_ in seeds]
 
     import torch
     import torch.distributed as dist
@@ -208,6 +220,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     mdist.init_from_env("nccl")
+    # the whole run, eager warm-up included, on one non-default stream: autograd's AccumulateGrad nodes remember the
+    # stream they were created on, and the CUDA-graph capture of the step must not touch the legacy default stream
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
 
     host = GraphBatch.from_data_list(graphs).pin_memory()
     n_nodes, n_edges = host.num_nodes, host.num_edges
@@ -246,54 +261,76 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident arm ----
+    def measure_resident(batch, steps):
+        """structures built once outside the timed region; forward + loss + backward of the fixed-shape batch replayed
+        as ONE CUDA graph (meta_gcn_b200/graphed.py), all-reduce and Adam eager; --no-cuda-graph times the eager
+        step.  Returns (ms per step as max over ranks, libmgcn launches in the timed region, graphed?, last loss)."""
+        structure_of(batch.edge_index, batch.num_nodes).fwd
+        structure_of(batch.edge_index, batch.num_nodes).bwd_plain
+        for _ in range(args.warmup):
+            step(batch)
+        use_graph = not args.no_cuda_graph
+        graph_launches = 0
+        resident_step = step
+        if use_graph:
+            from meta_gcn_b200.graphed import GraphedCall
+            try:
+                c0 = _lib.launch_count()
+                graphed = GraphedCall(lambda: fwd_loss_bwd(batch), warmup=1)
+                graph_launches = (_lib.launch_count() - c0) // 2      # one warm-up call + the captured call
+
+                def resident_step(_b):
+                    loss_sum = graphed()
+                    mean_loss, _ = reducer.reduce_mean(loss_sum, batch.num_nodes)
+                    opt.step()
+                    return mean_loss
+                for _ in range(2):
+                    resident_step(batch)
+            except Exception as exc:   # capture refused: report it and time the eager step instead
+                print(f"[bench] CUDA-graph capture failed, timing the eager step: {exc!r}", file=sys.stderr)
+                use_graph = False
+                resident_step = step
+                torch.cuda.synchronize()
+        barrier()
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            loss = resident_step(batch)
+        ev1.record()
+        barrier()
+        ms_ = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        # kernels of libmgcn.so inside the timed region: host-side launches + those replayed from the graph
+        n_launch = (_lib.launch_count() - launches0) + (graph_launches * steps if use_graph else 0)
+        return ms_, n_launch, use_graph, float(loss.item())
+
+    # ---- device-resident arm (weak scaling: every rank its own batch of --graphs graphs) ----
     batch = host.to(dev)
     batch.x = batch.x.contiguous()
-    structure_of(batch.edge_index, n_nodes).fwd  # structures built once, outside the timed region
-    structure_of(batch.edge_index, n_nodes).bwd
-    for _ in range(args.warmup):
-        step(batch)
-    # device-resident arm: forward + loss + backward of the fixed-shape batch replayed as ONE CUDA graph
-    # (meta_gcn_b200/graphed.py); the all-reduce and Adam stay eager.  --no-cuda-graph times the eager step.
-    use_graph = not args.no_cuda_graph
-    graph_launches = 0
-    resident_step = step
-    if use_graph:
-        from meta_gcn_b200.graphed import GraphedCall
-        try:
-            c0 = _lib.launch_count()
-            graphed = GraphedCall(lambda: fwd_loss_bwd(batch), warmup=1)
-            graph_launches = (_lib.launch_count() - c0) // 2      # one warm-up call + the captured call
-
-            def resident_step(_b):
-                loss_sum = graphed()
-                mean_loss, _ = reducer.reduce_mean(loss_sum, batch.num_nodes)
-                opt.step()
-                return mean_loss
-            for _ in range(2):
-                resident_step(batch)
-        except Exception as exc:   # capture refused: report it and time the eager step instead
-            print(f"[bench] CUDA-graph capture failed, timing the eager step: {exc!r}", file=sys.stderr)
-            use_graph = False
-            resident_step = step
-            torch.cuda.synchronize()
-    barrier()
     sampler = ClockSampler(local)
+    structure_of(batch.edge_index, n_nodes).fwd
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        loss = resident_step(batch)
-    ev1.record()
-    barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    # kernels of libmgcn.so inside the timed region: host-side launches + those replayed from the graph
-    launches = (_lib.launch_count() - launches0) + (graph_launches * args.steps if use_graph else 0)
+    ms, launches, use_graph, final_loss = measure_resident(batch, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    final_loss = float(loss.item())
+
+    # ---- strong scaling: one GLOBAL batch of G graphs sharded over the ranks ----
+    strong = []
+    for g_total in strong_sizes:
+        mine = [by_seed[i] for i in range(g_total) if i % world == rank]
+        clear_structure_cache()
+        sb = GraphBatch.from_data_list(mine).to(dev)
+        sb.x = sb.x.contiguous()
+        s_ms, _, s_graph, _ = measure_resident(sb, args.steps)
+        e_mine = torch.tensor([float(sb.num_edges)], device=dev)
+        if world > 1:
+            dist.all_reduce(e_mine)
+        strong.append({"global_batch_graphs": g_total, "graphs_on_rank0": len(mine), "ms_per_step": s_ms,
+                       "graphs_per_s": g_total / (s_ms / 1e3),
+                       "gedges_per_s": float(e_mine.item()) * LAYERS * 2 / (s_ms / 1e3) / 1e9, "cuda_graph": s_graph})
+        del sb
+    clear_structure_cache()
 
     # ---- dominant kernel alone: the fused forward layer (aggregation + dense tail) and the plain
     # aggregation of the backward, over this rank's batch, CUDA events on the launching stream ----
@@ -385,6 +422,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(workload_config(args, world), cuda_graph=bool(use_graph)),
         "loss": final_loss,
+        "strong_scaling": {"scaling": "strong", "partition": "graph i of the global batch -> rank i % n_gpus",
+                           "runs": strong},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm",

@@ -256,8 +256,27 @@ int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n_in, const 
  * for layer 0 without materialising x W_in or x R^T.  w_in [H_in][32] (in,out), res_w [32][H_in] (out,in). */
 int mgcn_gcn_first_layer_fwd(const float* s, const float* x, int64_t N, int64_t Hin, const float* w_in,
                              const float* res_w, const float* res_b, const float* w_next, const float* pre,
-                             const float* post, int act_out, int64_t H, float* x_next, float* m_next,
-                             uint32_t* hmask, void* stream);
+                             const float* post, const float* out_scale, int act_out, int64_t H, float* x_next,
+                             float* m_next, uint32_t* hmask, void* stream);
+/* out_scale [N] (may be NULL; only with w_next == NULL): x_next rows leave multiplied by it — the input format of
+ * mgcn_gcn_layer_fwd_tc below. */
+
+/* One residual GCN layer forward at hidden 32, AGGREGATE-THEN-TRANSFORM, on tcgen05.mma / tensor memory
+ * (csrc/gcn_fwd_tc.cu) — the default of the hidden-32 stack.  Same reference lines as mgcn_gcn_layer_fwd
+ * (gcn_model.py:89-106, gcn_base_models.py:199-243), computed as (A_hat x) W instead of A_hat (x W):
+ *     s_i    = post_i * sum_{e: col[e]=i} z[row[e]]          z = in_scale (.) x_n: the stored rows carry the
+ *                                                            per-source degree factor, so no per-edge weight is read
+ *     h_i    = relu(s_i w + bias);   hmask[i] bit c = (h[i,c] > 0)
+ *     y_i    = h_i + (z_i res_w^T) / in_scale_i + res_b      (= h_i + x_i res_w^T + res_b)
+ *     z_next = out_scale_i * (act_out ? relu(y_i) : y_i)
+ * The layer reads one [N,32] array and writes one (no message array beside the activations).  in_scale / post /
+ * out_scale are [N] or NULL (= 1); in_scale must be > 0 on every row (callers store sigma = pre where pre > 0, else 1:
+ * a row with pre == 0 computed from the graph's own out-degree is never gathered).  w [32][32] (in,out), res_w [32][32]
+ * (out,in).  Sums run in edge_index order per row; dense products are 3xTF32 with separately accumulated corrections. */
+int mgcn_gcn_layer_fwd_tc(const mgcn_csr_t* g, const float* z, int64_t n_in, const float* w, const float* res_w,
+                          const float* res_b, const float* bias, const float* in_scale, const float* post,
+                          const float* out_scale, int act_out, int64_t H, float* z_next, uint32_t* hmask,
+                          void* workspace, size_t* workspace_bytes, void* stream);
 
 /* backward, row-local part of layer n (dxw = pre * A^T gs comes from mgcn_aggregate_prescaled on the
  * structure built by source):
@@ -273,8 +292,10 @@ int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float* x, const 
  * once into tf32 hi/lo images in shared memory (K-major images for the row-local products, SWIZZLE_128B_BASE32B
  * images for the transposed ones); a persistent CTA per SM runs producer / issuer / epilogue roles over two operand
  * stages and two accumulator buffers (csrc/gcn_layer_tc.cu).  Same contract and the same results within rounding
- * as mgcn_gcn_layer_bwd; 0.58 ms against 0.81 ms per layer at the botnet batch (profiles/r1b_layer_summary.md). */
-int mgcn_gcn_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* w,
+ * as mgcn_gcn_layer_bwd; 0.58 ms against 0.81 ms per layer at the botnet batch (profiles/r1b_layer_summary.md).
+ * x_scale [N] or NULL: the array passed as x holds x_scale (.) x (the stored format of mgcn_gcn_layer_fwd_tc); the
+ * factor is divided out as the rows are loaded. */
+int mgcn_gcn_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* x_scale, const float* w,
                           const float* res_w, const uint32_t* hmask_prev, const float* post, int64_t N,
                           int64_t H, float* gy_prev, float* gs_prev, float* dw, float* d_res_w,
                           float* d_res_b, void* workspace, size_t* workspace_bytes, void* stream);

@@ -85,7 +85,7 @@ int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, in
 
 // tcgen05 row-local backward of the hidden-32 layer (gcn_layer_tc.cu)
 size_t bwd_tc_workspace_floats(int64_t N);
-int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* w, const float* res_w,
+int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* x_scale, const float* w, const float* res_w,
                         const uint32_t* hmask_prev, const float* post, int64_t N, float* gy_prev, float* gs_prev,
                         float* dw, float* d_res_w, float* d_res_b, float* ws, void* stream);
 // narrow-side dense transforms (dense_narrow.cu)

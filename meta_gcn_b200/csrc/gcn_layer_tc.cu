@@ -43,6 +43,7 @@ struct BwdTcArgs {
   const float* dxw;
   const float* gy;
   const float* x;
+  const float* x_scale;      // [N] or NULL: the stored rows are x_scale (.) x (aggregate-then-transform stack); undone on load
   const float* w;            // weight_node (in j, out c)
   const float* res_w;        // residual weight (out c, in j)
   const uint32_t* hmask_prev;
@@ -203,12 +204,19 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       const float* src[3] = {a.dxw, a.gy, a.x};
       const int64_t gr = tile * kTRows + r0;
       const bool ok = tile < n_tiles && gr < a.n_rows;
+      float xs = 1.f;
+      if (ok && a.x_scale) xs = __frcp_rn(__ldg(a.x_scale + gr));
 #pragma unroll
       for (int arr = 0; arr < 3; ++arr) {
         F8 v;
         v.lo = v.hi = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) v = ld_f8_hint(src[arr] + gr * kTH + 8 * qq, pol);
         dst[arr] = v;
+      }
+      if (a.x_scale) {
+        F8& v = dst[2];
+        v.lo.x *= xs; v.lo.y *= xs; v.lo.z *= xs; v.lo.w *= xs;
+        v.hi.x *= xs; v.hi.y *= xs; v.hi.z *= xs; v.hi.w *= xs;
       }
     };
     unsigned char* st = smem + pset * kStageB;
@@ -475,12 +483,12 @@ int bwd_tc_grid(int64_t N) {
 
 size_t bwd_tc_workspace_floats(int64_t N) { return (size_t)bwd_tc_grid(N) * (128 * 32 + 32); }
 
-int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* w, const float* res_w,
+int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const float* x_scale, const float* w, const float* res_w,
                         const uint32_t* hmask_prev, const float* post, int64_t N, float* gy_prev, float* gs_prev,
                         float* dw, float* d_res_w, float* d_res_b, float* ws, void* stream) {
   const int P = bwd_tc_grid(N);
   BwdTcArgs a{};
-  a.dxw = dxw; a.gy = gy; a.x = x; a.w = w; a.res_w = res_w; a.hmask_prev = hmask_prev; a.post = post;
+  a.dxw = dxw; a.gy = gy; a.x = x; a.x_scale = x_scale; a.w = w; a.res_w = res_w; a.hmask_prev = hmask_prev; a.post = post;
   a.gy_prev = gy_prev; a.gs_prev = gs_prev;
   a.part_t = ws;
   a.part_b = ws + (size_t)P * 128 * 32;

@@ -17,6 +17,9 @@ FUSED_WIDTHS = (16, 32, 64, 128)
 # row-local backward of the hidden-32 stack: tcgen05 / TMEM pipeline (0.64 ms per layer at the botnet batch)
 # or the mma.sync kernel (0.81 ms); both pass the same parity tests
 BWD_TENSOR_MEMORY = True
+# hidden-32 stack: aggregate-then-transform forward on tcgen05 (csrc/gcn_fwd_tc.cu; one [N,32] read + one write per
+# layer) or the transform-then-aggregate kernels of round 1 (csrc/gcn_layer.cu); both pass the same parity tests
+FORWARD_AGGREGATE_FIRST = True
 
 
 class _ResidualGCNStack(torch.autograd.Function):
@@ -149,11 +152,92 @@ class _ResidualGCNStack32(torch.autograd.Function):
         return (gx, None, None, None, None, *grads)
 
 
+class _ResidualGCNStack32AT(torch.autograd.Function):
+    """hidden width 32, no node-model bias, AGGREGATE-THEN-TRANSFORM: (A_hat x) W instead of A_hat (x W).  One
+    tcgen05 launch per layer forward (csrc/gcn_fwd_tc.cu) that reads one [N,32] array and writes one: activations are
+    stored as z_n = sigma (.) x_n (sigma = the per-source degree factor, 1 where that factor is 0 — such a row is
+    never a source when the degree is the graph's own out-degree), so the gather needs no per-edge weight and no
+    separate message array; the row-local terms divide sigma out per row.  Saved per layer: z_n and one mask word
+    per row.  Backward: dW_n = x_n^T (A_hat^T ga), dx = (A_hat^T ga) W_n^T + gy R_n — the transposed aggregation of
+    the masked gradient, then the row-local tcgen05 launch."""
+
+    @staticmethod
+    def forward(ctx, x, graph, pre, post, last_relu, *params):
+        L = len(params) // 3
+        layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
+        fwd = graph.fwd
+        x0 = x.contiguous()
+        sigma = None
+        if pre is not None:
+            sigma = torch.where(pre > 0, pre, torch.ones_like(pre))
+        zs, hmasks = [], []
+        agg_first = x0.size(1) <= 4
+        s0 = None
+        if agg_first:
+            xs0 = x0 * pre.unsqueeze(1) if pre is not None else x0            # pre_j x_j, one rounding as in the gather
+            s0 = ops.spmm_impl(fwd, xs0)                                      # [N, H_in]
+            z, _, hm = ops.gcn_first_layer_fwd_impl(
+                s0, x0, layers[0][0], layers[0][1], layers[0][2], None, None, post,
+                1 if (last_relu or L > 1) else 0, out_scale=sigma if L > 1 else None)
+            zs.append(None)
+            hmasks.append(hm)
+            first = 1
+        else:
+            z = x0 * sigma.unsqueeze(1) if sigma is not None else x0
+            first = 0
+        for n in range(first, L):
+            zs.append(z)
+            z, hm = ops.gcn_layer_fwd_tc_impl(
+                fwd, z, layers[n][0], layers[n][1], layers[n][2], None, sigma, post,
+                sigma if n < L - 1 else None, 1 if (last_relu or n < L - 1) else 0)
+            hmasks.append(hm)
+        ctx.agg_first = agg_first
+        ctx.graph, ctx.cfg = graph, (L, last_relu)
+        ctx.save_for_backward(x0, s0, pre, post, sigma, z if last_relu else None,
+                              *[t for t in zs if t is not None], *hmasks, *params)
+        return z
+
+    @staticmethod
+    def backward(ctx, g):
+        L, last_relu = ctx.cfg
+        saved = ctx.saved_tensors
+        x0, s0, pre, post, sigma, out = saved[:6]
+        nz = L - 1 if ctx.agg_first else L
+        zs = list(saved[6:6 + nz])
+        if ctx.agg_first:
+            zs = [None] + zs
+        hmasks = saved[6 + nz:6 + nz + L]
+        params = saved[6 + nz + L:]
+        layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
+        bwd = ctx.graph.bwd_plain
+        grads = [None] * len(params)
+        gy = g.contiguous()
+        if last_relu:
+            gy = ops.relu_backward_impl(gy, out)
+        gs = ops.mask_bits_scale_impl(gy, hmasks[L - 1], post)
+        last = 1 if ctx.agg_first else 0
+        for n in range(L - 1, last - 1, -1):
+            dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
+            want_prev = n > 0
+            gy_prev, gs_prev, dw, drw, drb = ops.gcn_layer_bwd_impl(
+                dxw, gy, zs[n], layers[n][0], layers[n][1], hmasks[n - 1] if want_prev else None, post,
+                want_prev, True, x_scale=sigma)
+            grads[3 * n], grads[3 * n + 1], grads[3 * n + 2] = dw, drw, drb
+            if want_prev:
+                gy, gs = gy_prev, gs_prev
+        if ctx.agg_first:
+            grads[1], grads[2] = ops.linear_wgrad_impl(x0, gy, True, True)
+            grads[0] = ops.linear_wgrad_impl(s0, gs, False, False)[0]    # dW0 = s0^T gs0
+        return (None, None, None, None, None, *grads)
+
+
 def residual_gcn_stack(x, graph, pre, post, layer_params, has_bias, last_relu=False):
     """layer_params: per layer (weight_node [Hin,H], [bias [H]], residual.weight [H,Hin],
     residual.bias [H]).  pre/post: per-source / per-target degree factors (either may be None)."""
     flat = [p for lp in layer_params for p in lp]
     widths = {lp[0].size(1) for lp in layer_params} | {lp[0].size(0) for lp in layer_params[1:]}
     if not has_bias and widths == {32}:
+        if FORWARD_AGGREGATE_FIRST and not x.requires_grad and (x.size(1) <= 4 or x.size(1) == 32):
+            return _ResidualGCNStack32AT.apply(x, graph, pre, post, last_relu, *flat)
         return _ResidualGCNStack32.apply(x, graph, pre, post, last_relu, *flat)
     return _ResidualGCNStack.apply(x, graph, pre, post, has_bias, last_relu, *flat)

@@ -16,19 +16,29 @@ import torch
 
 
 class GraphedCall:
+    """Run the training loop (eager warm-up steps included) under ONE non-default stream and construct this object
+    there: autograd's AccumulateGrad nodes remember the stream they were created on, and a node created on the legacy
+    default stream cannot run inside a capture (cudaErrorStreamCaptureImplicit).  Called on the default stream, a
+    private side stream is used for warm-up and capture, which works as long as no earlier eager backward on the
+    default stream is still referenced."""
+
     def __init__(self, fn, warmup=3):
         self.fn = fn
         self.graph = None
         self.out = None
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
+        cur = torch.cuda.current_stream()
+        if cur == torch.cuda.default_stream():
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+        else:
+            side = cur
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):       # lazy initialisation (cudaFuncSetAttribute, structure cache, allocator)
                 fn()
-        torch.cuda.current_stream().wait_stream(side)
+        cur.wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):
             self.out = fn()
         self.graph = graph
 

@@ -421,10 +421,11 @@ def gcn_layer_fwd_impl(csr, m, x, resid, res_w, res_b, w_next, bias, pre, post, 
     return x_next, m_next, hmask
 
 
-def gcn_first_layer_fwd_impl(s, x, w_in, res_w, res_b, w_next, pre, post, act_out):
+def gcn_first_layer_fwd_impl(s, x, w_in, res_w, res_b, w_next, pre, post, act_out, out_scale=None):
     """first layer with a narrow input (mgcn_gcn_first_layer_fwd): s = aggregated input [N,Hin], x = layer input
-    [N,Hin]; returns (x_next [N,32], m_next | None, hmask int32[N])"""
-    _need_cuda(s, x, w_in, res_w, res_b, w_next, pre, post)
+    [N,Hin]; returns (x_next [N,32], m_next | None, hmask int32[N]); out_scale [N]: x_next rows leave scaled"""
+    _need_cuda(s, x, w_in, res_w, res_b, w_next, pre, post, out_scale)
+    out_scale = _f32c(out_scale, "out_scale")
     s = _f32c(s, "s")
     x = _f32c(x, "x")
     w_in = _f32c(w_in, "w_in")
@@ -443,14 +444,43 @@ def gcn_first_layer_fwd_impl(s, x, w_in, res_w, res_b, w_next, pre, post, act_ou
     hmask = torch.empty(N, dtype=torch.int32, device=dev)
     _lib.check(_lib.load().mgcn_gcn_first_layer_fwd(
         _ptr(s), _ptr(x), N, Hin, _ptr(w_in), _ptr(res_w), _ptr(res_b), _ptr(w_next), _ptr(pre), _ptr(post),
-        int(act_out), H, _ptr(x_next), _ptr(m_next), _ptr(hmask), _stream()))
+        _ptr(out_scale), int(act_out), H, _ptr(x_next), _ptr(m_next), _ptr(hmask), _stream()))
     return x_next, m_next, hmask
 
 
-def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, tensor_memory=False):
+def gcn_layer_fwd_tc_impl(csr, z, w, res_w, res_b, bias, in_scale, post, out_scale, act_out):
+    """one aggregate-then-transform forward layer at hidden 32 on tcgen05 (mgcn_gcn_layer_fwd_tc): z = in_scale (.) x
+    [N,32]; returns (z_next = out_scale (.) x_next [N,32], hmask int32[N])"""
+    _need_cuda(z, w, res_w, res_b, bias, in_scale, post, out_scale)
+    z = _f32c(z, "z")
+    w = _f32c(w, "w")
+    res_w = _f32c(res_w, "res_w")
+    res_b = _f32c(res_b, "res_b")
+    bias = _f32c(bias, "bias")
+    in_scale = _f32c(in_scale, "in_scale")
+    post = _f32c(post, "post")
+    out_scale = _f32c(out_scale, "out_scale")
+    n_rows, H = csr.n_rows, z.size(1)
+    if tuple(w.shape) != (H, H) or tuple(res_w.shape) != (H, H):
+        raise ValueError("gcn_layer_fwd_tc needs square [32,32] weights")
+    dev = z.device
+    z_next = torch.empty(n_rows, H, dtype=torch.float32, device=dev)
+    hmask = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    args = (ctypes.byref(csr.struct()), _ptr(z), z.size(0), _ptr(w), _ptr(res_w), _ptr(res_b), _ptr(bias),
+            _ptr(in_scale), _ptr(post), _ptr(out_scale), int(act_out), H, _ptr(z_next), _ptr(hmask))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_gcn_layer_fwd_tc(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_gcn_layer_fwd_tc(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return z_next, hmask
+
+
+def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, tensor_memory=False, x_scale=None):
     """row-local backward of one layer at hidden 32 (mgcn_gcn_layer_bwd): returns
-    (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b)"""
-    _need_cuda(dxw, gy, x, w, res_w, hmask_prev, post)
+    (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b).  x_scale [N] (tensor_memory only): x holds x_scale (.) x"""
+    _need_cuda(dxw, gy, x, w, res_w, hmask_prev, post, x_scale)
+    if x_scale is not None and not tensor_memory:
+        raise ValueError("x_scale needs the tcgen05 backward")
+    x_scale = _f32c(x_scale, "x_scale")
     dxw = _f32c(dxw, "dxw")
     gy = _f32c(gy, "gy")
     x = _f32c(x, "x")
@@ -465,7 +495,8 @@ def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, t
     drw = torch.empty(H, H, dtype=torch.float32, device=dev)
     drb = torch.empty(H, dtype=torch.float32, device=dev)
     lib = _lib.load()
-    args = (_ptr(dxw), _ptr(gy), _ptr(x), _ptr(w), _ptr(res_w), _ptr(hmask_prev) if want_prev else None,
+    args = (_ptr(dxw), _ptr(gy), _ptr(x), *((_ptr(x_scale),) if tensor_memory else ()), _ptr(w), _ptr(res_w),
+            _ptr(hmask_prev) if want_prev else None,
             _ptr(post), N, H, _ptr(gy_prev), _ptr(gs_prev), _ptr(dw), _ptr(drw), _ptr(drb))
     fn = lib.mgcn_gcn_layer_bwd_tc if tensor_memory else lib.mgcn_gcn_layer_bwd
     ws, nbytes = _workspace(lambda w_, nb, stm: fn(*args, w_, nb, stm), dev)

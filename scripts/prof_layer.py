@@ -9,6 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--graphs", type=int, default=25)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--hub", type=int, default=64)
+ap.add_argument("--only", default="")
 args = ap.parse_args()
 
 from bench import make_graphs, b_agg  # noqa: E402
@@ -36,6 +37,8 @@ bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), device=dev, dtype=torch.int64)
 
 
 def timeit(name, fn, byts):
+    if args.only and args.only not in name:
+        return
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -53,6 +56,9 @@ nh = 4 * n * H
 print(f"N={n} E={e} hubs={int(gs.fwd.hub_count)} segs={int(gs.fwd.seg_count)}")
 timeit("layer_fwd (gather+2 products)", lambda: ops.gcn_layer_fwd_impl(gs.fwd, m, x, None, r, rb, w, None, dis, dis, 1),
        4 * e + 8 * n + 4 * nh)
+if hasattr(ops, "gcn_layer_fwd_tc_impl"):
+    timeit("layer_fwd_tc (aggregate-then-transform)",
+           lambda: ops.gcn_layer_fwd_tc_impl(gs.fwd, x, w, r, rb, None, dis, dis, dis, 1), b_agg(n, e, H))
 timeit("layer_fwd last (no next)", lambda: ops.gcn_layer_fwd_impl(gs.fwd, m, x, None, r, rb, None, None, dis, dis, 0),
        4 * e + 8 * n + 3 * nh)
 x1 = torch.ones(n, 1, device=dev)

@@ -144,7 +144,8 @@ def test_layer_fwd_row_local_mode(n):
     assert (got == (z.numpy() > 0)).all()
 
 
-@pytest.mark.parametrize("n,hin,act_out,with_next", [(1000, 1, 1, True), (1003, 2, 0, False), (37, 4, 1, True), (150001, 1, 1, True)])
+@pytest.mark.parametrize("n,hin,act_out,with_next", [(1000, 1, 1, True), (1003, 2, 0, False), (37, 4, 1, True), (150001, 1, 1, True),
+                                                     (1001, 1, 1, None)])
 def test_first_layer_fwd_narrow_input(n, hin, act_out, with_next):
     """mgcn_gcn_first_layer_fwd: h = relu(post (s W)), y = h + x R^T + r, x' = act(y), m' = pre (x' W') from the
     two [N, H_in] operands (gcn_base_models.py:199-243 + gcn_model.py:96-105 for layer 0), fp64 restatement"""
@@ -158,12 +159,16 @@ def test_first_layer_fwd_narrow_input(n, hin, act_out, with_next):
     pre = torch.rand(n, generator=gen) + 0.1
     post = torch.rand(n, generator=gen) + 0.1
     d = lambda t: t.to(DEV)
+    out_scale = torch.rand(n, generator=gen) + 0.1 if with_next is None else None   # the scaled-rows output format
     xn, mn, hm = ops.gcn_first_layer_fwd_impl(d(s), d(x), d(w_in), d(res_w), d(res_b), d(w_next) if with_next else None,
-                                              d(pre), d(post), act_out)
+                                              d(pre), d(post), act_out,
+                                              out_scale=None if out_scale is None else d(out_scale))
     D = lambda t: t.double()
     z = D(post).view(-1, 1) * (D(s) @ D(w_in))
     y = torch.relu(z) + D(x) @ D(res_w).t() + D(res_b)
     x_ref = torch.relu(y) if act_out else y
+    if out_scale is not None:
+        x_ref = x_ref * D(out_scale).view(-1, 1)
     assert_parity(xn, x_ref, "x_next")
     if with_next:
         assert_parity(mn, D(pre).view(-1, 1) * (x_ref @ D(w_next)), "m_next")
@@ -193,3 +198,90 @@ def test_giant_hub_rows_cta_wide_reduce():
     assert_bitexact(outs[0], outs[1], "run-to-run")
     ref = torch.zeros(n, H, dtype=torch.float64).index_add_(0, ei[1], x.double()[ei[0]])
     assert_parity(outs[0], ref, "aggregation with giant hubs")
+
+
+def _giant_hub_graph(n=4000):
+    g = np.random.default_rng(7)
+    src = g.integers(0, n, 30000)
+    dst = g.integers(0, n, 30000)
+    dst[:9000] = 11           # 141 segments at threshold 64
+    dst[9000:12500] = 12      # 55 segments
+    dst[12500:13000] = 13     # 8 segments
+    return torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+
+
+@pytest.mark.parametrize("n,e,act_out,scaled,with_bias", [
+    (1000, 9000, 1, True, False),
+    (1003, 12000, 0, True, True),
+    (517, 3000, 1, False, False),
+    (128, 700, 1, True, False),
+    (16, 40, 1, True, True),
+    (5, 0, 1, True, False),
+    (40000, 400000, 1, True, False),
+    (4000, -1, 1, True, False),      # giant hubs (141 / 55 / 8 segments)
+    (300001, 1500000, 1, True, False),
+])
+def test_layer_fwd_tc_aggregate_then_transform(n, e, act_out, scaled, with_bias):
+    """mgcn_gcn_layer_fwd_tc against an fp64 dense / sparse restatement of gcn_model.py:89-106 +
+    gcn_base_models.py:199-243 with the stored format z = sigma (.) x: outputs (scaled by out_scale), mask words;
+    ragged tile counts, empty rows, isolated nodes, hub rows, several tiles per CTA."""
+    if e == -1:
+        ei = _giant_hub_graph(n)
+    else:
+        ei = rand_graph(n, e, seed=n) if e else torch.zeros(2, 0, dtype=torch.int64)
+    gen = torch.Generator().manual_seed(n + 11)
+    x = torch.randn(n, H, generator=gen)
+    w = torch.randn(H, H, generator=gen) / H ** 0.5
+    res_w = torch.randn(H, H, generator=gen) / H ** 0.5
+    res_b = torch.randn(H, generator=gen)
+    bias = torch.randn(H, generator=gen) if with_bias else None
+    sigma = torch.rand(n, generator=gen) + 0.1 if scaled else None
+    post = torch.rand(n, generator=gen) + 0.1
+    outs = torch.rand(n, generator=gen) + 0.1 if scaled else None
+    z = x * sigma.view(-1, 1) if scaled else x
+    gs = GraphStructure(ei.to(DEV), n, hub_threshold=64)
+    d = lambda t: None if t is None else t.to(DEV)
+    zn, hm = ops.gcn_layer_fwd_tc_impl(gs.fwd, d(z), d(w), d(res_w), d(res_b), d(bias), d(sigma), d(post), d(outs),
+                                       act_out)
+    D = lambda t: t.double()
+    agg = torch.zeros(n, H, dtype=torch.float64).index_add_(0, ei[1], D(z)[ei[0]])
+    s = D(post).view(-1, 1) * agg
+    pre_act = s @ D(w) + (D(bias) if with_bias else 0.0)
+    h = torch.relu(pre_act)
+    xin = D(z) / D(sigma).view(-1, 1) if scaled else D(z)
+    y = h + xin @ D(res_w).t() + D(res_b)
+    x_ref = torch.relu(y) if act_out else y
+    if scaled:
+        x_ref = x_ref * D(outs).view(-1, 1)
+    assert_parity(zn, x_ref, "z_next")
+    bits = hm.cpu().numpy().astype(np.uint32)
+    got = ((bits[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(bool)
+    hn = pre_act.numpy()
+    sure = np.abs(hn) > 1e-5 * max(1.0, np.abs(hn).max())
+    assert (got[sure] == (hn[sure] > 0)).all()
+    # run-to-run identical (fixed summation orders, no atomics on data)
+    zn2, hm2 = ops.gcn_layer_fwd_tc_impl(gs.fwd, d(z), d(w), d(res_w), d(res_b), d(bias), d(sigma), d(post), d(outs),
+                                         act_out)
+    assert_bitexact(zn, zn2, "run-to-run")
+    assert_bitexact(hm, hm2, "run-to-run mask")
+
+
+@pytest.mark.parametrize("n", [1000, 40000])
+def test_layer_bwd_tc_scaled_input(n):
+    """x_scale: the x operand of the tcgen05 backward is stored as sigma (.) x"""
+    gen = torch.Generator().manual_seed(n)
+    dxw, gy, x = (torch.randn(n, H, generator=gen) for _ in range(3))
+    w = torch.randn(H, H, generator=gen) / H ** 0.5
+    res_w = torch.randn(H, H, generator=gen) / H ** 0.5
+    post = torch.rand(n, generator=gen) + 0.1
+    sigma = torch.rand(n, generator=gen) + 0.1
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), generator=gen, dtype=torch.int64).to(torch.int32)
+    d = lambda t: t.to(DEV)
+    gyp, gsp, dw, drw, drb = ops.gcn_layer_bwd_impl(d(dxw), d(gy), d(x * sigma.view(-1, 1)), d(w), d(res_w), d(bits),
+                                                    d(post), True, True, x_scale=d(sigma))
+    D = lambda t: t.double()
+    assert_parity(dw, D(x).t() @ D(dxw), "dW")
+    assert_parity(drw, D(gy).t() @ D(x), "dR")
+    assert_parity(drb, D(gy).sum(0), "dr")
+    G = D(dxw) @ D(w).t() + D(gy) @ D(res_w)
+    assert_parity(gyp, G * (x > 0), "gy_prev")
