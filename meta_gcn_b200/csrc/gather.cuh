@@ -37,6 +37,19 @@ __device__ __forceinline__ Row8 ld_row8(const float* p) {
   return r;
 }
 
+// Experiment switch (default off): L2 prefetch of a row that a later round will gather — the lane that holds the
+// index of entry k asks for that row's line while the current round is in flight.  Measured at the botnet batch: no
+// gain (k_agg_flat 0.482 -> 0.485 ms, k_gcn_fwd_tc 0.677 -> 0.681 ms): the gather is not waiting on HBM misses, it runs
+// at the rate the L2 slices deliver sectors (~11 TB/s here against a ~12.4 TB/s full-chip cap).
+#ifndef MGCN_GATHER_PREFETCH
+#define MGCN_GATHER_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_row_l2(const float* p) {
+#if MGCN_GATHER_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 __device__ __forceinline__ void row8_add(Row8& acc, const Row8& b) {
   // four packed f32x2 adds (sm_100 FADD2): same IEEE result per element as eight scalar adds
 #pragma unroll
@@ -62,6 +75,7 @@ __device__ __forceinline__ Row8 gather_sum(const float* __restrict__ m, const in
     const int cnt = min(4, end - e);
     int gi_nn = 0;
     if (e + 8 + sub < end) gi_nn = ld_i32_hint(nbr_w + e + 8 + sub, pol);
+    if (e + 4 + sub < end) prefetch_row_l2(m + (int64_t)gi_n * kGH);   // next round's row of this lane
 #pragma unroll
     for (int t0 = 0; t0 < 4; t0 += U) {
       if (t0 < cnt) {

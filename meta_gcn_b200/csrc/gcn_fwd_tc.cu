@@ -21,14 +21,20 @@
 //              the tile's 16 tcgen05.mma (M = 128, K = 8) from one lane:  D1 = s W (main | corrections), D2 = z R^T
 //              (main | corrections), 3xTF32 with the correction terms in their own TMEM columns — no issuer warp
 //              (a 25th warp would cost every warp 8 registers: 7 warps on one scheduler).
+//              Tiles are filled in COMPLETION order: a finished pass takes the next free 8-row slot of the CTA (a
+//              shared counter), whatever its place in the work order — a tile of 64-entry rows or hub segments takes
+//              16 gather rounds, its neighbours one or two, and with tiles bound to the work order every warp ended
+//              up waiting for the slowest pass of the tile two stages back (ncu: a quarter of all instructions were
+//              barrier polls).  A row's result does not depend on which rows share its tile, so results stay fixed.
+//              The slot's row ids and per-row scalars travel to the epilogue through shared memory.
 //   epilogue   4 warps, thread per row: tcgen05.ld -> scalars, ReLUs, mask word -> a 144-byte staged row -> ONE
 //              128-byte cp.async.bulk store per row (the TMA engine, not the LSU, moves the outputs)
-//   barriers   done[tile & 3] tensor core -> producers + epilogue, tfree[stage] epilogue -> issuing warp.  FOUR done
-//              barriers for two stages: a parity wait cannot tell phase u from phase u + 2, and with 20 warps over 16
-//              passes a warp skips a tile now and then, so with one barrier per stage it could find the barrier two
-//              phases ahead of the one it waits for and never return (the first version of this kernel did).  With
-//              four, a waiter would have to be eight tiles behind for the same confusion, and it never skips two
-//              tiles in a row.
+//   barriers   full[stage] producers -> issuing warp (16 arrivals), done[tile % 2S] tensor core -> producers + epilogue,
+//              tfree[stage] epilogue -> issuing warp.  TWO done barriers per stage: a parity wait cannot tell phase u
+//              from phase u + 2, and with 20 warps over 16 passes a warp skips a tile now and then, so with one
+//              barrier per stage it could find the barrier two phases ahead of the one it waits for and never return
+//              (the first version of this kernel did).  With two, a waiter would have to be 4 S tiles behind for the
+//              same confusion, and it never skips two tiles in a row.
 // Hub rows (longer than the hub threshold) are finished by a second launch of the same kernel (mode 1): its tiles
 // walk the hub list, a whole warp sums a hub's segment partials (8 runs in parallel, fixed combine order).
 #include <mutex>
@@ -42,21 +48,29 @@ namespace mgcn {
 constexpr int kFtRows = 128;                     // rows per tile = M of the accumulators
 constexpr int kFtImg = kFtRows * 128;            // one operand image: 128 rows x 128 bytes
 constexpr int kFtStageB = 4 * kFtImg;            // S_hi, S_lo, Z_hi, Z_lo
-constexpr int kFtStages = 2;
+#ifndef MGCN_FT_STAGES
+#define MGCN_FT_STAGES 2
+#endif
+constexpr int kFtStages = MGCN_FT_STAGES;   // operand stages == accumulator buffers
 constexpr int kFtOffB1 = kFtStages * kFtStageB;  // B1(n, k) = W[k][n]: rows 0..31 hi, 32..63 lo; 64 rows x 128 bytes
 constexpr int kFtOffB2 = kFtOffB1 + 8192;        // B2(n, k) = R[n][k]
-constexpr int kFtLdo = 36;                       // floats per staged output row (144 bytes)
+constexpr int kFtLdo = kFtStages >= 3 ? 32 : 36;   // floats per staged output row: 144-byte rows are conflict-free; with
+                                                 // three operand stages only unpadded rows fit (8-way conflicts on the
+                                                 // epilogue's 8 stores per row — 3 % of the kernel's wavefronts)
 constexpr int kFtOffOut = kFtOffB2 + 8192;
 constexpr int kFtOffVec = kFtOffOut + kFtRows * kFtLdo * 4;   // res_b[32], bias[32]
-constexpr int kFtOffMisc = kFtOffVec + 256;                   // barriers, tmem slot
-constexpr int kFtSmem = kFtOffMisc + 128 + 1024;
+constexpr int kFtOffScal = kFtOffVec + 256;                   // [tile % 2S][128] {post, 1 / in_scale, out_scale, row id}
+constexpr int kFtOffMisc = kFtOffScal + 2 * kFtStages * kFtRows * 16;   // barriers, counters, tmem slot
+constexpr int kFtSmem = kFtOffMisc + 256 + 1024;
 constexpr int kFtEpiWarps = 4;
 #ifndef MGCN_FT_PROD
 #define MGCN_FT_PROD 20
 #endif
 constexpr int kFtProdWarps = MGCN_FT_PROD;
 constexpr int kFtThreads = 32 * (kFtEpiWarps + kFtProdWarps);
-constexpr int kFtTmemCols = 256;                 // 2 accumulator buffers x (D1 main | D1 corr | D2 main | D2 corr)
+constexpr int kFtTmemCols = kFtStages <= 2 ? 256 : 512;   // accumulator buffers x (D1 main | D1 corr | D2 main | D2 corr)
+static_assert(kFtStages >= 2 && kFtStages <= 4, "stages");
+static_assert(kFtSmem <= 232448, "shared memory");
 
 struct FwdTcArgs {
   const int4* tasks;
@@ -122,10 +136,13 @@ template <int kMode>   // 0: tiles of the work order (rows + hub segments), 1: t
 __global__ void __launch_bounds__(kFtThreads, 1) k_gcn_fwd_tc(const FwdTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bar_done = reinterpret_cast<uint64_t*>(smem + kFtOffMisc);      // [4]: tile tl of this CTA commits to tl & 3
-  uint64_t* bar_tfree = bar_done + 4;                                        // [2]
-  uint32_t* arrivals = reinterpret_cast<uint32_t*>(smem + kFtOffMisc + 48);   // [stage] passes finished, never reset
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kFtOffMisc + 64);
+  uint64_t* bar_done = reinterpret_cast<uint64_t*>(smem + kFtOffMisc);      // [2 S]: tile tl of this CTA commits to tl % 2S
+  uint64_t* bar_tfree = bar_done + 2 * kFtStages;                            // [S]
+  uint64_t* bar_full = bar_tfree + kFtStages;                                // [2 S] 16 pass arrivals per tile
+  uint32_t* arrivals = reinterpret_cast<uint32_t*>(bar_full + 2 * kFtStages);   // [S] passes stored, never reset
+  uint32_t* next_slot = arrivals + kFtStages;                                // passes finished by this CTA so far
+  uint32_t* tmem_slot = next_slot + 1;
+  float4* scal = reinterpret_cast<float4*>(smem + kFtOffScal);
   float* vec = reinterpret_cast<float*>(smem + kFtOffVec);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -152,9 +169,12 @@ __global__ void __launch_bounds__(kFtThreads, 1) k_gcn_fwd_tc(const FwdTcArgs a)
 #pragma unroll
     for (int s = 0; s < kFtStages; ++s) {
       arrivals[s] = 0;
+      if (s == 0) *next_slot = 0;
       mbar_init(bar_done + s, 1);
-      mbar_init(bar_done + 2 + s, 1);
+      mbar_init(bar_done + kFtStages + s, 1);
       mbar_init(bar_tfree + s, kFtEpiWarps);
+      mbar_init(bar_full + s, 16);
+      mbar_init(bar_full + kFtStages + s, 16);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -208,36 +228,61 @@ __global__ void __launch_bounds__(kFtThreads, 1) k_gcn_fwd_tc(const FwdTcArgs a)
       }
       return d;
     };
-    int4 dn = load_desc(pw);
-    for (int64_t g = pw;; g += kFtProdWarps) {
-      const int64_t tl = g >> 4;
-      if (blockIdx.x + tl * (int64_t)gridDim.x >= n_tiles) break;
-      const int pass = (int)(g & 15), stage = (int)(tl & 1), use = (int)(tl >> 1);
-      const int4 d = dn;
-      dn = load_desc(g + kFtProdWarps);
+    // software pipeline over this warp's passes: descriptors two passes ahead, the first two index batches one pass
+    // ahead, so that a pass starts gathering at once (ncu: 21 % of the producers' stall samples sat on these loads)
+    struct PassIdx {
+      int beg, end, gi, gin;
+    };
+    auto load_idx = [&](const int4& d) {
+      PassIdx p{0, 0, 0, 0};
+      if (kMode == 0) {
+        p.beg = __shfl_sync(0xffffffffu, d.y, grp);
+        p.end = __shfl_sync(0xffffffffu, d.z, grp);
+        if (p.beg + sub < p.end) p.gi = ld_i32_hint(a.nbr_w + p.beg + sub, pol);
+        if (p.beg + 4 + sub < p.end) p.gin = ld_i32_hint(a.nbr_w + p.beg + 4 + sub, pol);
+      }
+      return p;
+    };
+    int4 d = load_desc(pw);
+    int4 dn = load_desc(pw + kFtProdWarps);
+    PassIdx pi = load_idx(d);
+    // this CTA's tiles of the work order: blockIdx.x, + gridDim.x, ...; its passes fill ceil(passes / 16) tiles
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    for (int64_t g = pw; g < my_tiles * 16; g += kFtProdWarps) {
       const int rowp = __shfl_sync(0xffffffffu, d.x, grp);
       const int slot = __shfl_sync(0xffffffffu, d.w, grp);
-      const bool finish = rowp >= 0 && slot == 0;   // this group completes a row of the tile
-      Row8 zrow, acc;
+      const bool finish = rowp >= 0 && slot == 0;   // this group completes a row
+      // the row's own z (unconditional address: the value is only looked at when the row is stored, so the load
+      // stays in flight during the gather) and its scalars, one per lane of the group
+      const Row8 zrow = ld_row8(a.z + (int64_t)(finish ? rowp : 0) * kGH + col);
+      float sc = 1.f;
+      {
+        const float* sp = sub == 0 ? a.post : sub == 1 ? a.in_scale : sub == 2 ? a.out_scale : nullptr;
+        if (finish && sp) sc = __ldg(sp + rowp);   // one load per lane, looked at only when the row is stored
+      }
+      const PassIdx pc = pi;
+      const int4 dc = d;
+      d = dn;
+      pi = load_idx(d);                               // next pass: index batches in flight during this gather
+      dn = load_desc(g + 2 * kFtProdWarps);
+      Row8 acc;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) zrow.v[q] = acc.v[q] = 0.f;
-      if (finish) zrow = ld_row8(a.z + (int64_t)rowp * kGH + col);
+      for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
       if (kMode == 0) {
-        const int beg = __shfl_sync(0xffffffffu, d.y, grp), end = __shfl_sync(0xffffffffu, d.z, grp);
         if (rowp >= 0) {
-          const int gi = (beg + sub < end) ? ld_i32_hint(a.nbr_w + beg + sub, pol) : 0;
-          const int gin = (beg + 4 + sub < end) ? ld_i32_hint(a.nbr_w + beg + 4 + sub, pol) : 0;
-          acc = gather_sum(a.z, a.nbr_w, beg, end, gi, gin, sub, grp_lane0, gmask, col, pol);
+          acc = gather_sum(a.z, a.nbr_w, pc.beg, pc.end, pc.gi, pc.gin, sub, grp_lane0, gmask, col, pol);
           if (slot != 0) store_partial(a.partial, slot, col, acc);
         }
+        // first round of the NEXT pass: its index batch was fetched before this gather and has arrived by now
+        if (pi.beg + sub < pi.end) prefetch_row_l2(a.z + (int64_t)pi.gi * kGH);
       } else {
         // the whole warp sums one hub row at a time: 8 contiguous runs of its segment partials in parallel, the run
         // sums added left to right (a fixed order)
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
-          const int rowi = __shfl_sync(0xffffffffu, d.x, i);
+          const int rowi = __shfl_sync(0xffffffffu, dc.x, i);
           if (rowi < 0) continue;
-          const int s0 = __shfl_sync(0xffffffffu, d.y, i), ns = __shfl_sync(0xffffffffu, d.z, i);
+          const int s0 = __shfl_sync(0xffffffffu, dc.y, i), ns = __shfl_sync(0xffffffffu, dc.z, i);
           const int per = (ns + 7) >> 3;
           const Row8 run = hub_run_sum(a.partial, s0, grp * per, min(ns, grp * per + per), col);
           Row8 tot;
@@ -253,23 +298,45 @@ __global__ void __launch_bounds__(kFtThreads, 1) k_gcn_fwd_tc(const FwdTcArgs a)
           if (grp == i) acc = tot;
         }
       }
-      // the tensor core has consumed this stage's previous tile (tile tl - 2 of this CTA)
-      if (tl >= 2) mbar_wait(bar_done + ((tl - 2) & 3), (uint32_t)((tl - 2) >> 2) & 1u);
-      if (finish) {
-        unsigned char* st = smem + stage * kFtStageB;
-        const int r = pass * 8 + grp;
-        ft_store_row(st, st + kFtImg, r, sub, acc);
-        ft_store_row(st + 2 * kFtImg, st + 3 * kFtImg, r, sub, zrow);
+      // next free 8-row slot of this CTA: tile tl (in completion order), rows 8 ps .. 8 ps + 7
+      uint32_t my = 0;
+      if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(my) : "r"(smem_u32(next_slot)) : "memory");
+      my = __shfl_sync(0xffffffffu, my, 0);
+      const int64_t tl = my >> 4;
+      const int ps = (int)(my & 15u), stage = (int)(tl % kFtStages);
+      // the tensor core has consumed this stage's previous tile (tile tl - S of this CTA)
+      if (tl >= kFtStages) {
+        const int64_t tp = tl - kFtStages;
+        mbar_wait(bar_done + (int)(tp % (2 * kFtStages)), (uint32_t)(tp / (2 * kFtStages)) & 1u);
+      }
+      {
+        const int r = ps * 8 + grp;
+        if (finish) {
+          unsigned char* st = smem + stage * kFtStageB;
+          ft_store_row(st, st + kFtImg, r, sub, acc);
+          ft_store_row(st + 2 * kFtImg, st + 3 * kFtImg, r, sub, zrow);
+        }
+        if (sub == 1) sc = __frcp_rn(sc);
+        if (sub == 3) sc = __int_as_float(finish ? rowp : -1);
+        // slot tl % 2S of the scalar ring: its previous tile tl - 2S was drained by the epilogue before MMA(tl - S)
+        // was issued (tfree), and done(tl - S) has just been observed
+        reinterpret_cast<float*>(scal + (int)(tl % (2 * kFtStages)) * kFtRows + r)[sub] = sc;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's image stores -> async proxy
       __syncwarp();
+      // arrival: release on the stage's mbarrier; a relaxed counter only elects the warp that issues the tile's MMAs,
+      // which then acquires through the mbarrier (16 arrivals) — no acq_rel atomic, no MEMBAR per pass
       uint32_t old = 0;
-      if (lane == 0)
-        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(arrivals + stage)) : "memory");
+      if (lane == 0) {
+        mbar_arrive(bar_full + (int)(tl % (2 * kFtStages)));
+        asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(arrivals + stage)) : "memory");
+      }
       old = __shfl_sync(0xffffffffu, old, 0);
       if ((old & 15u) == 15u) {
-        // 16th pass of the tile: every image row is in place; the accumulator buffer was drained two tiles ago
-        if (use >= 1) mbar_wait(bar_tfree + stage, (use - 1) & 1);
+        // 16th pass of the tile: wait for the other passes' arrivals (acquire), then the accumulator buffer
+        const uint32_t use = (uint32_t)(tl / kFtStages);
+        mbar_wait(bar_full + (int)(tl % (2 * kFtStages)), (uint32_t)(tl / (2 * kFtStages)) & 1u);
+        if (use >= 1) mbar_wait(bar_tfree + stage, (use - 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t tb = tmem + stage * 128;
@@ -283,7 +350,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) k_gcn_fwd_tc(const FwdTcArgs a)
             umma_tf32(tb + 64, dsc + (so + (2 * kFtImg >> 4) + ko), b2, id64, k > 0);     // z_hi [R_hi | R_lo]
             umma_tf32(tb + 96, dsc + (so + (3 * kFtImg >> 4) + ko), b2, id32, 1);         // z_lo R_hi
           }
-          umma_commit(bar_done + (tl & 3));
+          umma_commit(bar_done + (int)(tl % (2 * kFtStages)));
         }
         __syncwarp();
       }
@@ -292,34 +359,18 @@ __global__ void __launch_bounds__(kFtThreads, 1) k_gcn_fwd_tc(const FwdTcArgs a)
     // ------------------------------- epilogue: thread per row -------------------------------
     const int r = 32 * warp + lane;
     float* stg = reinterpret_cast<float*>(smem + kFtOffOut) + r * kFtLdo;
-    auto load_row = [&](int64_t tile) {
-      int row = -1;
-      const int64_t e = tile * kFtRows + r;
-      if (tile < n_tiles && e < limit) {
-        if (kMode == 0) {
-          const int4 d = ld_i4_hint(a.tasks + e, pol);
-          row = (d.x >= 0 && d.w == 0) ? d.x : -1;
-        } else {
-          row = __ldg(a.hub_rows + e);
-        }
-      }
-      return row;
-    };
-    int row_n = load_row(blockIdx.x);
     int tl = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      const int stage = tl & 1, use = tl >> 1;
-      const int row = row_n;
-      row_n = load_row(tile + gridDim.x);
-      float postv = 1.f, inv = 1.f, outs = 1.f;
-      if (row >= 0) {
-        if (a.post) postv = __ldg(a.post + row);
-        if (a.in_scale) inv = __frcp_rn(__ldg(a.in_scale + row));
-        if (a.out_scale) outs = __ldg(a.out_scale + row);
-      }
-      mbar_wait(bar_done + (tl & 3), (uint32_t)(tl >> 2) & 1u);
+      const int stage = tl % kFtStages;
+      mbar_wait(bar_done + tl % (2 * kFtStages), (uint32_t)(tl / (2 * kFtStages)) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staged row of the previous tile has been read
+      // acquire the producers' scalar / row-id stores (two full barriers per stage, like done: this wait may come
+      // after the stage's NEXT tile has filled)
+      mbar_wait(bar_full + tl % (2 * kFtStages), (uint32_t)(tl / (2 * kFtStages)) & 1u);
+      const float4 sc4 = scal[(tl % (2 * kFtStages)) * kFtRows + r];
+      const float postv = sc4.x, inv = sc4.y, outs = sc4.z;
+      const int row = __float_as_int(sc4.w);
       const uint32_t ta = tmem + stage * 128 + ((uint32_t)(32 * warp) << 16);
       uint32_t bits = 0;
 #pragma unroll
