@@ -28,9 +28,13 @@ if ROOT not in sys.path:
 
 LAYERS = 12
 HIDDEN = 32
-# dram__bytes_read.sum + dram__bytes_write.sum of k_layer_fwd per launch at the default workload, from
-# the ncu --set full capture summarised in profiles/ (None until captured for the current kernel)
-TRAFFIC_FWD_BYTES = 2_103_522_000   # profiles/r1b_ncu_k_layer_fwd.csv: 1.2161 GB read + 0.8874 GB written
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the ncu --set full captures
+# summarised under profiles/ (None until captured for the current kernel)
+TRAFFIC = {
+    "fwd": 1_238_066_944,    # profiles/r2_ncu_k_gcn_fwd_tc.csv: k_gcn_fwd_tc<0> 770.9 MB read + 448.1 MB written, <1> 19.0 MB
+    "agg": 1_208_880_128,    # profiles/r1b_ncu_k_agg_flat.csv: 767.7 MB read + 441.1 MB written
+    "bwd": 2_262_567_000,    # profiles/r1b_ncu_k_layer_bwd_tc.csv: 1402.5 MB read + 860.0 MB written
+}
 CFG = dict(in_channels=1, enc_sizes=[HIDDEN] * LAYERS, num_classes=2, non_linear="relu",
            non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj",
            pred_on="node", nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="add", bias=False)
@@ -46,6 +50,9 @@ def parse():
     ap.add_argument("--nodes", type=int, default=143107)
     ap.add_argument("--edges", type=int, default=1_500_000)
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configs[k]; 1 (default) is the contract line, the others print one JSON line "
+                         "with their own results and cpu_baseline (scripts/bench_configs.py)")
     ap.add_argument("--e2e-steps", type=int, default=12)   # the first copy of a loop cannot be overlapped
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -137,16 +144,20 @@ def cpu_step_time(graph, steps, warmup):
     y = torch.from_numpy(graph["y"]).long()
     crit = torch.nn.CrossEntropyLoss()
     times = []
+    state0 = {k: v.clone() for k, v in model.state_dict().items()}
+    loss0 = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
         out = model(x[:, 0].view(-1, 1), ei, x[:, 1])      # train_botnet.py:286
         loss = crit(out, y)
+        if loss0 is None:
+            loss0 = float(loss.detach())
         loss.backward()
         opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times, float(loss)
+    return times, float(loss.detach()), loss0, state0
 
 
 def run_reference(args):
@@ -160,7 +171,7 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count() or 1)
     g = make_graphs([0], args.nodes, args.edges)[0]
     e = g["edge_index"].shape[1]
-    times, loss = cpu_step_time(g, args.steps, args.warmup)
+    times, loss, _, _ = cpu_step_time(g, args.steps, args.warmup)
     t = sum(times) / len(times)
     gedges = e * LAYERS * 2 / t / 1e9
     sample = (f"1 of the {args.graphs} graphs of a batch per step (N={g['x'].shape[0]}, E={e}), "
@@ -354,11 +365,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         return k0.elapsed_time(k1) / reps
 
-    fwd_ms = time_kernel(lambda: ops.gcn_layer_fwd_impl(gs.fwd, feat, xin, None, w_a, r_b, w_b, None, dis, dis, 1))
-    agg_ms = time_kernel(lambda: ops.aggregate_prescaled_impl(gs.bwd, feat, dis, 0, None, None, 0))
+    # the three per-layer launches of the hidden-32 stack (meta_gcn_b200/fused.py), each alone over this rank's batch
+    fwd_ms = time_kernel(lambda: ops.gcn_layer_fwd_tc_impl(gs.fwd, xin, w_a, w_b, r_b, None, dis, dis, dis, 1))
+    agg_ms = time_kernel(lambda: ops.aggregate_prescaled_impl(gs.bwd_plain, feat, dis, 0, None, None, 0))
     hbits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n_nodes,), device=dev, dtype=torch.int64).to(torch.int32)
     gyv = torch.randn(n_nodes, HIDDEN, device=dev)
-    bwd_ms = time_kernel(lambda: ops.gcn_layer_bwd_impl(feat, gyv, xin, w_a, w_b, hbits, dis, True, True))
+    bwd_ms = time_kernel(lambda: ops.gcn_layer_bwd_impl(feat, gyv, xin, w_a, w_b, hbits, dis, True, True, x_scale=dis))
     del feat, xin, gyv, hbits
 
     # ---- end to end from pinned host buffers through the public API ----
@@ -411,10 +423,30 @@ def run_ours(args):
     t = ms / 1e3
     gedges = edges_global * LAYERS * 2 / t / 1e9
     agg_bytes = b_agg(n_nodes, n_edges, HIDDEN)
-    # forward layer: index stream + descriptors/scales + gathered m + x read + x', m' written
-    fwd_bytes = 4 * n_edges + 24 * n_nodes + 4 * 4 * n_nodes * HIDDEN
-    fwd_gbs = fwd_bytes / (fwd_ms / 1e3) / 1e9
+    nh4 = 4 * n_nodes * HIDDEN
     step_bytes = b_step(n_nodes, n_edges, HIDDEN, LAYERS)
+
+    def kernel_entry(name, alg_bytes, own_bytes, ms_, traffic):
+        """achieved = ALGORITHMIC bytes / time; kernel_bytes = the bytes this design's kernel has to move
+        (its own operand arrays, each once); traffic = DRAM bytes ncu measured"""
+        gbs = alg_bytes / (ms_ / 1e3) / 1e9
+        return {"kernel": name, "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": ms_,
+                "achieved": gbs, "frac": gbs / peak_bw, "kernel_bytes": int(own_bytes),
+                "traffic": traffic, "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None}
+
+    k_fwd = kernel_entry("k_gcn_fwd_tc<0> + <1>: forward layer, aggregate-then-transform — row-owned gather of the "
+                         "stored activations, both dense products on tcgen05 (TMEM accumulators), ReLUs / residual / "
+                         "mask word in the epilogue, bulk row stores; one [N,32] array read, one written",
+                         agg_bytes, agg_bytes + 28 * n_nodes, fwd_ms, TRAFFIC["fwd"])
+    k_fwd["gather_l2_to_sm_gbs"] = n_edges * HIDDEN * 4 / (fwd_ms / 1e3) / 1e9
+    k_agg = kernel_entry("k_agg_flat (+k_hub_reduce, k_agg_flat_hubs): transposed aggregation of the backward",
+                         agg_bytes, agg_bytes + 16 * n_nodes, agg_ms, TRAFFIC["agg"])
+    k_agg["gather_l2_to_sm_gbs"] = n_edges * HIDDEN * 4 / (agg_ms / 1e3) / 1e9
+    k_bwd = kernel_entry("k_layer_bwd_tc: row-local backward (4 products, both ReLU masks) on tcgen05.mma / TMEM, "
+                         "warp-specialised; §8d charges a layer's backward B_agg + 4NH in total, of which this launch "
+                         "owns the 4NH re-read of the saved layer input",
+                         nh4, 5 * nh4 + 8 * n_nodes, bwd_ms, TRAFFIC["bwd"])
+    per_layer_ms = fwd_ms + agg_ms + bwd_ms
     line = {
         "metric": "GCN fwd+bwd GEdges/s", "value": gedges, "unit": "GEdges/s",
         "graphs_per_s": args.graphs * world / t,
@@ -426,27 +458,18 @@ def run_ours(args):
                            "runs": strong},
         "clocks": clocks,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm",
-                     "kernel": "k_layer_fwd (+k_layer_fwd_hubs): fused forward layer = row-owned aggregation "
-                               "of pre-scaled messages + residual transform + next layer's messages",
-                     "achieved": fwd_gbs, "peak": peak_bw, "unit": "GB/s", "frac": fwd_gbs / peak_bw,
-                     "traffic": TRAFFIC_FWD_BYTES, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": fwd_bytes, "ms_per_launch": fwd_ms,
-                     "gather_l2_to_sm_gbs": n_edges * HIDDEN * 4 / (fwd_ms / 1e3) / 1e9,
-                     "second_kernel": {"kernel": "k_agg_flat (+hubs): transposed aggregation of the backward",
-                                       "algorithmic_bytes_per_launch": agg_bytes, "ms_per_launch": agg_ms,
-                                       "achieved": agg_bytes / (agg_ms / 1e3) / 1e9,
-                                       "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / peak_bw,
-                                       "gather_l2_to_sm_gbs": n_edges * HIDDEN * 4 / (agg_ms / 1e3) / 1e9},
-                     "third_kernel": {"kernel": "k_layer_bwd_tc: row-local backward (4 products, both ReLU masks) on "
-                                                "tcgen05.mma / TMEM, warp-specialised",
-                                      "algorithmic_bytes_per_launch": 5 * 4 * n_nodes * HIDDEN + 8 * n_nodes,
-                                      "ms_per_launch": bwd_ms,
-                                      "achieved": (5 * 4 * n_nodes * HIDDEN + 8 * n_nodes) / (bwd_ms / 1e3) / 1e9,
-                                      "frac": (5 * 4 * n_nodes * HIDDEN + 8 * n_nodes) / (bwd_ms / 1e3) / 1e9 / peak_bw},
-                     "step_algorithmic_bytes": step_bytes,
-                     "step_frac": step_bytes / t / 1e9 / peak_bw,
-                     "step_frac_of_nominal_8TBs": step_bytes / t / 1e9 / 8000.0},
+        # dominant kernel = largest share of the step (the forward layer launch: 11 of them per step)
+        "roofline": dict({"bound": "hbm", "peak": peak_bw, "unit": "GB/s", "peak_source": peak_src}, **k_fwd,
+                         second_kernel=k_agg, third_kernel=k_bwd,
+                         layer={"what": "one hidden layer forward + backward = the three launches above",
+                                "ms": per_layer_ms,
+                                "algorithmic_bytes": int(2 * agg_bytes + nh4),
+                                "frac": (2 * agg_bytes + nh4) / (per_layer_ms / 1e3) / 1e9 / peak_bw,
+                                "traffic": sum(TRAFFIC.values()),
+                                "traffic_over_algorithmic": sum(TRAFFIC.values()) / (2 * agg_bytes + nh4)},
+                         step_algorithmic_bytes=int(step_bytes),
+                         step_frac=step_bytes / t / 1e9 / peak_bw,
+                         step_frac_of_nominal_8TBs=step_bytes / t / 1e9 / 8000.0),
     }
     if e2e_ms is not None:
         h2d = host.x.numel() * 4 + host.edge_index.numel() * 8 + host.y.numel() * host.y.element_size()
@@ -455,8 +478,20 @@ def run_ours(args):
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        times, _ = cpu_step_time(graphs[0], args.cpu_steps, 1)
+        times, _, cpu_loss0, state0 = cpu_step_time(graphs[0], args.cpu_steps, 1)
         tc = min(times)
+        # same graph, same initial weights: the CUDA path's loss must equal the CPU arm's first loss
+        chk = GCNModel(**CFG)
+        chk.load_state_dict(state0)
+        chk.to(dev)
+        one = GraphBatch.from_data_list([graphs[0]]).to(dev)
+        with torch.no_grad():
+            o_ = chk(one.x[:, 0].contiguous().view(-1, 1), one.edge_index, deg_K=one.x[:, 1].contiguous())
+            gpu_loss0 = float(F_mgcn.cross_entropy(o_, one.y.long(), "mean").item())
+        if abs(gpu_loss0 - cpu_loss0) > 1e-5 * max(1.0, abs(cpu_loss0)):
+            raise RuntimeError(f"loss mismatch between the CUDA path ({gpu_loss0}) and the CPU arm ({cpu_loss0})")
+        line["loss_check"] = {"graph": 0, "gpu": gpu_loss0, "cpu": cpu_loss0, "abs_diff": abs(gpu_loss0 - cpu_loss0),
+                              "tolerance": "1e-5 relative (asserted)"}
         e1g = graphs[0]["edge_index"].shape[1]
         line["cpu_baseline"] = {
             "value": e1g * LAYERS * 2 / tc / 1e9, "unit": "GEdges/s", "graphs_per_s": 1.0 / tc,
@@ -466,6 +501,18 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.barrier()
+
+
+def run_secondary(args):
+    """--config 0 / 2 / 3 / 4: the other BASELINE.json configurations, one GPU, with the reference's CPU path beside
+    each (bounded samples; see scripts/bench_configs.py)"""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import bench_configs
+    rows = bench_configs.CONFIGS[args.config](not args.no_cpu_baseline)
+    emit({"metric": "see results", "config": {"workload": f"BASELINE.json configs[{args.config}]"}, "n_gpus": 1,
+          "data": "synthetic", "dtype": "f32", "results": rows})
 
 
 _JSON_OUT = None
@@ -483,7 +530,9 @@ def main():
     sys.stdout.flush()
     _JSON_OUT = os.dup(1)
     os.dup2(2, 1)
-    if args.impl == "reference":
+    if args.config != 1:
+        run_secondary(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -200,23 +200,19 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
 #pragma unroll
       for (int t = 0; t < 4; ++t) acc_dr[i][t] = 0.f;
     F8 cur[3], nxt[3];
-    auto load_tile = [&](F8 (&dst)[3], int64_t tile) {
+    float xs_cur = 1.f, xs_nxt = 1.f;   // 1 / x_scale of this thread's row, fetched with the tile, applied at use
+    auto load_tile = [&](F8 (&dst)[3], float& xs_out, int64_t tile) {
       const float* src[3] = {a.dxw, a.gy, a.x};
       const int64_t gr = tile * kTRows + r0;
       const bool ok = tile < n_tiles && gr < a.n_rows;
-      float xs = 1.f;
-      if (ok && a.x_scale) xs = __frcp_rn(__ldg(a.x_scale + gr));
+      xs_out = 1.f;
+      if (ok && a.x_scale) xs_out = __ldg(a.x_scale + gr);
 #pragma unroll
       for (int arr = 0; arr < 3; ++arr) {
         F8 v;
         v.lo = v.hi = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) v = ld_f8_hint(src[arr] + gr * kTH + 8 * qq, pol);
         dst[arr] = v;
-      }
-      if (a.x_scale) {
-        F8& v = dst[2];
-        v.lo.x *= xs; v.lo.y *= xs; v.lo.z *= xs; v.lo.w *= xs;
-        v.hi.x *= xs; v.hi.y *= xs; v.hi.z *= xs; v.hi.w *= xs;
       }
     };
     unsigned char* st = smem + pset * kStageB;
@@ -225,9 +221,9 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
     const uint64_t dK = umma_desc(smem_u32(smem), 128, 1024, 0), dM = umma_desc(smem_u32(smem), kTileB, 512, 1);
     int it = pset;
     int64_t tile = blockIdx.x + (int64_t)pset * gridDim.x;
-    load_tile(cur, tile);
+    load_tile(cur, xs_cur, tile);
     for (; tile < n_tiles; tile += 2 * (int64_t)gridDim.x, it += 2) {
-      load_tile(nxt, tile + 2 * (int64_t)gridDim.x);
+      load_tile(nxt, xs_nxt, tile + 2 * (int64_t)gridDim.x);
       const int use = it >> 1;
       // the tensor core has consumed this stage's previous tile (done barriers: [pair buffer][set])
       if (use >= 1) mbar_wait(bar_done + 2 * ((use - 1) & 1) + pset, ((use - 1) >> 1) & 1);
@@ -264,6 +260,12 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       *reinterpret_cast<float4*>(st + kOffMN + 1 * kTileB + mo_b) = hi;
       *reinterpret_cast<float4*>(st + kOffMN + 3 * kTileB + mo_b) = lo;
       // x
+      if (a.x_scale) {
+        const float xs = __frcp_rn(xs_cur);
+        F8& v = cur[2];
+        v.lo.x *= xs; v.lo.y *= xs; v.lo.z *= xs; v.lo.w *= xs;
+        v.hi.x *= xs; v.hi.y *= xs; v.hi.z *= xs; v.hi.w *= xs;
+      }
       uint32_t b;
       {
         const float4 x0 = cur[2].lo, x1 = cur[2].hi;
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
       }
 #pragma unroll
       for (int arr = 0; arr < 3; ++arr) cur[arr] = nxt[arr];
+      xs_cur = xs_nxt;
     }
     // dr[c]: this thread holds columns 8 qq + 4 i + t summed over its rows; rows of the warp are added in a fixed
     // butterfly order, the 16 warps by one thread per column below

@@ -231,13 +231,13 @@ class _ResidualGCNStack32AT(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
-def residual_gcn_stack(x, graph, pre, post, layer_params, has_bias, last_relu=False):
+def residual_gcn_stack(x, graph, pre, post, layer_params, has_bias, last_relu=False, aggregate_first=True):
     """layer_params: per layer (weight_node [Hin,H], [bias [H]], residual.weight [H,Hin],
     residual.bias [H]).  pre/post: per-source / per-target degree factors (either may be None)."""
     flat = [p for lp in layer_params for p in lp]
     widths = {lp[0].size(1) for lp in layer_params} | {lp[0].size(0) for lp in layer_params[1:]}
     if not has_bias and widths == {32}:
-        if FORWARD_AGGREGATE_FIRST and not x.requires_grad and (x.size(1) <= 4 or x.size(1) == 32):
+        if FORWARD_AGGREGATE_FIRST and aggregate_first and not x.requires_grad and (x.size(1) <= 4 or x.size(1) == 32):
             return _ResidualGCNStack32AT.apply(x, graph, pre, post, last_relu, *flat)
         return _ResidualGCNStack32.apply(x, graph, pre, post, last_relu, *flat)
     return _ResidualGCNStack.apply(x, graph, pre, post, has_bias, last_relu, *flat)

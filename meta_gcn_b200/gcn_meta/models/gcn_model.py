@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from ... import functional as F_mgcn
 from ... import fused
-from ...graph import structure_of
+from ...graph import all_positive, structure_of
 from .common import activation
 from .gcn_base_models import NodeModelBase
 from .gcn_multi_kernel import GCNMultiKernel
@@ -95,6 +95,12 @@ class GCNModel(nn.Module):
         nm = self.gcn_net[0].gcn.node_models[0]
         if nm.deg_norm is None:
             return None
+        # one vector serves every layer only if every node model normalises the same way (final_layer_config may
+        # override deg_norm for the last layer: the reference recomputes norm per layer with that layer's own method,
+        # gcn_base_models.py:215); otherwise each layer derives its own factors
+        for layer in self.gcn_net:
+            if any(getattr(m, "deg_norm", None) != nm.deg_norm for m in layer.gcn.node_models):
+                return None
         deg = deg_K if isinstance(deg_K, torch.Tensor) or deg_K is None else deg_K[0]
         ew = edge_weight_K if isinstance(edge_weight_K, torch.Tensor) or edge_weight_K is None \
             else edge_weight_K[0]
@@ -123,9 +129,14 @@ class GCNModel(nn.Module):
         return all(type(m[0]).__name__ == "NodeModelAdditive" and m[0].aggr == "add" and m[0].edge_gate is None and m[0].deg_norm == first.deg_norm and m[0].in_edgedim is None
                    and (m[0].bias is None) == (first.bias is None) for m in nms)
 
-    def _forward_stack(self, x, edge_index, dis):
+    def _forward_stack(self, x, edge_index, dis, deg=None):
         nm0 = self.gcn_net[0].gcn.node_models[0]
         graph = structure_of(edge_index, x.size(0))
+        # the aggregate-then-transform kernels need a non-zero degree factor on every gathered row: true by construction
+        # for the graph's own out-degree (a source has an out-edge), checked once per tensor for a caller's deg_K
+        aggregate_first = True
+        if deg is not None and dis is not None:
+            aggregate_first = all_positive(deg) is True
         pre = dis
         post = dis if nm0.deg_norm == "sm" else None
         has_bias = nm0.bias is not None
@@ -134,13 +145,14 @@ class GCNModel(nn.Module):
             nm = layer.gcn.node_models[0]
             params.append((nm.weight_node, nm.bias, lin.weight, lin.bias) if has_bias
                           else (nm.weight_node, lin.weight, lin.bias))
-        return fused.residual_gcn_stack(x, graph, pre, post, params, has_bias)
+        return fused.residual_gcn_stack(x, graph, pre, post, params, has_bias, aggregate_first=aggregate_first)
 
     def forward(self, x, edge_index_K, edge_attr_K=None, deg_K=None, edge_weight_K=None, **kwargs):
         dis = self._shared_degree_factors(x, edge_index_K, deg_K, edge_weight_K)
         if self._stack_eligible(edge_index_K, edge_attr_K, edge_weight_K) and not kwargs.get("_no_stack"):
             ei = edge_index_K if isinstance(edge_index_K, torch.Tensor) else edge_index_K[0]
-            x = self._forward_stack(x, ei, dis)
+            deg = deg_K if isinstance(deg_K, torch.Tensor) or deg_K is None else deg_K[0]
+            x = self._forward_stack(x, ei, dis, deg)
             return self._head(x, kwargs)
         kwargs.pop("_no_stack", None)
         hop = self.residual_hop

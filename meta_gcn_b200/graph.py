@@ -100,21 +100,38 @@ class GraphStructure:
             raise IndexError("edge_index contains node ids outside [0, num_nodes)")
 
 
-class _StructureCache:
-    """Keeps the structures of the last few edge_index tensors (keyed on storage identity and
-    version counter), so that the L layers of a model and its backward build them once."""
+def _version_of(t):
+    """in-place modification counter; tensors created under torch.inference_mode() have none"""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
 
-    def __init__(self, capacity=8):
+
+class _StructureCache:
+    """Keeps the structures of the last few edge_index tensors (keyed on storage identity and version counter), so
+    that the L layers of a model and its backward build them once.  Each entry pins its edge_index and ~30 bytes of
+    int32 structure per edge on the device, so the cache stays small: an entry is dropped as soon as the SAME
+    storage shows up with a new version (a loader slot that was refilled), and at most `capacity` distinct storages
+    are kept (the current batch and the one a prefetching loader is filling).  Tensors without a version counter
+    (inference mode) are not cached."""
+
+    def __init__(self, capacity=3):
         self.capacity = capacity
         self._items = OrderedDict()
 
     def get(self, edge_index, num_nodes, loop_mode, hub_threshold=ops.DEFAULT_HUB_THRESHOLD):
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version,
-               int(num_nodes), int(loop_mode), int(hub_threshold), edge_index.device.index)
+        version = _version_of(edge_index)
+        if version is None:
+            return GraphStructure(edge_index, num_nodes, loop_mode, hub_threshold)
+        ident = (edge_index.data_ptr(), edge_index.device.index)
+        key = (ident, tuple(edge_index.shape), version, int(num_nodes), int(loop_mode), int(hub_threshold))
         hit = self._items.get(key)
         if hit is not None:
             self._items.move_to_end(key)
             return hit
+        for stale in [k for k in self._items if k[0] == ident and (k[1] != key[1] or k[2] != version)]:
+            del self._items[stale]          # the storage was rewritten: its old structures are dead
         gs = GraphStructure(edge_index, num_nodes, loop_mode, hub_threshold)
         self._items[key] = gs  # holds edge_index alive, so the data_ptr cannot be recycled
         while len(self._items) > self.capacity:
@@ -139,7 +156,10 @@ _INDEX_CACHE = OrderedDict()
 def structure_of_index(index, dim_size, hub_threshold=ops.DEFAULT_HUB_THRESHOLD):
     """Structure for the primitive seam scatter_(name, src, index): rows = values of ``index``,
     perm = positions in ``index`` (a stable sort).  Cached on the identity of ``index``."""
-    key = (index.data_ptr(), index.numel(), index._version, int(dim_size), int(hub_threshold),
+    version = _version_of(index)
+    if version is None:
+        return GraphStructure(torch.stack([index, index]), dim_size, LOOPS_KEEP, hub_threshold)
+    key = (index.data_ptr(), index.numel(), version, int(dim_size), int(hub_threshold),
            index.device.index)
     hit = _INDEX_CACHE.get(key)
     if hit is not None:
@@ -147,7 +167,7 @@ def structure_of_index(index, dim_size, hub_threshold=ops.DEFAULT_HUB_THRESHOLD)
         return hit[1]
     gs = GraphStructure(torch.stack([index, index]), dim_size, LOOPS_KEEP, hub_threshold)
     _INDEX_CACHE[key] = (index, gs)
-    while len(_INDEX_CACHE) > 8:
+    while len(_INDEX_CACHE) > 3:
         _INDEX_CACHE.popitem(last=False)
     return gs
 
@@ -155,3 +175,26 @@ def structure_of_index(index, dim_size, hub_threshold=ops.DEFAULT_HUB_THRESHOLD)
 def clear_structure_cache():
     _CACHE.clear()
     _INDEX_CACHE.clear()
+
+
+_POSITIVE = OrderedDict()
+
+
+def all_positive(t):
+    """every entry of a device vector is > 0 and finite — one host read per (storage, version), cached.  Used by the
+    hidden-32 stack: its aggregate-then-transform kernels store activations scaled by the per-source degree factor and
+    need that factor to be non-zero on every gathered row, which a user-supplied degree vector (deg_K) need not give.
+    Inside a CUDA-graph capture only the cached answer is available (None = unknown)."""
+    version = _version_of(t)
+    key = (t.data_ptr(), t.numel(), version, t.device.index)
+    if version is not None and key in _POSITIVE:
+        _POSITIVE.move_to_end(key)
+        return _POSITIVE[key]
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    ok = bool(((t > 0) & torch.isfinite(t)).all().item())
+    if version is not None:
+        _POSITIVE[key] = ok
+        while len(_POSITIVE) > 16:
+            _POSITIVE.popitem(last=False)
+    return ok

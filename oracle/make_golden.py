@@ -89,6 +89,36 @@ def case_gcn_meta(name, seed, n, m, model_kwargs, use_deg=True, edge_weight=Fals
     return d
 
 
+def case_gcn_meta_multi(name, seed, n, m, model_kwargs, num_sets=1, edge_attr_dim=None):
+    """GCNModel over K edge sets (GCNMultiKernel, gcn_multi_kernel.py:76-114) and / or with per-edge attributes
+    (gcn_base_models.py:204-206,227): inputs are lists, one entry per edge set"""
+    from gcn_meta.models.gcn_model import GCNModel
+    eis = [small_graph(seed + 17 * k, n, m)[1] for k in range(num_sets)]
+    torch.manual_seed(seed)
+    model = GCNModel(**model_kwargs)
+    model.train()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(n, model_kwargs["in_channels"], generator=g)
+    degs = [torch.bincount(ei[0], minlength=n).float() for ei in eis]
+    eas = [torch.randn(ei.size(1), edge_attr_dim, generator=g) for ei in eis] if edge_attr_dim else None
+    out = model(x, eis if num_sets > 1 else eis[0], edge_attr_K=(eas if num_sets > 1 else eas[0]) if eas else None,
+                deg_K=degs if num_sets > 1 else degs[0])
+    y = torch.randint(0, out.size(1), (out.size(0),), generator=g)
+    loss = torch.nn.CrossEntropyLoss()(out, y)
+    loss.backward()
+    d = {"x": x.numpy(), "y": y.numpy(), "out": out.detach().numpy(), "loss": np.array(loss.item(), dtype=np.float64),
+         "num_sets": np.array(num_sets)}
+    for k in range(num_sets):
+        d[f"edge_index{k}"] = eis[k].numpy()
+        d[f"deg{k}"] = degs[k].numpy()
+        if eas:
+            d[f"edge_attr{k}"] = eas[k].numpy()
+    d.update(np_state(model))
+    d.update(np_grads(model))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    return d
+
+
 def case_primitives():
     """degnorm_const, NodeModelAdditive.forward, scatter_ and the legacy GCN.norm on one graph"""
     from gcn_meta.models.common import scatter_
@@ -240,6 +270,17 @@ def main():
         case_gcn_meta("gcn_meta_attention", 11, 150, 500, v_, use_deg=False)
         case_gcn_meta("gcn_meta_attention_out_mean", 12, 150, 500,
                       dict(v_, nheads=[2, 4, 1], att_combine="mean", att_dir="out", att_act="relu"), use_deg=False)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":    # round 2: per-layer deg_norm override, edge attributes, two edge sets
+        v_ = dict(in_channels=5, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",
+                  non_linear_layer_wise="relu", residual_hop=1, dropout=0.0, final_type="proj", pred_on="node",
+                  nodemodel="additive", deg_norm="sm", edge_gate=None, aggr="add", bias=True)
+        case_gcn_meta("gcn_meta_final_rw", 21, 150, 500, dict(v_, final_layer_config={"deg_norm": "rw"}))
+        case_gcn_meta("gcn_meta_final_rw_nobias32", 22, 300, 1200,
+                      dict(v_, in_channels=1, enc_sizes=[32] * 4, bias=False, final_layer_config={"deg_norm": "rw"}))
+        case_gcn_meta_multi("gcn_meta_edgeattr", 23, 150, 500, dict(v_, in_edgedim=3), edge_attr_dim=3)
+        case_gcn_meta_multi("gcn_meta_two_kernels_add", 24, 150, 400, dict(v_, num_kernel=2, kernel_combine="add"),
+                            num_sets=2)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "gate":  # edge-gate cases (added later)
         v_ = dict(in_channels=1, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",

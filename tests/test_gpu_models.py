@@ -36,6 +36,9 @@ CASES = {
                                 att_combine="cat", att_dir="in"), {"use_deg": False}),
     "gcn_meta_attention_out_mean": (dict(V, in_channels=5, nodemodel="attention", nheads=[2, 4, 1], att_act="relu",
                                          att_dropout=0, att_combine="mean", att_dir="out"), {"use_deg": False}),
+    # a last layer that normalises differently (final_layer_config, gcn_model.py:49-59): degree factors per method
+    "gcn_meta_final_rw": (dict(V, in_channels=5, final_layer_config={"deg_norm": "rw"}), {}),
+    "gcn_meta_final_rw_nobias32": (dict(V, enc_sizes=[32] * 4, bias=False, final_layer_config={"deg_norm": "rw"}), {}),
     "gcn_meta_gate_proj": (dict(V, edge_gate="proj"), {}),
     "gcn_meta_gate_proj_mean_ew": (dict(V, in_channels=5, aggr="mean", deg_norm="rw", edge_gate="proj"),
                                    {"edge_weight": True}),
@@ -74,6 +77,55 @@ def test_gcn_model_matches_reference_golden(name, path):
     assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(1.0, abs(float(g["loss"])))
     for k, p in model.named_parameters():
         assert_parity(p.grad, g["grad." + k], f"{name}.grad.{k}")
+
+
+@pytest.mark.parametrize("name,cfg,num_sets,with_attr", [
+    ("gcn_meta_edgeattr", dict(V, in_channels=5, in_edgedim=3), 1, True),
+    ("gcn_meta_two_kernels_add", dict(V, in_channels=5, num_kernel=2, kernel_combine="add"), 2, False),
+])
+def test_gcn_model_edge_attributes_and_two_edge_sets_match_reference_golden(name, cfg, num_sets, with_attr):
+    """per-edge attribute messages (gcn_base_models.py:204-206,227) and K = 2 edge sets combined by 'add'
+    (gcn_multi_kernel.py:76-114): goldens from the unmodified reference (oracle/make_golden.py r2)"""
+    g = golden(name)
+    model = GCNModel(**cfg)
+    model.load_state_dict(params_of(g), strict=True)
+    model.to(DEV).train()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    eis = [torch.from_numpy(g[f"edge_index{k}"]).to(DEV) for k in range(num_sets)]
+    degs = [torch.from_numpy(g[f"deg{k}"]).to(DEV) for k in range(num_sets)]
+    eas = [torch.from_numpy(g[f"edge_attr{k}"]).to(DEV) for k in range(num_sets)] if with_attr else None
+    one = num_sets == 1
+    out = model(x, eis[0] if one else eis, edge_attr_K=(eas[0] if one else eas) if eas else None,
+                deg_K=degs[0] if one else degs)
+    loss = torch.nn.CrossEntropyLoss()(out, torch.from_numpy(g["y"]).to(DEV))
+    loss.backward()
+    assert_parity(out, g["out"], name + ".out")
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * max(1.0, abs(float(g["loss"])))
+    for k, p in model.named_parameters():
+        assert_parity(p.grad, g["grad." + k], f"{name}.grad.{k}")
+
+
+def test_user_degree_with_zeros_takes_the_exact_path():
+    """a caller's deg_K with zeros on source nodes (inf -> 0 factors, gcn_base_models.py:135): the stack must not use
+    the scaled-activation kernels, and both host paths agree"""
+    g = golden("gcn_meta_botnet12")
+    model = GCNModel(**BOTNET)
+    model.load_state_dict(params_of(g), strict=True)
+    model.to(DEV).eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    ei = torch.from_numpy(g["edge_index"]).to(DEV)
+    deg = torch.from_numpy(g["deg"]).to(DEV).clone()
+    deg[::7] = 0.0
+    with torch.no_grad():
+        a = model(x, ei, deg_K=deg)
+        b = model(x, ei, deg_K=deg, _no_stack=True)
+    assert torch.isfinite(a).all()
+    assert_parity(a, b, "zero-degree rows: stack vs per-layer path")
+    ref = port.OracleGCNModel(**BOTNET)
+    ref.load_state_dict(params_of(g), strict=True)
+    with torch.no_grad():
+        r = ref(x.cpu(), ei.cpu(), deg.cpu())
+    assert_parity(a, r, "zero-degree rows vs oracle")
 
 
 def test_primitive_seam_matches_reference_golden():
