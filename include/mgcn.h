@@ -108,6 +108,11 @@ int mgcn_csr_capacities(int64_t E, int64_t N, int loop_mode, int32_t hub_thresho
 int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by, int loop_mode,
                    const mgcn_csr_t* out, int32_t* bad_index, void* workspace,
                    size_t* workspace_bytes, void* stream);
+/* the same for an edge_index stored as int32 [2,E] (converted once when the dataset is loaded): the botnet batch
+ * ships 600 MB of int64 indices per step over PCIe (batch.to(device), train_botnet.py:282), 300 MB as int32 */
+int mgcn_csr_build_i32(const int32_t* edge_index, int64_t E, int64_t N, int by, int loop_mode,
+                       const mgcn_csr_t* out, int32_t* bad_index, void* workspace,
+                       size_t* workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Edge preprocessing that defines the botnet edge order: to_undirected_ey +
@@ -137,6 +142,7 @@ int mgcn_weighted_degree(const mgcn_csr_t* g, const float* edge_weight, int64_t 
  * edge_index the structure by source (the transposed aggregation of the autograd, train_botnet.py:293) holds
  * the same neighbour multisets per row as the structure by target and is not built a second time. */
 int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint64_t* out4, void* stream);
+int mgcn_edge_fingerprint_i32(const int32_t* edge_index, int64_t E, uint64_t* out4, void* stream);
 
 /* dis = deg^-1/2 (mode 0, 'sm') or deg^-1 (mode 1, 'rw') with inf -> 0:
  * gcn_base_models.py:128-135.  Computed as correctly rounded 1/sqrt(d) resp. 1/d. */

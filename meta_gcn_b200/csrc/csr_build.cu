@@ -106,7 +106,8 @@ static int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_
 // ------------------------------------------------------------------------------------------------
 // keys + row histogram
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_make_keys(const int64_t* __restrict__ ei, int64_t E,
+template <typename IndexT>   // int64_t (the reference's edge_index dtype) or int32_t (half the H2D bytes)
+__global__ void __launch_bounds__(256) k_make_keys(const IndexT* __restrict__ ei, int64_t E,
                                                    int64_t N, int by, int loop_mode,
                                                    int64_t total, uint32_t* __restrict__ keys,
                                                    int32_t* __restrict__ counts,
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) k_make_keys(const int64_t* __restrict__ e
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     uint32_t key;
     if (e < E) {
-      const int64_t s = ei[e], d = ei[E + e];
+      const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
       const bool ok = s >= 0 && s < N && d >= 0 && d < N;
       if (!ok) {
         *bad_index = 1;
@@ -253,8 +254,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+template <typename IndexT>
 __global__ void __launch_bounds__(256)
-    k_finalize(const int64_t* __restrict__ ei, int64_t E, int by, int64_t total,
+    k_finalize(const IndexT* __restrict__ ei, int64_t E, int by, int64_t total,
                const int32_t* __restrict__ sorted_pos, const int32_t* __restrict__ rowptr,
                int64_t N, int32_t* __restrict__ nbr, int32_t* __restrict__ perm) {
   const int32_t kept = rowptr[N];
@@ -595,9 +597,10 @@ extern "C" int mgcn_csr_capacities(int64_t E, int64_t N, int loop_mode, int32_t 
   return MGCN_OK;
 }
 
-extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by,
-                              int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
-                              void* workspace, size_t* workspace_bytes, void* stream) {
+template <typename IndexT>
+static int csr_build_any(const IndexT* edge_index, int64_t E, int64_t N, int by,
+                         int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
+                         void* workspace, size_t* workspace_bytes, void* stream) {
   MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(by == 0 || by == 1, MGCN_ERR_SHAPE);
   MGCN_REQUIRE(loop_mode >= 0 && loop_mode <= 2, MGCN_ERR_SHAPE);
@@ -654,7 +657,7 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
   MGCN_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, sizeof(int32_t), st));
   MGCN_CHECK_CUDA(cudaMemsetAsync(bad_index, 0, sizeof(int32_t), st));
   if (total > 0) {
-    MGCN_LAUNCH(k_make_keys, grid_for(total, 256), 256, 0, stream, edge_index, E, N, by,
+    MGCN_LAUNCH(k_make_keys<IndexT>, grid_for(total, 256), 256, 0, stream, edge_index, E, N, by,
                 loop_mode, total, keys_a, rowptr, bad_index);
   }
   int rc = exclusive_scan_i32(rowptr, rowptr, N + 1, tile_sums, stream);
@@ -665,7 +668,7 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
     rc = radix_sort_positions(keys_a, keys_b, vals_a, vals_b, total, (uint64_t)N, block_hist,
                               tile_sums, &sorted_pos, stream);
     if (rc != MGCN_OK) return rc;
-    MGCN_LAUNCH(k_finalize, grid_for(total, 256), 256, 0, stream, edge_index, E, by, total,
+    MGCN_LAUNCH(k_finalize<IndexT>, grid_for(total, 256), 256, 0, stream, edge_index, E, by, total,
                 sorted_pos, rowptr, N, nbr, perm);
   }
   if (N > 0 && out->hub_cap > 0 && out->seg_cap > 0) {
@@ -708,6 +711,18 @@ extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, i
   return MGCN_OK;
 }
 
+extern "C" int mgcn_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int by,
+                              int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
+                              void* workspace, size_t* workspace_bytes, void* stream) {
+  return csr_build_any<int64_t>(edge_index, E, N, by, loop_mode, out, bad_index, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mgcn_csr_build_i32(const int32_t* edge_index, int64_t E, int64_t N, int by,
+                                  int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
+                                  void* workspace, size_t* workspace_bytes, void* stream) {
+  return csr_build_any<int32_t>(edge_index, E, N, by, loop_mode, out, bad_index, workspace, workspace_bytes, stream);
+}
+
 extern "C" int mgcn_degree_from_rowptr(const int32_t* rowptr, int64_t N, float* deg, void* stream) {
   MGCN_REQUIRE(N >= 0, MGCN_ERR_RANGE);
   if (N == 0) return MGCN_OK;
@@ -737,12 +752,13 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
   return z ^ (z >> 31);
 }
-__global__ void __launch_bounds__(256) k_edge_fingerprint(const int64_t* __restrict__ ei, int64_t E,
+template <typename IndexT>
+__global__ void __launch_bounds__(256) k_edge_fingerprint(const IndexT* __restrict__ ei, int64_t E,
                                                           unsigned long long* __restrict__ out) {
   unsigned long long f[4] = {0ull, 0ull, 0ull, 0ull};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
-    const uint64_t a = (uint64_t)ei[e], b = (uint64_t)ei[E + e];
+    const uint64_t a = (uint64_t)(int64_t)ei[e], b = (uint64_t)(int64_t)ei[E + e];
     const uint64_t ab = a * 0x9e3779b97f4a7c15ull + b, ba = b * 0x9e3779b97f4a7c15ull + a;
     f[0] += mix64(ab);
     f[1] += mix64(ba);
@@ -767,7 +783,8 @@ __global__ void __launch_bounds__(256) k_edge_fingerprint(const int64_t* __restr
 }
 }  // namespace mgcn
 
-extern "C" int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint64_t* out4, void* stream) {
+template <typename IndexT>
+static int edge_fingerprint_any(const IndexT* edge_index, int64_t E, uint64_t* out4, void* stream) {
   MGCN_REQUIRE(out4 != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(E >= 0 && E < (int64_t(1) << 31), MGCN_ERR_RANGE);
   MGCN_CHECK_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
@@ -775,9 +792,17 @@ extern "C" int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint6
   MGCN_REQUIRE(edge_index != nullptr, MGCN_ERR_NULL);
   int64_t blocks = ceil_div(E, 256 * 8);
   if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
-  MGCN_LAUNCH(k_edge_fingerprint, (unsigned)blocks, 256, 0, stream, edge_index, E,
+  MGCN_LAUNCH(k_edge_fingerprint<IndexT>, (unsigned)blocks, 256, 0, stream, edge_index, E,
               reinterpret_cast<unsigned long long*>(out4));
   return MGCN_OK;
+}
+
+extern "C" int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint64_t* out4, void* stream) {
+  return edge_fingerprint_any<int64_t>(edge_index, E, out4, stream);
+}
+
+extern "C" int mgcn_edge_fingerprint_i32(const int32_t* edge_index, int64_t E, uint64_t* out4, void* stream) {
+  return edge_fingerprint_any<int32_t>(edge_index, E, out4, stream);
 }
 
 extern "C" int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream) {

@@ -21,16 +21,27 @@ class GraphBatch:
     def __init__(self, x, edge_index, y=None, batch=None, slices_x=None, slices_e=None):
         self.x, self.edge_index, self.y = x, edge_index, y
         if batch is None:
-            batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
             if slices_x is None:
                 slices_x = [0, int(x.size(0))]
         elif slices_x is None:  # boundaries from the (sorted) graph-id vector
             counts = torch.bincount(batch.cpu()) if batch.numel() else torch.zeros(0, dtype=torch.long)
             slices_x = [0] + torch.cumsum(counts, 0).tolist()
-        self.batch = batch
+        self._batch = batch     # None: built from the boundaries when first asked for (node-level models never do)
         self.slices_x = list(slices_x)
         self.slices_e = list(slices_e) if slices_e is not None else [0, int(edge_index.size(1))]
         self.__slices__ = {"x": self.slices_x, "edge_index": self.slices_e}
+
+    @property
+    def batch(self):
+        if self._batch is None:
+            counts = torch.tensor([b - a for a, b in zip(self.slices_x, self.slices_x[1:])], dtype=torch.long,
+                                  device=self.x.device)
+            self._batch = torch.repeat_interleave(torch.arange(counts.numel(), device=self.x.device), counts)
+        return self._batch
+
+    @batch.setter
+    def batch(self, value):
+        self._batch = value
 
     @property
     def num_graphs(self):
@@ -50,7 +61,7 @@ class GraphBatch:
 
     def _map(self, fn):
         out = GraphBatch(fn(self.x), fn(self.edge_index), None if self.y is None else fn(self.y),
-                         fn(self.batch), self.slices_x, self.slices_e)
+                         None if self._batch is None else fn(self._batch), self.slices_x, self.slices_e)
         return out
 
     def to(self, device, non_blocking=False):
@@ -58,6 +69,16 @@ class GraphBatch:
 
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())
+
+    def with_int32_indices(self):
+        """edge_index as int32 (N, E < 2^31): half the bytes of the host -> device copy, which is what bounds a
+        botnet step end to end (600 MB of int64 indices per 25-graph batch, train_botnet.py:282).  Convert once when
+        the dataset is loaded; every structure-building entry point accepts either dtype."""
+        if self.edge_index.dtype == torch.int32:
+            return self
+        if self.num_nodes >= 2 ** 31 - 2 ** 20:
+            raise ValueError("too many nodes for int32 indices")
+        return GraphBatch(self.x, self.edge_index.to(torch.int32), self.y, self._batch, self.slices_x, self.slices_e)
 
     @staticmethod
     def from_data_list(graphs):
@@ -103,8 +124,10 @@ class DeviceLoader:
 
     FIELDS = ("x", "edge_index", "y", "batch")
 
-    def __init__(self, batches, device, slots=2):
+    def __init__(self, batches, device, slots=2, fields=None):
         self.batches = batches
+        if fields is not None:          # e.g. ("x", "edge_index", "y"): node-level models never read `batch`
+            self.FIELDS = tuple(fields)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DeviceLoader copies to a CUDA device (no CPU path)")
@@ -133,8 +156,12 @@ class DeviceLoader:
                 out[name] = dst
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        b = GraphBatch(out["x"], out["edge_index"], out["y"], out["batch"], host.slices_x, host.slices_e)
+        b = GraphBatch(out["x"], out["edge_index"], out.get("y"), out.get("batch"), host.slices_x, host.slices_e)
         return b, ev
+
+    def bytes_per_batch(self, host):
+        """bytes one batch moves host -> device (what the copies above transfer)"""
+        return sum(t.numel() * t.element_size() for t in (getattr(host, n) for n in self.FIELDS) if t is not None)
 
     def __iter__(self):
         it = iter(self.batches)

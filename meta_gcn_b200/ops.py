@@ -90,13 +90,14 @@ def _as_csr(csr, hub_threshold=None):
 # ------------------------------------------------------------------------------------------------
 def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRESHOLD):
     _need_cuda(edge_index)
-    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
-        raise TypeError("edge_index must be int64 [2,E]")
+    if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("edge_index must be int64 (the reference's dtype) or int32, shape [2,E]")
     ei = edge_index.contiguous()
     E = ei.size(1)
     N = int(N)
     dev = ei.device
     lib = _lib.load()
+    build = lib.mgcn_csr_build if ei.dtype == torch.int64 else lib.mgcn_csr_build_i32
     caps = [ctypes.c_int64(0) for _ in range(3)]
     _lib.check(lib.mgcn_csr_capacities(E, N, int(loop_mode), int(hub_threshold),
                                        *[ctypes.byref(c) for c in caps]))
@@ -109,11 +110,11 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRES
               torch.empty(1, **i32))
     nbytes = ctypes.c_size_t(0)
     st = csr.struct()
-    _lib.check(lib.mgcn_csr_build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
-                                  _ptr(csr.bad), None, ctypes.byref(nbytes), None))
+    _lib.check(build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
+                     _ptr(csr.bad), None, ctypes.byref(nbytes), None))
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-    _lib.check(lib.mgcn_csr_build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
-                                  _ptr(csr.bad), _ptr(ws), ctypes.byref(nbytes), _stream()))
+    _lib.check(build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
+                     _ptr(csr.bad), _ptr(ws), ctypes.byref(nbytes), _stream()))
     return csr
 
 
@@ -190,11 +191,13 @@ def edge_symmetry_impl(edge_index):
     """True iff the directed edge multiset equals its transpose (mgcn_edge_fingerprint).  Reads four words
     back from the device: one host synchronisation per edge_index."""
     _need_cuda(edge_index)
-    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
-        raise TypeError("edge_index must be int64 [2, E]")
+    if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("edge_index must be int64 or int32, shape [2, E]")
     ei = edge_index.contiguous()
     out = torch.empty(4, dtype=torch.int64, device=ei.device)
-    _lib.check(_lib.load().mgcn_edge_fingerprint(_ptr(ei), ei.size(1), _ptr(out), _stream()))
+    lib = _lib.load()
+    fn = lib.mgcn_edge_fingerprint if ei.dtype == torch.int64 else lib.mgcn_edge_fingerprint_i32
+    _lib.check(fn(_ptr(ei), ei.size(1), _ptr(out), _stream()))
     f = out.tolist()
     return f[0] == f[1] and f[2] == f[3]
 

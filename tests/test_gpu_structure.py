@@ -216,3 +216,30 @@ def test_edge_symmetry_fingerprint_and_structure_reuse():
     assert_bitexact(gs.out_degree().cpu().numpy(), np.diff(gs.bwd.rowptr.cpu().numpy()).astype(np.float32), "deg")
     gs2 = G.GraphStructure(ei2, 5000)
     assert not gs2.symmetric and gs2.bwd_plain is gs2.bwd
+
+
+def test_int32_edge_index_builds_the_same_structures():
+    """mgcn_csr_build_i32 / mgcn_edge_fingerprint_i32: an edge_index held as int32 (half the host -> device bytes)
+    gives bit-identical structures, symmetry verdict and model output as the reference's int64"""
+    from meta_gcn_b200 import data as D
+    from meta_gcn_b200 import ops as O
+    from meta_gcn_b200.gcn_meta.models import GCNModel
+    g = D.synth_botnet_graph(seed=3, num_nodes=20000, edge_entries=200000, evil=1000)
+    ei64 = torch.from_numpy(g["edge_index"]).to("cuda")
+    ei32 = ei64.to(torch.int32)
+    n = g["x"].shape[0]
+    for by in (0, 1):
+        for loop_mode in (0, 1, 2):
+            a = O.csr_build_impl(ei64, n, by, loop_mode)
+            b = O.csr_build_impl(ei32, n, by, loop_mode)
+            for name in ("rowptr", "nbr", "perm", "order", "hub_count", "seg_count", "tasks", "nbr_w"):
+                assert torch.equal(getattr(a, name), getattr(b, name)), (by, loop_mode, name)
+    assert O.edge_symmetry_impl(ei32) == O.edge_symmetry_impl(ei64) is True
+    torch.manual_seed(0)
+    model = GCNModel(in_channels=1, enc_sizes=[32] * 3, num_classes=2, residual_hop=1, dropout=0.0, final_type="proj",
+                     deg_norm="sm", aggr="add", bias=False).to("cuda").eval()
+    x = torch.from_numpy(g["x"]).to("cuda")
+    with torch.no_grad():
+        o64 = model(x[:, 0:1].contiguous(), ei64, deg_K=x[:, 1].contiguous())
+        o32 = model(x[:, 0:1].contiguous(), ei32, deg_K=x[:, 1].contiguous())
+    assert torch.equal(o64, o32)
