@@ -11,7 +11,19 @@ namespace mgcn {
 
 extern std::atomic<long long> g_launch_count;
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+// SM count of the CURRENT device (B200: 148 = 2 dies x 74), queried once per device and cached; grids of the
+// persistent kernels are sized from it.  Falls back to 148 if the query fails.
+inline int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
+#define kNumSMs (::mgcn::num_sms())
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

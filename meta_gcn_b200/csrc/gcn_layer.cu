@@ -925,13 +925,14 @@ extern "C" int mgcn_gcn_layer_fwd(const mgcn_csr_t* g, const float* m, int64_t n
   a.hub_cap = hubs ? g->hub_cap : 0;
   a.act_out = act_out;
   const size_t smem = sizeof(float) * kFwdSmemFloats;
-  static std::once_flag once;   // per process; the attribute is per function, set on the current device
+  // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
+  // gets it too and a failure is reported every time
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
+  {
     attr_err = cudaFuncSetAttribute(k_layer_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(k_layer_fwd_hubs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  }
   MGCN_CHECK_CUDA(attr_err);
   const int64_t max_tiles = ceil_div(n_rows + a.seg_cap, 16);
   int64_t blocks = ceil_div(max_tiles, kFwdWarps);
@@ -972,11 +973,12 @@ extern "C" int mgcn_gcn_first_layer_fwd(const float* s, const float* x, int64_t 
   a.n_rows = N;
   a.act_out = act_out;
   const size_t smem = sizeof(float) * kFwdSmemFloats;
-  static std::once_flag once;
+  // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
+  // gets it too and a failure is reported every time
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
+  {
     attr_err = cudaFuncSetAttribute(k_first_layer_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  }
   MGCN_CHECK_CUDA(attr_err);
   int64_t blocks = ceil_div(ceil_div(N, 16), kFwdWarps);
   if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
@@ -1015,11 +1017,12 @@ extern "C" int mgcn_gcn_layer_bwd(const float* dxw, const float* gy, const float
   a.part_w = part_w; a.part_r = part_r; a.part_b = part_b;
   a.n_rows = N;
   const size_t smem = sizeof(float) * kBwdSmemFloats;
-  static std::once_flag once;
+  // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
+  // gets it too and a failure is reported every time
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
+  {
     attr_err = cudaFuncSetAttribute(k_layer_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  }
   MGCN_CHECK_CUDA(attr_err);
   MGCN_LAUNCH(k_layer_bwd, P, kBwdWarps * 32, smem, stream, a);
   int rc = launch_reduce_partials(part_w, P, kH * kH, kH, dw, kH, 1, stream);

@@ -496,11 +496,12 @@ int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const
   a.part_t = ws;
   a.part_b = ws + (size_t)P * 128 * 32;
   a.n_rows = N;
-  static std::once_flag once;
+  // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
+  // gets it too and a failure is reported every time
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
+  {
     attr_err = cudaFuncSetAttribute(k_layer_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdTcSmem);
-  });
+  }
   MGCN_CHECK_CUDA(attr_err);
   MGCN_LAUNCH(k_layer_bwd_tc, P, kBwdTcThreads, kBwdTcSmem, stream, a);
   MGCN_LAUNCH(k_bwd_tc_reduce, 64, 256, 0, stream, a.part_t, P, dw, d_res_w);

@@ -256,11 +256,12 @@ extern "C" int mgcn_linear_wide(const float* x, int64_t N, int64_t Hi, const flo
   a.n_rows = N; a.Hi = (int)Hi; a.Ho = (int)Ho; a.n_chunks = n_chunks; a.act = act;
   size_t smem = 2 * (2 * (size_t)kAChunkBytes + 2 * (size_t)Ho * kWK * 4) + 128 + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
-  static std::once_flag once;
+  // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
+  // gets it too and a failure is reported every time
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
+  {
     attr_err = cudaFuncSetAttribute(k_linear_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  });
+  }
   MGCN_CHECK_CUDA(attr_err);
   int64_t tiles = ceil_div(N, kWM);
   const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);

@@ -283,11 +283,12 @@ int launch_wide_wgrad(const float* x, int64_t N, int64_t Hi, const float* g, con
   a.x = x; a.g = g; a.gmask = gmask; a.partial = partial; a.partial_b = db ? partial_b : nullptr;
   a.n_rows = N; a.Hi = (int)Hi; a.Ho = (int)Ho; a.S = wide_wgrad_splits(Hi);
   const int n_mb = (int)((Hi + 127) / 128);
-  static std::once_flag once;
+  // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
+  // gets it too and a failure is reported every time
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
+  {
     attr_err = cudaFuncSetAttribute(k_wgrad_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem);
-  });
+  }
   MGCN_CHECK_CUDA(attr_err);
   MGCN_LAUNCH(k_wgrad_wide, (unsigned)(a.S * n_mb), kGThreads, kGSmem, stream, a);
   int rc = launch_reduce_partials(partial, a.S, (int)(Hi * Ho), (int)Ho, dw, dw_sk, dw_sc, stream);

@@ -31,8 +31,6 @@ class NodeModelBase(nn.Module):
         self.in_edgedim = in_edgedim
         self.deg_norm = deg_norm
         self.aggr = aggr
-        if edge_gate is not None and aggr == "max":
-            raise NotImplementedError("edge gates together with aggr='max' are not built")
         if edge_gate == "proj":                                           # gcn_base_models.py:57-63
             self.edge_gate = EdgeGateProj(out_channels, in_edgedim=in_edgedim, bias=True)
         elif edge_gate == "free":
@@ -119,15 +117,10 @@ class NodeModelAdditive(NodeModelBase):
             row_scale = dis if self.deg_norm == "sm" else None
         eg = None
         if self.edge_gate is not None:                                    # gcn_base_models.py:230-232
-            if self.aggr == "max":
-                raise NotImplementedError("edge gates together with aggr='max' are not built")
             eg = self.edge_gate(xw, edge_index, edge_attr=edge_attr, edge_weight=edge_weight).view(-1)
         if self.aggr == "max":
             # gcn_base_models.py:209-237 with scatter_('max'): max over the incoming edges of (x W)[row] * norm_e,
             # norm_e formed exactly as degnorm_const does (one factor per edge, same roundings)
-            if edge_attr is not None:
-                raise NotImplementedError("aggr='max' with edge attributes is not built (the max is taken over the "
-                                          "SUM of node and edge messages: not separable)")
             norm_e = None
             if self.deg_norm is not None:
                 dis = nbr_scale
@@ -136,7 +129,21 @@ class NodeModelAdditive(NodeModelBase):
                     norm_e = dis[row] * dis[col] if edge_weight is None else dis[row] * edge_weight.view(-1) * dis[col]
                 else:
                     norm_e = dis[row] if edge_weight is None else dis[row] * edge_weight.view(-1)
-            out = F_mgcn.aggregate_max(xw, graph, norm_e)
+            if eg is None and edge_attr is None:
+                out = F_mgcn.aggregate_max(xw, graph, norm_e)
+            else:
+                # the maximum is taken over gate_e * (x W [row_e] * norm_e + edge_attr_e W_e): not separable into a
+                # per-node and a per-edge part, so the [E,H] messages are formed as the reference does
+                # (gcn_base_models.py:223-232) and reduced by the primitive seam's first-maximum kernel
+                msg = xw.index_select(0, edge_index[0])
+                if norm_e is not None:
+                    msg = msg * norm_e.view(-1, 1)
+                if edge_attr is not None:
+                    assert self.in_edgedim is not None
+                    msg = msg + F_mgcn.linear(edge_attr, self.weight_edge)
+                if eg is not None:
+                    msg = eg.view(-1, 1) * msg
+                out = F_mgcn.scatter_rows_max(msg, edge_index[1], n)[0]
             if self.bias is not None:
                 out = out + self.bias
             return torch.relu(out) if act == "relu" else out

@@ -761,4 +761,210 @@ def _(gout, offsets, N, mode):
     return torch.empty(N, gout.size(1), dtype=torch.float32, device=gout.device)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# second group: the fused layer launches, the wide transform, 'max' aggregation, edge gates, preprocessing and
+# metrics as torch.ops.mgcn.* too (the op table is the library's Python surface), plus
+# register_autograd for the differentiable core (propagate, linear, segment_reduce) so that
+# torch.ops.mgcn.propagate / linear / segment_reduce carry gradients without the wrappers of functional.py
+# ------------------------------------------------------------------------------------------------
+_LIBDEF.define("gcn_layer_fwd_tc(Tensor[] csr, int hub_threshold, Tensor z, Tensor w, Tensor res_w, Tensor? res_b, "
+               "Tensor? bias, Tensor? in_scale, Tensor? post, Tensor? out_scale, int act_out) -> (Tensor, Tensor)")
+_LIBDEF.define("gcn_first_layer_fwd(Tensor s, Tensor x, Tensor w_in, Tensor res_w, Tensor? res_b, Tensor? w_next, "
+               "Tensor? pre, Tensor? post, int act_out, Tensor? out_scale) -> (Tensor, Tensor, Tensor)")
+_LIBDEF.define("gcn_layer_bwd(Tensor dxw, Tensor gy, Tensor x, Tensor w, Tensor res_w, Tensor? hmask_prev, Tensor? post, "
+               "bool want_prev, bool tensor_memory, Tensor? x_scale) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+_LIBDEF.define("mask_bits_scale(Tensor gy, Tensor bits, Tensor? post) -> Tensor")
+_LIBDEF.define("segment_max(Tensor[] csr, int hub_threshold, Tensor x, bool gather_perm, Tensor? edge_val) -> (Tensor, Tensor)")
+_LIBDEF.define("segment_max_bwd(Tensor[] csr_t, int hub_threshold, Tensor grad, Tensor arg, Tensor? edge_val) -> Tensor")
+_LIBDEF.define("scatter_max_bwd(Tensor arg, Tensor grad, int n_src) -> Tensor")
+_LIBDEF.define("edge_dot(Tensor edge_index, Tensor a, Tensor b, Tensor? scale_src, Tensor? scale_tgt) -> Tensor")
+_LIBDEF.define("binary_confusion(Tensor target, Tensor? logits, Tensor? pred) -> Tensor")
+_LIBDEF.define("preprocess_edges(Tensor edge_index, int N, bool undirected, bool add_loops) -> (Tensor, Tensor, Tensor)")
+_LIBDEF.define("edge_fingerprint(Tensor edge_index) -> Tensor")
+_LIBDEF.define("propagate(Tensor[] csr, Tensor[] csr_t, int hub_threshold, Tensor x, Tensor? nbr_scale, "
+               "Tensor? row_scale, int act) -> Tensor")
+
+
+def _none_to_empty(t, like):
+    return t if t is not None else torch.empty(0, dtype=torch.float32, device=like.device)
+
+
+def _op_layer_fwd_tc(csr, hub_threshold, z, w, res_w, res_b, bias, in_scale, post, out_scale, act_out):
+    return gcn_layer_fwd_tc_impl(_as_csr(csr, hub_threshold), z, w, res_w, res_b, bias, in_scale, post, out_scale,
+                                 act_out)
+
+
+def _op_first_layer_fwd(s, x, w_in, res_w, res_b, w_next, pre, post, act_out, out_scale):
+    xn, mn, hm = gcn_first_layer_fwd_impl(s, x, w_in, res_w, res_b, w_next, pre, post, act_out, out_scale)
+    return xn, _none_to_empty(mn, xn), hm
+
+
+def _op_layer_bwd(dxw, gy, x, w, res_w, hmask_prev, post, want_prev, tensor_memory, x_scale):
+    gyp, gsp, dw, drw, drb = gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev, tensor_memory,
+                                                x_scale)
+    return _none_to_empty(gyp, dw), _none_to_empty(gsp, dw), dw, drw, drb
+
+
+def _op_edge_fingerprint(edge_index):
+    _need_cuda(edge_index)
+    ei = edge_index.contiguous()
+    out = torch.empty(4, dtype=torch.int64, device=ei.device)
+    lib = _lib.load()
+    fn = lib.mgcn_edge_fingerprint if ei.dtype == torch.int64 else lib.mgcn_edge_fingerprint_i32
+    _lib.check(fn(_ptr(ei), ei.size(1), _ptr(out), _stream()))
+    return out
+
+
+def _op_propagate(csr, csr_t, hub_threshold, x, nbr_scale, row_scale, act):
+    return spmm_impl(_as_csr(csr, hub_threshold), x, False, None, nbr_scale, row_scale, 0, None, None, act)
+
+
+_IMPLS2 = {
+    "gcn_layer_fwd_tc": _op_layer_fwd_tc,
+    "gcn_first_layer_fwd": _op_first_layer_fwd,
+    "gcn_layer_bwd": _op_layer_bwd,
+    "mask_bits_scale": mask_bits_scale_impl,
+    "segment_max": lambda csr, ht, x, gp, ev: segment_max_impl(_as_csr(csr, ht), x, gp, ev),
+    "segment_max_bwd": lambda csr_t, ht, grad, arg, ev: segment_max_bwd_impl(_as_csr(csr_t, ht), grad, arg, ev),
+    "scatter_max_bwd": scatter_max_bwd_impl,
+    "edge_dot": edge_dot_impl,
+    "binary_confusion": binary_confusion_impl,
+    "preprocess_edges": preprocess_edges_impl,
+    "edge_fingerprint": _op_edge_fingerprint,
+    "propagate": _op_propagate,
+}
+for _name, _fn in _IMPLS2.items():
+    _LIBDEF.impl(_name, _fn, "CUDA")
+    _LIBDEF.impl(_name, _cpu_refusal(_name), "CPU")
+_IMPLS.update(_IMPLS2)
+
+
+def _rows_of(csr):
+    return csr[0].numel() - 1
+
+
+@torch.library.register_fake("mgcn::gcn_layer_fwd_tc")
+def _(csr, hub_threshold, z, w, res_w, res_b, bias, in_scale, post, out_scale, act_out):
+    n = _rows_of(csr)
+    return (torch.empty(n, z.size(1), dtype=torch.float32, device=z.device),
+            torch.empty(n, dtype=torch.int32, device=z.device))
+
+
+@torch.library.register_fake("mgcn::gcn_first_layer_fwd")
+def _(s, x, w_in, res_w, res_b, w_next, pre, post, act_out, out_scale):
+    n, h = x.size(0), w_in.size(1)
+    return (torch.empty(n, h, dtype=torch.float32, device=x.device),
+            torch.empty((n, h) if w_next is not None else (0,), dtype=torch.float32, device=x.device),
+            torch.empty(n, dtype=torch.int32, device=x.device))
+
+
+@torch.library.register_fake("mgcn::gcn_layer_bwd")
+def _(dxw, gy, x, w, res_w, hmask_prev, post, want_prev, tensor_memory, x_scale):
+    h = x.size(1)
+    prev = torch.empty_like(x) if want_prev else torch.empty(0, dtype=torch.float32, device=x.device)
+    f = dict(dtype=torch.float32, device=x.device)
+    return prev, torch.empty_like(prev), torch.empty(h, h, **f), torch.empty(h, h, **f), torch.empty(h, **f)
+
+
+@torch.library.register_fake("mgcn::mask_bits_scale")
+def _(gy, bits, post):
+    return torch.empty_like(gy)
+
+
+@torch.library.register_fake("mgcn::segment_max")
+def _(csr, hub_threshold, x, gather_perm, edge_val):
+    n = _rows_of(csr)
+    return (torch.empty(n, x.size(1), dtype=torch.float32, device=x.device),
+            torch.empty(n, x.size(1), dtype=torch.int32, device=x.device))
+
+
+@torch.library.register_fake("mgcn::segment_max_bwd")
+def _(csr_t, hub_threshold, grad, arg, edge_val):
+    return torch.empty(_rows_of(csr_t), grad.size(1), dtype=torch.float32, device=grad.device)
+
+
+@torch.library.register_fake("mgcn::scatter_max_bwd")
+def _(arg, grad, n_src):
+    return torch.empty(n_src, grad.size(1), dtype=torch.float32, device=grad.device)
+
+
+@torch.library.register_fake("mgcn::edge_dot")
+def _(edge_index, a, b, scale_src, scale_tgt):
+    return torch.empty(edge_index.size(1), dtype=torch.float32, device=a.device)
+
+
+@torch.library.register_fake("mgcn::binary_confusion")
+def _(target, logits, pred):
+    return torch.empty(5, dtype=torch.int64, device=target.device)
+
+
+@torch.library.register_fake("mgcn::edge_fingerprint")
+def _(edge_index):
+    return torch.empty(4, dtype=torch.int64, device=edge_index.device)
+
+
+@torch.library.register_fake("mgcn::propagate")
+def _(csr, csr_t, hub_threshold, x, nbr_scale, row_scale, act):
+    return torch.empty(_rows_of(csr), x.size(1), dtype=torch.float32, device=x.device)
+
+
+# ---- autograd formulas (deterministic: the transposed aggregation is the same row-owned kernel on csr_t) ----
+def _propagate_setup(ctx, inputs, output):
+    csr, csr_t, hub_threshold, x, nbr_scale, row_scale, act = inputs
+    ctx.csr_t, ctx.hub_threshold, ctx.act = csr_t, hub_threshold, act
+    ctx.save_for_backward(output if act else None, nbr_scale, row_scale)
+
+
+def _propagate_backward(ctx, g):
+    out, nbr_scale, row_scale = ctx.saved_tensors
+    g = g.contiguous()
+    if ctx.act:
+        g = torch.ops.mgcn.relu_backward(g, out)
+    # transpose: rows = sources; the per-target factor is gathered, the per-source factor scales the row
+    dx = torch.ops.mgcn.spmm(ctx.csr_t, ctx.hub_threshold, g, False, None, row_scale, nbr_scale, 0, None, None, 0)
+    return None, None, None, dx, None, None, None
+
+
+torch.library.register_autograd("mgcn::propagate", _propagate_backward, setup_context=_propagate_setup)
+
+
+def _linear_setup(ctx, inputs, output):
+    x, w, w_out_in, bias, add, act, xmask, row_scale = inputs
+    if xmask is not None or row_scale is not None:
+        raise RuntimeError("mgcn::linear is differentiable without xmask / row_scale only")
+    ctx.cfg = (w_out_in, act, bias is not None, add is not None)
+    ctx.save_for_backward(x, w, output if act else None)
+
+
+def _linear_backward(ctx, g):
+    x, w, y = ctx.saved_tensors
+    w_out_in, act, has_bias, has_add = ctx.cfg
+    g = g.contiguous()
+    if act:
+        g = torch.ops.mgcn.relu_backward(g, y)
+    dx = torch.ops.mgcn.linear(g, w, not w_out_in, None, None, 0) if ctx.needs_input_grad[0] else None
+    dw = db = None
+    if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[3]):
+        dw, db_ = torch.ops.mgcn.linear_wgrad(x, g, w_out_in, has_bias)
+        db = db_ if has_bias else None
+    return dx, dw, None, db, (g if has_add else None), None, None, None
+
+
+torch.library.register_autograd("mgcn::linear", _linear_backward, setup_context=_linear_setup)
+
+
+def _segred_setup(ctx, inputs, output):
+    x, offsets, mode = inputs
+    ctx.n, ctx.mode = x.size(0), mode
+    ctx.save_for_backward(offsets)
+
+
+def _segred_backward(ctx, g):
+    (offsets,) = ctx.saved_tensors
+    return torch.ops.mgcn.segment_broadcast(g.contiguous(), offsets, ctx.n, ctx.mode), None, None
+
+
+torch.library.register_autograd("mgcn::segment_reduce", _segred_backward, setup_context=_segred_setup)
+
 OP_NAMES = tuple(_IMPLS)

@@ -281,6 +281,8 @@ def main():
         case_gcn_meta_multi("gcn_meta_edgeattr", 23, 150, 500, dict(v_, in_edgedim=3), edge_attr_dim=3)
         case_gcn_meta_multi("gcn_meta_two_kernels_add", 24, 150, 400, dict(v_, num_kernel=2, kernel_combine="add"),
                             num_sets=2)
+        case_gcn_meta_multi("gcn_meta_max_edgeattr", 25, 150, 500, dict(v_, aggr="max", in_edgedim=3), edge_attr_dim=3)
+        case_gcn_meta("gcn_meta_max_gate_proj", 26, 150, 500, dict(v_, aggr="max", edge_gate="proj"))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "gate":  # edge-gate cases (added later)
         v_ = dict(in_channels=1, enc_sizes=[16, 16, 16], num_classes=2, non_linear="relu",

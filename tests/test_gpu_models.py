@@ -39,6 +39,7 @@ CASES = {
     # a last layer that normalises differently (final_layer_config, gcn_model.py:49-59): degree factors per method
     "gcn_meta_final_rw": (dict(V, in_channels=5, final_layer_config={"deg_norm": "rw"}), {}),
     "gcn_meta_final_rw_nobias32": (dict(V, enc_sizes=[32] * 4, bias=False, final_layer_config={"deg_norm": "rw"}), {}),
+    "gcn_meta_max_gate_proj": (dict(V, in_channels=5, aggr="max", edge_gate="proj"), {}),
     "gcn_meta_gate_proj": (dict(V, edge_gate="proj"), {}),
     "gcn_meta_gate_proj_mean_ew": (dict(V, in_channels=5, aggr="mean", deg_norm="rw", edge_gate="proj"),
                                    {"edge_weight": True}),
@@ -82,6 +83,7 @@ def test_gcn_model_matches_reference_golden(name, path):
 @pytest.mark.parametrize("name,cfg,num_sets,with_attr", [
     ("gcn_meta_edgeattr", dict(V, in_channels=5, in_edgedim=3), 1, True),
     ("gcn_meta_two_kernels_add", dict(V, in_channels=5, num_kernel=2, kernel_combine="add"), 2, False),
+    ("gcn_meta_max_edgeattr", dict(V, in_channels=5, aggr="max", in_edgedim=3), 1, True),
 ])
 def test_gcn_model_edge_attributes_and_two_edge_sets_match_reference_golden(name, cfg, num_sets, with_attr):
     """per-edge attribute messages (gcn_base_models.py:204-206,227) and K = 2 edge sets combined by 'add'

@@ -216,3 +216,47 @@ def test_torch_library_ops_roundtrip():
     assert_bitexact(a, b, "torch.ops.mgcn.spmm")
     c = torch.ops.mgcn.aggregate_prescaled(csr, 256, x, None, 0, None, None, 0)
     assert_bitexact(c, b, "torch.ops.mgcn.aggregate_prescaled")
+
+
+def test_registered_ops_are_differentiable():
+    """torch.ops.mgcn.propagate / linear / segment_reduce carry gradients through torch.library.register_autograd
+    (SURVEY.md §8b): same values and gradients as the differentiable wrappers of meta_gcn_b200.functional"""
+    from meta_gcn_b200 import functional as F
+    from meta_gcn_b200.graph import GraphStructure
+    n, e, h = 700, 5000, 32
+    g = np.random.default_rng(5)
+    ei = torch.from_numpy(np.stack([g.integers(0, n, e), g.integers(0, n, e)]).astype(np.int64)).to(DEV)
+    gs = GraphStructure(ei, n, hub_threshold=64)
+    gen = torch.Generator().manual_seed(1)
+    x0 = torch.randn(n, h, generator=gen).to(DEV)
+    w0 = (torch.randn(h, h, generator=gen) / 6).to(DEV)
+    b0 = torch.randn(h, generator=gen).to(DEV)
+    dis = (torch.rand(n, generator=gen) + 0.2).to(DEV)
+    offsets = torch.tensor([0, 100, 350, n], dtype=torch.int32, device=DEV)
+    wout = torch.randn(3, h, generator=gen).to(DEV)
+
+    def run(use_ops):
+        x = x0.clone().requires_grad_(True)
+        w = w0.clone().requires_grad_(True)
+        b = b0.clone().requires_grad_(True)
+        if use_ops:
+            y = torch.ops.mgcn.linear(x, w, False, b, None, 1)
+            z = torch.ops.mgcn.propagate(gs.fwd.tensors(), gs.bwd.tensors(), 64, y, dis, dis, 1)
+            p = torch.ops.mgcn.segment_reduce(z, offsets, 1)
+        else:
+            y = F.linear(x, w, b, act="relu")
+            z = F.aggregate(y, gs, dis, dis, act="relu")
+            p = F.segment_pool(z, offsets, "mean")
+        (p * wout).sum().backward()
+        return p.detach(), x.grad, w.grad, b.grad
+
+    a, b = run(True), run(False)
+    for u, v, name in zip(a, b, ("out", "dx", "dw", "db")):
+        assert_bitexact(u, v, "torch.ops.mgcn autograd " + name)
+    # the fused layer launch through the op table
+    zn, hm = torch.ops.mgcn.gcn_layer_fwd_tc(gs.fwd.tensors(), 64, x0, w0, w0.t().contiguous(), b0, None, dis, dis, dis, 1)
+    zn2, hm2 = ops.gcn_layer_fwd_tc_impl(gs.fwd, x0, w0, w0.t().contiguous(), b0, None, dis, dis, dis, 1)
+    assert_bitexact(zn, zn2, "torch.ops.mgcn.gcn_layer_fwd_tc")
+    assert_bitexact(hm, hm2, "torch.ops.mgcn.gcn_layer_fwd_tc mask")
+    f = torch.ops.mgcn.edge_fingerprint(ei).tolist()
+    assert (f[0] == f[1] and f[2] == f[3]) == ops.edge_symmetry_impl(ei)

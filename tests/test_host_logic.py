@@ -88,8 +88,7 @@ def test_unsupported_reference_options_fail_loudly():
     assert GCNModel(1, [8], 2, nodemodel="attention", nheads=2) is not None
     assert GCNModel(1, [8], 2, edge_gate="proj") is not None    # edge gates and 'max' are built (csrc/segmax.cu)
     assert GCNModel(1, [8], 2, aggr="max") is not None
-    with pytest.raises(NotImplementedError):
-        GCNModel(1, [8], 2, aggr="max", edge_gate="proj")
+    assert GCNModel(1, [8], 2, aggr="max", edge_gate="proj") is not None   # max over gated messages: primitive seam
     with pytest.raises(RuntimeError):                           # ... and, like every op, refuses CPU tensors
         scatter_("max", torch.ones(3, 2), torch.zeros(3, dtype=torch.long))
 
