@@ -912,7 +912,7 @@ def _(csr, csr_t, hub_threshold, x, nbr_scale, row_scale, act):
 # ---- autograd formulas (deterministic: the transposed aggregation is the same row-owned kernel on csr_t) ----
 def _propagate_setup(ctx, inputs, output):
     csr, csr_t, hub_threshold, x, nbr_scale, row_scale, act = inputs
-    ctx.csr_t, ctx.hub_threshold, ctx.act = csr_t, hub_threshold, act
+    ctx.csr_t, ctx.hub_threshold, ctx.act, ctx.n_csr = csr_t, hub_threshold, act, len(csr)
     ctx.save_for_backward(output if act else None, nbr_scale, row_scale)
 
 
@@ -923,7 +923,8 @@ def _propagate_backward(ctx, g):
         g = torch.ops.mgcn.relu_backward(g, out)
     # transpose: rows = sources; the per-target factor is gathered, the per-source factor scales the row
     dx = torch.ops.mgcn.spmm(ctx.csr_t, ctx.hub_threshold, g, False, None, row_scale, nbr_scale, 0, None, None, 0)
-    return None, None, None, dx, None, None, None
+    # gradients mirror the input structure: one entry per tensor of the two structure lists
+    return [None] * ctx.n_csr, [None] * len(ctx.csr_t), None, dx, None, None, None
 
 
 torch.library.register_autograd("mgcn::propagate", _propagate_backward, setup_context=_propagate_setup)
