@@ -326,6 +326,21 @@ int mgcn_segment_broadcast(const float* gout, int64_t H, const int32_t* offsets,
                            int64_t N, int mode, float* dx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d — the last stage of the GIN convolution's MLP (kernel/gin.py:10-16: Sequential(Linear, ReLU, Linear,
+ * ReLU, BatchNorm1d(hidden)); torch defaults eps 1e-5, momentum 0.1, affine).  x, y, g, dx: [N,H] row-major.
+ * training != 0: batch statistics (two passes: mean, then centred second moment), running_mean / running_var updated
+ * in place (unbiased variance, as torch does; either may be NULL); training == 0: the running statistics are used.
+ * mean [H] / rstd [H] are outputs of the forward and inputs of the backward.  gamma / beta may be NULL (no affine).
+ * backward: dbeta = colsum(g), dgamma = colsum(g * xhat), dx = gamma rstd (g - dbeta/N - xhat dgamma/N) in training
+ * mode, gamma rstd g in evaluation mode (dx may be NULL).  Fixed-order reductions: deterministic, no atomics. */
+int mgcn_batchnorm_fwd(const float* x, int64_t N, int64_t H, const float* gamma, const float* beta, float eps,
+                       float momentum, int training, float* running_mean, float* running_var, float* mean,
+                       float* rstd, float* y, void* workspace, size_t* workspace_bytes, void* stream);
+int mgcn_batchnorm_bwd(const float* x, const float* g, int64_t N, int64_t H, const float* gamma, const float* mean,
+                       const float* rstd, int training, float* dx, float* dgamma, float* dbeta, void* workspace,
+                       size_t* workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Node-level cross entropy — nn.CrossEntropyLoss()(x, batch.y.long()) (train_botnet.py:225,287).
  * loss[0] = sum_n ( logsumexp(logits[n,:]) - logits[n, target[n]] ) (* 1/N if mean), fixed-order
  * two-stage sum.  bad_target int32[1] is set if a label is outside [0,C).

@@ -97,7 +97,29 @@ class GINConv(torch.nn.Module):
     def forward(self, x, edge_index):
         x = x.unsqueeze(-1) if x.dim() == 1 else x
         graph = structure_of(edge_index, x.size(0), LOOPS_REMOVE)
-        return self.nn((1 + self.eps) * x + F_mgcn.aggregate(x, graph))
+        return self._mlp((1 + self.eps) * x + F_mgcn.aggregate(x, graph))
+
+    def _mlp(self, h):
+        """self.nn on libmgcn when it is the reference's Sequential of Linear / ReLU / BatchNorm1d (kernel/gin.py:10-16):
+        each Linear (+ the ReLU behind it) is one mgcn_linear launch, BatchNorm1d the fixed-order kernels of
+        csrc/batchnorm.cu.  Any other module is called as is."""
+        mods = list(self.nn) if isinstance(self.nn, torch.nn.Sequential) else None
+        if mods is None or not all(isinstance(m, (torch.nn.Linear, torch.nn.ReLU, torch.nn.BatchNorm1d)) for m in mods):
+            return self.nn(h)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, torch.nn.Linear):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], torch.nn.ReLU)
+                h = F_mgcn.linear(h, m.weight, m.bias, act="relu" if relu else None, weight_layout="out_in")
+                i += 2 if relu else 1
+            elif isinstance(m, torch.nn.BatchNorm1d):
+                h = F_mgcn.batch_norm(h, m)
+                i += 1
+            else:
+                h = torch.relu(h)
+                i += 1
+        return h
 
     def __repr__(self):
         return "{}(nn={})".format(self.__class__.__name__, self.nn)

@@ -122,6 +122,37 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, dadd, None, None
 
 
+class _BatchNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):
+        y, mean, rstd = ops.batchnorm_fwd_impl(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+        ctx.training = bool(training)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.batchnorm_bwd_impl(x, g.contiguous(), gamma, mean, rstd, ctx.training,
+                                                   ctx.needs_input_grad[0])
+        return (dx, dgamma if gamma is not None else None, dbeta if gamma is not None else None, None, None, None,
+                None, None)
+
+
+def batch_norm(x, bn, training=None):
+    """torch.nn.BatchNorm1d ``bn`` applied to x [N,H] by the fixed-order kernels of csrc/batchnorm.cu (kernel/gin.py:15);
+    running statistics and num_batches_tracked are updated as torch does in training mode"""
+    training = bn.training if training is None else training
+    use_batch = training or not bn.track_running_stats
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if training and bn.track_running_stats:
+        bn.num_batches_tracked += 1
+        if bn.momentum is None:
+            momentum = 1.0 / float(bn.num_batches_tracked)
+    return _BatchNorm.apply(x, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
+                            bn.running_var if bn.track_running_stats else None, use_batch, momentum, bn.eps)
+
+
 def linear(x, weight, bias=None, add=None, act=None, weight_layout="in_out"):
     """y = act(x @ W + bias + add).  weight_layout 'in_out': weight_node [Hi,Ho]
     (gcn_base_models.py:201); 'out_in': nn.Linear.weight [Ho,Hi] (gcn_model.py:64,73)."""

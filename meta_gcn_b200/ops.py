@@ -586,6 +586,44 @@ def segment_broadcast_impl(gout, offsets, N, mode):
     return dx
 
 
+def batchnorm_fwd_impl(x, gamma, beta, running_mean, running_var, training, momentum, eps):
+    """mgcn_batchnorm_fwd: returns (y, mean [H], rstd [H]); running statistics are updated in place when training"""
+    _need_cuda(x, gamma, beta, running_mean, running_var)
+    x = _f32c(x, "x")
+    gamma = _f32c(gamma, "gamma")
+    beta = _f32c(beta, "beta")
+    N, H = x.shape
+    dev = x.device
+    y = torch.empty_like(x)
+    mean = torch.empty(H, dtype=torch.float32, device=dev)
+    rstd = torch.empty(H, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    args = (_ptr(x), N, H, _ptr(gamma), _ptr(beta), float(eps), float(momentum), int(bool(training)),
+            _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(rstd), _ptr(y))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_batchnorm_fwd(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_batchnorm_fwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return y, mean, rstd
+
+
+def batchnorm_bwd_impl(x, g, gamma, mean, rstd, training, want_dx=True):
+    """mgcn_batchnorm_bwd: returns (dx | None, dgamma [H], dbeta [H])"""
+    _need_cuda(x, g, gamma, mean, rstd)
+    x = _f32c(x, "x")
+    g = _f32c(g, "g")
+    gamma = _f32c(gamma, "gamma")
+    N, H = x.shape
+    dev = x.device
+    dx = torch.empty_like(x) if want_dx else None
+    dgamma = torch.empty(H, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(H, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    args = (_ptr(x), _ptr(g), N, H, _ptr(gamma), _ptr(mean), _ptr(rstd), int(bool(training)), _ptr(dx),
+            _ptr(dgamma), _ptr(dbeta))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_batchnorm_bwd(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_batchnorm_bwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return dx, dgamma, dbeta
+
+
 # ------------------------------------------------------------------------------------------------
 # torch.library registration
 # ------------------------------------------------------------------------------------------------

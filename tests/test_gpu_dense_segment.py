@@ -153,3 +153,39 @@ def test_masked_scale_and_masked_operands():
     gm = (m2 * (m1 > 0)).double()
     assert_parity(dw, gm.t() @ a.double(), "masked wgrad")
     assert_parity(db, gm.sum(0), "masked bias grad")
+
+
+@pytest.mark.parametrize("n,h,training", [(5146, 64, True), (37, 64, True), (1000, 48, False), (200001, 32, True), (1, 8, False)])
+def test_batch_norm_matches_torch_fp64(n, h, training):
+    """csrc/batchnorm.cu behind torch.nn.BatchNorm1d (kernel/gin.py:15): outputs, running statistics and every
+    gradient against torch's own BatchNorm1d evaluated in fp64 on the CPU"""
+    from meta_gcn_b200 import functional as F
+    gen = torch.Generator().manual_seed(n + h)
+    x = torch.randn(n, h, generator=gen) * 2.0 + 3.0        # mean^2 >> var: the one-pass variance would cancel
+    wout = torch.randn(n, h, generator=gen)
+    bn = torch.nn.BatchNorm1d(h)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(h, generator=gen) + 0.5)
+        bn.bias.copy_(torch.randn(h, generator=gen))
+        bn.running_mean.copy_(torch.randn(h, generator=gen))
+        bn.running_var.copy_(torch.rand(h, generator=gen) + 0.5)
+    import copy
+    ref = copy.deepcopy(bn).double()
+    bn = bn.to("cuda")
+    bn.train(training)
+    ref.train(training)
+    if n == 1 and training:
+        pytest.skip("torch refuses batch statistics of a single row")
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    (yr * wout.double()).sum().backward()
+    xd = x.to("cuda").requires_grad_(True)
+    y = F.batch_norm(xd, bn)
+    (y * wout.to("cuda")).sum().backward()
+    assert_parity(y, yr, "bn.y")
+    assert_parity(xd.grad, xr.grad, "bn.dx")
+    assert_parity(bn.weight.grad, ref.weight.grad, "bn.dgamma")
+    assert_parity(bn.bias.grad, ref.bias.grad, "bn.dbeta")
+    assert_parity(bn.running_mean, ref.running_mean, "bn.running_mean")
+    assert_parity(bn.running_var, ref.running_var, "bn.running_var")
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
