@@ -144,6 +144,34 @@ int mgcn_weighted_degree(const mgcn_csr_t* g, const float* edge_weight, int64_t 
 int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint64_t* out4, void* stream);
 int mgcn_edge_fingerprint_i32(const int32_t* edge_index, int64_t E, uint64_t* out4, void* stream);
 
+/* Fingerprints plus the ORDER of the list, in one pass pair and one 64-byte result: out8[0..3] as mgcn_edge_fingerprint;
+ * out8[4] = number of positions e with (src,dst)[e] > (src,dst)[e+1] over the whole list; out8[5] the same over the
+ * first E-N entries; out8[6] = entries among the last N that are not the self loop (e-(E-N), e-(E-N)); out8[7] =
+ * adjacent equal entries.  out8[4] == 0: the list is in (src,dst) order; out8[5] == 0 && out8[6] == 0: sorted prefix +
+ * the N loops appended at the end — the layout the reference's preprocessing gives every botnet graph
+ * (data_procs/undirected.py:6-35: unique over row*N+col, sorted; loop.py:13-17: loops at the END).
+ * A BATCH of graphs (Batch.from_data_list, dataloader.py:11: the lists of G graphs one after the other, node ids
+ * shifted) is described by node_off / edge_off int32 [G+1] (device; G = 0 and NULL: one graph): the order tests are
+ * then made per graph (out8[4]: every graph's list sorted; out8[5], out8[6]: every graph = sorted prefix + its own
+ * loops), and an endpoint outside its graph's node range counts as a violation. */
+int mgcn_edge_layout(const int64_t* edge_index, int64_t E, int64_t N, int64_t G, const int32_t* node_off,
+                     const int32_t* edge_off, uint64_t* out8, void* stream);
+int mgcn_edge_layout_i32(const int32_t* edge_index, int64_t E, int64_t N, int64_t G, const int32_t* node_off,
+                         const int32_t* edge_off, uint64_t* out8, void* stream);
+
+/* mgcn_csr_build (loop_mode 0) for a list whose order the caller has established with mgcn_edge_layout — no sort:
+ * layout 1 = sorted by (src,dst); 2 = sorted prefix + N trailing loops; + 4 if entries may repeat (out8[7] != 0).
+ * by = 0 (source): any such list.  by = 1 (target): the list must also be symmetric (fingerprints equal); each
+ * entry's place is then that of its mirror edge, found by a binary search in the mirror's row (one graph only).
+ * G / node_off / edge_off as in mgcn_edge_layout (batches: by = 0, layout 2 or 6).  Same outputs, bit for bit, as
+ * mgcn_csr_build; the botnet batch (37.5 M entries): 1.3 ms by source against 3.5 ms with the three radix passes. */
+int mgcn_csr_build_presorted(const int64_t* edge_index, int64_t E, int64_t N, int by, int layout, int64_t G,
+                             const int32_t* node_off, const int32_t* edge_off, const mgcn_csr_t* out,
+                             int32_t* bad_index, void* workspace, size_t* workspace_bytes, void* stream);
+int mgcn_csr_build_presorted_i32(const int32_t* edge_index, int64_t E, int64_t N, int by, int layout, int64_t G,
+                                 const int32_t* node_off, const int32_t* edge_off, const mgcn_csr_t* out,
+                                 int32_t* bad_index, void* workspace, size_t* workspace_bytes, void* stream);
+
 /* dis = deg^-1/2 (mode 0, 'sm') or deg^-1 (mode 1, 'rw') with inf -> 0:
  * gcn_base_models.py:128-135.  Computed as correctly rounded 1/sqrt(d) resp. 1/d. */
 int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream);

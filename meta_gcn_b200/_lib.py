@@ -54,6 +54,12 @@ SIGNATURES = {
     "mgcn_csr_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, CSR_P, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_csr_build_i32": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, CSR_P, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_edge_fingerprint_i32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "mgcn_edge_layout": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "mgcn_edge_layout_i32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "mgcn_csr_build_presorted": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_ptr, c_ptr, CSR_P, c_ptr, c_ptr,
+                                         c_size_p, c_ptr]),
+    "mgcn_csr_build_presorted_i32": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_ptr, c_ptr, CSR_P, c_ptr,
+                                             c_ptr, c_size_p, c_ptr]),
     "mgcn_preprocess_edges": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                       c_ptr, c_size_p, c_ptr]),
     "mgcn_degree_from_rowptr": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),

@@ -597,10 +597,134 @@ extern "C" int mgcn_csr_capacities(int64_t E, int64_t N, int loop_mode, int32_t 
   return MGCN_OK;
 }
 
+// Entries of a list that is ALREADY in (source, target) lexicographic order — optionally followed by the N self loops
+// (0,0) .. (N-1,N-1), the layout data_procs/undirected.py:6-35 + loop.py:13-17 give every botnet graph — need no
+// sort: the stable grouping by source is "prefix entry e of source s -> e (+ s loops of smaller rows), loop i -> end
+// of row i".  For a symmetric list the grouping by target is the same row contents (sources ascending, loop last),
+// and the edge that sits at a by-target position is the mirror (d, s) of the by-source one, found by a binary search
+// in row d.  `dups` != 0: the list may repeat an entry; the k-th copy of (s, d) is paired with the k-th copy of (d, s).
+// graph of list position e in a batch: edge_off[g] <= e < edge_off[g+1]  (G <= a few hundred: a short binary search)
+__device__ __forceinline__ int segment_of(const int32_t* __restrict__ off, int G, int64_t v) {
+  int lo = 0, hi = G;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int64_t)off[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// A BATCH of such lists (Batch.from_data_list: graph after graph, node ids shifted; dataloader.py:11) is the same
+// layout per graph: node_off / edge_off [G+1] delimit the graphs (G = 0: the whole list is one graph).
+template <typename IndexT>
+__global__ void __launch_bounds__(256)
+    k_fill_presorted(const IndexT* __restrict__ ei, int64_t E, int64_t N, int by, int tail, int dups, int G,
+                     const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off,
+                     const int32_t* __restrict__ rowptr, int32_t* __restrict__ nbr, int32_t* __restrict__ perm) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    int64_t n0 = 0, e0 = 0, ng = N, eg = E;   // this entry's graph: first node, first entry, sizes
+    if (G > 0) {
+      const int g = segment_of(edge_off, G, e);
+      n0 = node_off[g];
+      e0 = edge_off[g];
+      ng = node_off[g + 1] - n0;
+      eg = edge_off[g + 1] - e0;
+    }
+    const int64_t Ep = e0 + (tail ? eg - ng : eg);   // end of the graph's sorted prefix
+    if (e >= Ep) {
+      const int64_t i = n0 + (e - Ep);
+      const int32_t k = rowptr[i + 1] - 1;
+      nbr[k] = (int32_t)i;
+      perm[k] = (int32_t)e;
+      continue;
+    }
+    const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
+    if (s < 0 || s >= N || d < 0 || d >= N) continue;   // flagged by k_make_keys
+    if (by == 0) {
+      const int64_t k = e + (tail ? s - n0 : 0);
+      nbr[k] = (int32_t)d;
+      perm[k] = (int32_t)e;
+      continue;
+    }
+    // first position of value v among the targets of prefix row r
+    auto lower = [&](int64_t r, int64_t v) {
+      int64_t lo = rowptr[r] - (tail ? r : 0), hi = rowptr[r + 1] - (tail ? r + 1 : 0);
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)ei[E + mid] < v) lo = mid + 1; else hi = mid;
+      }
+      return lo;
+    };
+    const int64_t off = dups ? e - lower(s, d) : 0;
+    const int64_t k = lower(d, s) + off + (tail ? d : 0);
+    nbr[k] = (int32_t)s;
+    perm[k] = (int32_t)e;
+  }
+}
+
+// out[0..3]: the multiset fingerprints (k_edge_fingerprint); out[4] entries e with (src,dst)[e] > (src,dst)[e+1]
+// over the whole list, out[5] the same over the first E-N entries, out[6] entries of the last N that are not the
+// loop (e-(E-N), e-(E-N)), out[7] adjacent equal entries (whole list).
+template <typename IndexT>
+__global__ void __launch_bounds__(256) k_edge_order_check(const IndexT* __restrict__ ei, int64_t E, int64_t N, int G,
+                                                          const int32_t* __restrict__ node_off,
+                                                          const int32_t* __restrict__ edge_off,
+                                                          unsigned long long* __restrict__ out) {
+  unsigned long long f[4] = {0ull, 0ull, 0ull, 0ull};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
+    const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
+    int64_t n0 = 0, e0 = 0, ng = N, eg = E;
+    if (G > 0) {
+      const int g = segment_of(edge_off, G, e);
+      n0 = node_off[g];
+      e0 = edge_off[g];
+      ng = node_off[g + 1] - n0;
+      eg = edge_off[g + 1] - e0;
+      // every endpoint of a graph's entries lies in the graph's own node range
+      if (s < n0 || s >= n0 + ng || d < n0 || d >= n0 + ng) {
+        f[0] += 1u;
+        f[1] += 1u;
+      }
+    }
+    const int64_t Ep = eg >= ng ? e0 + eg - ng : -1;   // end of the sorted prefix under the "+ loops" reading
+    if (e + 1 < e0 + eg) {
+      const int64_t s1 = (int64_t)ei[e + 1], d1 = (int64_t)ei[E + e + 1];
+      const bool gt = s > s1 || (s == s1 && d > d1);
+      f[0] += gt ? 1u : 0u;
+      if (Ep >= 0 && e + 1 < Ep) f[1] += gt ? 1u : 0u;
+      f[3] += (s == s1 && d == d1) ? 1u : 0u;
+    }
+    if (Ep < 0) f[2] += 1u;
+    else if (e >= Ep) f[2] += (s == n0 + e - Ep && d == n0 + e - Ep) ? 0u : 1u;
+  }
+  __shared__ unsigned long long red[8][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    unsigned long long v = f[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long v = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (v) atomicAdd(out + 4 + threadIdx.x, v);
+  }
+}
+
 template <typename IndexT>
 static int csr_build_any(const IndexT* edge_index, int64_t E, int64_t N, int by,
                          int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
-                         void* workspace, size_t* workspace_bytes, void* stream) {
+                         void* workspace, size_t* workspace_bytes, void* stream, int presorted = 0, int64_t G = 0,
+                         const int32_t* node_off = nullptr, const int32_t* edge_off = nullptr) {
+  MGCN_REQUIRE(G >= 0 && G < (1 << 24) && (G == 0 || (node_off && edge_off && presorted && by == 0)), MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(presorted >= 0 && presorted <= 6, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(presorted == 0 || loop_mode == 0, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(!((presorted & 3) == 2) || E >= N, MGCN_ERR_SHAPE);
+  MGCN_REQUIRE(G == 0 || (presorted & 3) == 2, MGCN_ERR_SHAPE);
   MGCN_REQUIRE(workspace_bytes != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(by == 0 || by == 1, MGCN_ERR_SHAPE);
   MGCN_REQUIRE(loop_mode >= 0 && loop_mode <= 2, MGCN_ERR_SHAPE);
@@ -657,13 +781,19 @@ static int csr_build_any(const IndexT* edge_index, int64_t E, int64_t N, int by,
   MGCN_CHECK_CUDA(cudaMemsetAsync(seg_count, 0, sizeof(int32_t), st));
   MGCN_CHECK_CUDA(cudaMemsetAsync(bad_index, 0, sizeof(int32_t), st));
   if (total > 0) {
-    MGCN_LAUNCH(k_make_keys<IndexT>, grid_for(total, 256), 256, 0, stream, edge_index, E, N, by,
+    // (a presorted list is counted by source: its prefix is indexed through these row starts; a symmetric list has
+    // the same counts by target)
+    MGCN_LAUNCH(k_make_keys<IndexT>, grid_for(total, 256), 256, 0, stream, edge_index, E, N, presorted ? 0 : by,
                 loop_mode, total, keys_a, rowptr, bad_index);
   }
   int rc = exclusive_scan_i32(rowptr, rowptr, N + 1, tile_sums, stream);
   if (rc != MGCN_OK) return rc;
 
-  if (total > 0) {
+  if (total > 0 && presorted) {
+    // layout bits: 1 = sorted, 2 = sorted prefix + N trailing loops, +4 = repeated entries possible
+    MGCN_LAUNCH(k_fill_presorted<IndexT>, grid_for(total, 256), 256, 0, stream, edge_index, E, N, by,
+                (presorted & 3) == 2 ? 1 : 0, (presorted & 4) ? 1 : 0, (int)G, node_off, edge_off, rowptr, nbr, perm);
+  } else if (total > 0) {
     const int32_t* sorted_pos = nullptr;
     rc = radix_sort_positions(keys_a, keys_b, vals_a, vals_b, total, (uint64_t)N, block_hist,
                               tile_sums, &sorted_pos, stream);
@@ -721,6 +851,24 @@ extern "C" int mgcn_csr_build_i32(const int32_t* edge_index, int64_t E, int64_t 
                                   int loop_mode, const mgcn_csr_t* out, int32_t* bad_index,
                                   void* workspace, size_t* workspace_bytes, void* stream) {
   return csr_build_any<int32_t>(edge_index, E, N, by, loop_mode, out, bad_index, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mgcn_csr_build_presorted(const int64_t* edge_index, int64_t E, int64_t N, int by, int layout,
+                                        int64_t G, const int32_t* node_off, const int32_t* edge_off,
+                                        const mgcn_csr_t* out, int32_t* bad_index, void* workspace,
+                                        size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(layout >= 1 && layout <= 6 && (layout & 3) != 0 && (layout & 3) != 3, MGCN_ERR_SHAPE);
+  return csr_build_any<int64_t>(edge_index, E, N, by, 0, out, bad_index, workspace, workspace_bytes, stream, layout, G,
+                                node_off, edge_off);
+}
+
+extern "C" int mgcn_csr_build_presorted_i32(const int32_t* edge_index, int64_t E, int64_t N, int by, int layout,
+                                            int64_t G, const int32_t* node_off, const int32_t* edge_off,
+                                            const mgcn_csr_t* out, int32_t* bad_index, void* workspace,
+                                            size_t* workspace_bytes, void* stream) {
+  MGCN_REQUIRE(layout >= 1 && layout <= 6 && (layout & 3) != 0 && (layout & 3) != 3, MGCN_ERR_SHAPE);
+  return csr_build_any<int32_t>(edge_index, E, N, by, 0, out, bad_index, workspace, workspace_bytes, stream, layout, G,
+                                node_off, edge_off);
 }
 
 extern "C" int mgcn_degree_from_rowptr(const int32_t* rowptr, int64_t N, float* deg, void* stream) {
@@ -803,6 +951,32 @@ extern "C" int mgcn_edge_fingerprint(const int64_t* edge_index, int64_t E, uint6
 
 extern "C" int mgcn_edge_fingerprint_i32(const int32_t* edge_index, int64_t E, uint64_t* out4, void* stream) {
   return edge_fingerprint_any<int32_t>(edge_index, E, out4, stream);
+}
+
+template <typename IndexT>
+static int edge_layout_any(const IndexT* edge_index, int64_t E, int64_t N, int64_t G, const int32_t* node_off,
+                           const int32_t* edge_off, uint64_t* out8, void* stream) {
+  MGCN_REQUIRE(out8 != nullptr, MGCN_ERR_NULL);
+  MGCN_REQUIRE(N >= 0 && G >= 0 && G < (1 << 24), MGCN_ERR_RANGE);
+  MGCN_REQUIRE(G == 0 || (node_off && edge_off), MGCN_ERR_NULL);
+  MGCN_CHECK_CUDA(cudaMemsetAsync(out8 + 4, 0, 4 * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
+  const int rc = edge_fingerprint_any<IndexT>(edge_index, E, out8, stream);
+  if (rc != MGCN_OK || E == 0) return rc;
+  int64_t blocks = ceil_div(E, 256 * 8);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  MGCN_LAUNCH(k_edge_order_check<IndexT>, (unsigned)blocks, 256, 0, stream, edge_index, E, N, (int)G, node_off,
+              edge_off, reinterpret_cast<unsigned long long*>(out8));
+  return MGCN_OK;
+}
+
+extern "C" int mgcn_edge_layout(const int64_t* edge_index, int64_t E, int64_t N, int64_t G, const int32_t* node_off,
+                                const int32_t* edge_off, uint64_t* out8, void* stream) {
+  return edge_layout_any<int64_t>(edge_index, E, N, G, node_off, edge_off, out8, stream);
+}
+
+extern "C" int mgcn_edge_layout_i32(const int32_t* edge_index, int64_t E, int64_t N, int64_t G,
+                                    const int32_t* node_off, const int32_t* edge_off, uint64_t* out8, void* stream) {
+  return edge_layout_any<int32_t>(edge_index, E, N, G, node_off, edge_off, out8, stream);
 }
 
 extern "C" int mgcn_gcn_norm(const float* deg, int64_t N, int mode, float* dis, void* stream) {

@@ -18,7 +18,7 @@ class _Aggregate(torch.autograd.Function):
     def forward(ctx, x, bias, residual, graph, nbr_scale, row_scale, ev_fwd, ev_bwd, reduce, act, edge_weight=None):
         # edge_weight (edge_index order) is passed only when its gradient is wanted (edge gates); ev_fwd / ev_bwd are
         # its row-order copies for the two structures
-        out = ops.spmm_impl(graph.fwd, x, False, ev_fwd, nbr_scale, row_scale, reduce, bias,
+        out = ops.spmm_impl(graph.fwd if ev_fwd is not None else graph.fwd_plain, x, False, ev_fwd, nbr_scale, row_scale, reduce, bias,
                             residual, act)
         ctx.graph = graph
         ctx.cfg = (reduce, act, bias is not None, residual is not None)

@@ -29,7 +29,7 @@ class _ResidualGCNStack(torch.autograd.Function):
         L = len(params) // per
         layers = [params[i * per:(i + 1) * per] for i in range(L)]
         xs, hs = [x.contiguous()], []
-        fwd = graph.fwd
+        fwd = graph.fwd_plain
         xw = ops.linear_impl(xs[0], layers[0][0], False, row_scale=pre)
         for n, lp in enumerate(layers):
             w, b = lp[0], (lp[1] if has_bias else None)
@@ -87,7 +87,7 @@ class _ResidualGCNStack32(torch.autograd.Function):
     def forward(ctx, x, graph, pre, post, last_relu, *params):
         L = len(params) // 3
         layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
-        fwd = graph.fwd
+        fwd = graph.fwd_plain
         x0 = x.contiguous()
         xs, hmasks = [x0], []
         # A first layer of small input width is aggregated BEFORE its transform — (A_hat x) W instead of
@@ -165,7 +165,7 @@ class _ResidualGCNStack32AT(torch.autograd.Function):
     def forward(ctx, x, graph, pre, post, last_relu, *params):
         L = len(params) // 3
         layers = [params[i * 3:(i + 1) * 3] for i in range(L)]
-        fwd = graph.fwd
+        fwd = graph.fwd_plain
         x0 = x.contiguous()
         sigma = None
         if pre is not None:

@@ -88,7 +88,9 @@ def _as_csr(csr, hub_threshold=None):
 # ------------------------------------------------------------------------------------------------
 # implementations (plain functions; also what meta_gcn_b200.functional calls directly)
 # ------------------------------------------------------------------------------------------------
-def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRESHOLD):
+def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRESHOLD, layout=0, segments=None):
+    """layout != 0 (from edge_layout_impl; loop_mode 0 only): the list is already in (src,dst) order — no sort.
+    segments = (node_off, edge_off) int32 device tensors [G+1] for a batch of graphs (by = 0 only)."""
     _need_cuda(edge_index)
     if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise TypeError("edge_index must be int64 (the reference's dtype) or int32, shape [2,E]")
@@ -97,7 +99,15 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRES
     N = int(N)
     dev = ei.device
     lib = _lib.load()
-    build = lib.mgcn_csr_build if ei.dtype == torch.int64 else lib.mgcn_csr_build_i32
+    if layout:
+        if int(loop_mode) != 0:
+            raise ValueError("a presorted build keeps the edges as given (loop_mode 0)")
+        build = lib.mgcn_csr_build_presorted if ei.dtype == torch.int64 else lib.mgcn_csr_build_presorted_i32
+        g_ = 0 if segments is None else segments[0].numel() - 1
+        mode_arg = (int(layout), g_, _ptr(segments[0]) if g_ else None, _ptr(segments[1]) if g_ else None)
+    else:
+        build = lib.mgcn_csr_build if ei.dtype == torch.int64 else lib.mgcn_csr_build_i32
+        mode_arg = (int(loop_mode),)
     caps = [ctypes.c_int64(0) for _ in range(3)]
     _lib.check(lib.mgcn_csr_capacities(E, N, int(loop_mode), int(hub_threshold),
                                        *[ctypes.byref(c) for c in caps]))
@@ -110,10 +120,10 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRES
               torch.empty(1, **i32))
     nbytes = ctypes.c_size_t(0)
     st = csr.struct()
-    _lib.check(build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
+    _lib.check(build(_ptr(ei), E, N, int(by), *mode_arg, ctypes.byref(st),
                      _ptr(csr.bad), None, ctypes.byref(nbytes), None))
     ws = torch.empty(max(nbytes.value, 1), dtype=torch.uint8, device=dev)
-    _lib.check(build(_ptr(ei), E, N, int(by), int(loop_mode), ctypes.byref(st),
+    _lib.check(build(_ptr(ei), E, N, int(by), *mode_arg, ctypes.byref(st),
                      _ptr(csr.bad), _ptr(ws), ctypes.byref(nbytes), _stream()))
     return csr
 
@@ -200,6 +210,32 @@ def edge_symmetry_impl(edge_index):
     _lib.check(fn(_ptr(ei), ei.size(1), _ptr(out), _stream()))
     f = out.tolist()
     return f[0] == f[1] and f[2] == f[3]
+
+
+def edge_layout_impl(edge_index, N, segments=None):
+    """One pass pair + ONE host read per edge_index (mgcn_edge_layout): {'symmetric': the directed multiset equals its
+    transpose, 'layout': 0 unsorted | 1 sorted by (src,dst) | 2 sorted prefix + N trailing self loops (+4: repeated
+    entries)} — what decides whether the structures need a sort and whether the by-source one is needed at all."""
+    _need_cuda(edge_index)
+    if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise TypeError("edge_index must be int64 or int32, shape [2, E]")
+    ei = edge_index.contiguous()
+    out = torch.empty(8, dtype=torch.int64, device=ei.device)
+    lib = _lib.load()
+    fn = lib.mgcn_edge_layout if ei.dtype == torch.int64 else lib.mgcn_edge_layout_i32
+    g_ = 0 if segments is None else segments[0].numel() - 1
+    _lib.check(fn(_ptr(ei), ei.size(1), int(N), g_, _ptr(segments[0]) if g_ else None,
+                  _ptr(segments[1]) if g_ else None, _ptr(out), _stream()))
+    f = out.tolist()
+    E = ei.size(1)
+    layout = 0
+    if E > 0 and f[4] == 0:
+        layout = 1
+    elif E >= N > 0 and f[5] == 0 and f[6] == 0:
+        layout = 2
+    if layout and f[7] != 0:
+        layout |= 4
+    return {"symmetric": f[0] == f[1] and f[2] == f[3], "layout": layout}
 
 
 def gcn_norm_impl(deg, mode):

@@ -1,90 +1,59 @@
-"""Where the e2e step goes beyond the resident step: variants of bench.py's e2e loop at the C2 shape.
+"""Where the end-to-end step's time goes (C2 batch): eager resident step, + structure build per step, + loader.
     python scripts/prof_e2e.py"""
-import itertools
-import os
-import sys
-import time
-
+import itertools, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import CFG, make_graphs  # noqa: E402
-
+from bench import CFG, make_graphs
 graphs = make_graphs(list(range(25)), 143107, 1_500_000)
-import torch  # noqa: E402
-from meta_gcn_b200 import functional as F  # noqa: E402
-from meta_gcn_b200.data import DeviceLoader, GraphBatch  # noqa: E402
-from meta_gcn_b200.gcn_meta.models import GCNModel  # noqa: E402
-from meta_gcn_b200.graph import clear_structure_cache, structure_of  # noqa: E402
-
+import torch
+from meta_gcn_b200 import dist as mdist, functional as F
+from meta_gcn_b200.data import DeviceLoader, GraphBatch
+from meta_gcn_b200.gcn_meta.models import GCNModel
+from meta_gcn_b200.graph import clear_structure_cache
 dev = torch.device("cuda")
-host = GraphBatch.from_data_list(graphs).pin_memory()
+torch.cuda.set_stream(torch.cuda.Stream(dev))
+host = GraphBatch.from_data_list(graphs).with_int32_indices().pin_memory()
 torch.manual_seed(0)
 model = GCNModel(**CFG).to(dev)
+reducer = mdist.FlatGradientReducer(model.parameters())
 opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4, fused=True)
 
-
-def step(b):
-    opt.zero_grad(set_to_none=False)
+def step(b, sync=True):
+    reducer.zero()
     out = model(b.x[:, 0].view(-1, 1), b.edge_index, deg_K=b.x[:, 1])
     loss = F.cross_entropy(out, b.y.long(), "sum")
     loss.backward()
+    m, _ = reducer.reduce_mean(loss, b.num_nodes)
     opt.step()
-    return loss
+    return float(m.item()) if sync else m
 
-
-def timed(name, fn, k=12):
-    fn(2)
-    torch.cuda.synchronize()
+def wall(fn, k=10):
+    fn(); fn(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    fn(k)
+    for _ in range(k):
+        fn()
     torch.cuda.synchronize()
-    print(f"{name:58s} {(time.perf_counter() - t0) / k * 1e3:8.2f} ms/step", flush=True)
+    return (time.perf_counter() - t0) / k * 1e3
 
-
-resident = host.to(dev)
-loader = DeviceLoader((), dev)
-
-
-def v_resident(k):
-    for _ in range(k):
-        step(resident)
-
-
-def v_resident_sync(k):
-    for _ in range(k):
-        float(step(resident).item())
-
-
-def v_resident_rebuild(k):
-    for _ in range(k):
-        clear_structure_cache()
-        float(step(resident).item())
-
-
-def v_loader_nobuild(k):
-    loader.batches = itertools.repeat(host, k)
-    for b in loader:
-        float(step(b).item())
-
-
-def v_full(k):
-    loader.batches = itertools.repeat(host, k)
-    for b in loader:
-        clear_structure_cache()
-        float(step(b).item())
-
-
-timed("resident batch, structures cached, no per-step sync", v_resident)
-timed("  + loss.item() every step", v_resident_sync)
-timed("  + structure rebuilt every step", v_resident_rebuild)
-timed("DeviceLoader H2D every step, structures cached (slot reuse)", v_loader_nobuild)
-timed("DeviceLoader + rebuild (= bench e2e)", v_full)
-gs = structure_of(resident.edge_index, resident.num_nodes)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-for _ in range(5):
+b = host.to(dev)
+b.x = b.x.contiguous()
+print(f"eager resident step, loss read every step : {wall(lambda: step(b)):.2f} ms")
+print(f"eager resident step, no host read          : {wall(lambda: step(b, False)):.2f} ms")
+def with_build():
     clear_structure_cache()
-    g2 = structure_of(resident.edge_index, resident.num_nodes)
-    g2.fwd
-    g2.symmetric
+    b.structure()
+    return step(b)
+print(f"+ structure build every step               : {wall(with_build):.2f} ms")
+t0 = time.perf_counter(); 
+for _ in range(10):
+    reducer.zero(); out = model(b.x[:, 0].view(-1, 1), b.edge_index, deg_K=b.x[:, 1])
+t_host = (time.perf_counter() - t0) / 10 * 1e3
 torch.cuda.synchronize()
-print(f"structure build (fwd) + symmetry check alone                  {(time.perf_counter() - t0) / 5 * 1e3:8.2f} ms")
+print(f"host time to ENQUEUE a forward             : {t_host:.2f} ms")
+loader = DeviceLoader((), dev, fields=("x", "edge_index", "y"))
+def e2e(k):
+    loader.batches = itertools.repeat(host, k)
+    for bb in loader:
+        step(bb)
+e2e(2); torch.cuda.synchronize()
+t0 = time.perf_counter(); e2e(20); torch.cuda.synchronize()
+print(f"loader e2e (20 steps)                      : {(time.perf_counter() - t0) / 20 * 1e3:.2f} ms")

@@ -207,7 +207,14 @@ def test_edge_symmetry_fingerprint_and_structure_reuse():
     assert ops.edge_symmetry_impl(dup) is (bool(ei[0, 0] == ei[1, 0]))
     assert ops.edge_symmetry_impl(torch.zeros(2, 0, dtype=torch.int64, device=DEV)) is True
     gs = G.GraphStructure(ei, 5000)
-    assert gs.symmetric and gs.bwd_plain is gs.fwd
+    # (this list is also in (src,dst) order: the plain structures are then the sort-free by-source build)
+    assert gs.symmetric and gs.bwd_plain is gs.fwd_plain
+    G.USE_PRESORTED = False
+    try:
+        gsu = G.GraphStructure(ei, 5000)
+        assert gsu.symmetric and gsu.bwd_plain is gsu.fwd and gsu._bwd is None
+    finally:
+        G.USE_PRESORTED = True
     x = torch.randn(5000, 32, device=DEV)
     a = ops.aggregate_prescaled_impl(gs.bwd_plain, x, None, 0, None, None, 0)
     b = ops.aggregate_prescaled_impl(gs.bwd, x, None, 0, None, None, 0)
@@ -244,3 +251,95 @@ def test_int32_edge_index_builds_the_same_structures():
         o64 = model(x[:, 0:1].contiguous(), ei64, deg_K=x[:, 1].contiguous())
         o32 = model(x[:, 0:1].contiguous(), ei32, deg_K=x[:, 1].contiguous())
     assert torch.equal(o64, o32)
+
+
+@pytest.mark.parametrize("case", ["botnet", "sorted", "sorted_dups", "sorted_asym", "unsorted"])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_presorted_build_equals_the_sorting_build(case, dtype):
+    """mgcn_edge_layout + mgcn_csr_build_presorted: a list already in (src,dst) order (optionally + the N trailing self
+    loops of data_procs/loop.py:13-17) is grouped without a sort — rowptr / nbr / perm bit-identical to the radix-sort
+    build, by source always, by target when the list is symmetric"""
+    from meta_gcn_b200 import data as D
+    from meta_gcn_b200 import graph as G
+    from meta_gcn_b200 import ops as O
+    rng = np.random.default_rng(11)
+    n = 5000
+    if case == "botnet":
+        g = D.synth_botnet_graph(seed=5, num_nodes=n, edge_entries=60000, evil=300)
+        ei = g["edge_index"]
+    else:
+        src, dst = rng.integers(0, n, 40000), rng.integers(0, n, 40000)
+        if case != "sorted_asym":
+            src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])     # symmetric multiset
+        if case == "sorted_dups":
+            src, dst = np.concatenate([src, src[:5000], dst[:5000]]), np.concatenate([dst, dst[:5000], src[:5000]])
+        elif case != "unsorted":
+            key = np.unique(src * n + dst)
+            src, dst = key // n, key % n
+        if case != "unsorted":
+            o = np.lexsort((dst, src))
+            src, dst = src[o], dst[o]
+        ei = np.stack([src, dst])
+    ei = torch.from_numpy(ei.astype(np.int64)).to("cuda").to(dtype)
+    facts = O.edge_layout_impl(ei, n)
+    want = {"botnet": 2, "sorted": 1, "sorted_dups": 5, "sorted_asym": 1, "unsorted": 0}[case]
+    assert facts["layout"] == want, facts
+    assert facts["symmetric"] == (case != "sorted_asym")
+    for by in (0, 1):
+        ref = O.csr_build_impl(ei, n, by, 0)
+        if want and (by == 0 or facts["symmetric"]):
+            fast = O.csr_build_impl(ei, n, by, 0, layout=want)
+            for name in ("rowptr", "nbr", "perm", "order"):
+                assert torch.equal(getattr(fast, name), getattr(ref, name)), (case, by, name)
+    if want and facts["symmetric"]:
+        # sorted + symmetric: the by-source rows ARE the by-target rows, entry for entry (GraphStructure.fwd_plain)
+        a0, a1 = O.csr_build_impl(ei, n, 0, 0), O.csr_build_impl(ei, n, 1, 0)
+        assert torch.equal(a0.rowptr, a1.rowptr) and torch.equal(a0.nbr, a1.nbr)
+        gsp = G.GraphStructure(ei, n)
+        assert gsp.fwd_plain is gsp.bwd and gsp._fwd is None
+    # the structure cache picks the sort-free path on its own and the model result does not change
+    gs = G.GraphStructure(ei, n)
+    x = torch.randn(n, 32, device="cuda")
+    out_fast = O.aggregate_prescaled_impl(gs.fwd_plain, x)
+    assert torch.equal(out_fast, O.aggregate_prescaled_impl(gs.fwd, x))
+    G.USE_PRESORTED = False
+    try:
+        out_ref = O.aggregate_prescaled_impl(G.GraphStructure(ei, n).fwd, x)
+    finally:
+        G.USE_PRESORTED = True
+    assert torch.equal(out_fast, out_ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_ordered_batch_is_grouped_without_a_sort(dtype):
+    """a BATCH of graphs in the reference's preprocessed layout (Batch.from_data_list of sorted-unique lists with their
+    loops appended, dataloader.py:11 + data_procs/loop.py:13-17): GraphBatch.structure() hands the batch boundaries to
+    the structure, the per-graph order check passes, and the sort-free by-source build equals the radix-sort one"""
+    from meta_gcn_b200 import data as D
+    from meta_gcn_b200 import graph as G
+    from meta_gcn_b200 import ops as O
+    graphs = [D.synth_botnet_graph(seed=s, num_nodes=3000 + 500 * s, edge_entries=30000 + 1000 * s, evil=200) for s in range(4)]
+    batch = D.GraphBatch.from_data_list(graphs)
+    if dtype == torch.int32:
+        batch = batch.with_int32_indices()
+    batch = batch.to("cuda")
+    n = batch.num_nodes
+    assert O.edge_layout_impl(batch.edge_index, n)["layout"] == 0            # not ordered as ONE list ...
+    gs = batch.structure()
+    assert gs.facts == {"symmetric": True, "layout": 2}                       # ... but graph by graph
+    assert G.structure_of(batch.edge_index, n) is gs                          # what the model classes will find
+    ref0 = O.csr_build_impl(batch.edge_index, n, 0, 0)
+    ref1 = O.csr_build_impl(batch.edge_index, n, 1, 0)
+    for name in ("rowptr", "nbr", "perm", "order"):
+        assert torch.equal(getattr(gs.bwd, name), getattr(ref0, name)), name
+    assert gs.fwd_plain is gs.bwd and gs.bwd_plain is gs.bwd
+    assert torch.equal(gs.fwd_plain.rowptr, ref1.rowptr) and torch.equal(gs.fwd_plain.nbr, ref1.nbr)
+    for name in ("rowptr", "nbr", "perm"):                                    # the exact by-target structure still sorts
+        assert torch.equal(getattr(gs.fwd, name), getattr(ref1, name)), name
+    # a batch with one graph out of order falls back to the sort
+    bad = [dict(g) for g in graphs]
+    bad[2]["edge_index"] = np.ascontiguousarray(bad[2]["edge_index"][:, ::-1])
+    bb = D.GraphBatch.from_data_list(bad).to("cuda")
+    gb = bb.structure()
+    assert gb.facts["layout"] == 0
+    assert torch.equal(gb.bwd.nbr, O.csr_build_impl(bb.edge_index, bb.num_nodes, 0, 0).nbr)
