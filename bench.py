@@ -244,10 +244,12 @@ def run_ours(args):
     def crit_sum(out, target):   # nn.CrossEntropyLoss(reduction="sum") as deterministic kernels
         return F_mgcn.cross_entropy(out, target, "sum")
 
+    # model.forward_loss = model(...) + CrossEntropyLoss(reduction="sum") (train_botnet.py:286-287) with the output
+    # layer and the loss in one launch (csrc/head.cu); same values as the two separate calls (tests/test_gpu_head.py)
     def step(batch_dev):
         reducer.zero()
-        out = model(batch_dev.x[:, 0].view(-1, 1), batch_dev.edge_index, deg_K=batch_dev.x[:, 1])
-        loss_sum = crit_sum(out, batch_dev.y.long())
+        loss_sum, _logits = model.forward_loss(batch_dev.x[:, 0].view(-1, 1), batch_dev.edge_index, batch_dev.y.long(),
+                                               deg_K=batch_dev.x[:, 1], reduction="sum")
         loss_sum.backward()
         mean_loss, _ = reducer.reduce_mean(loss_sum, batch_dev.num_nodes)
         opt.step()
@@ -255,8 +257,8 @@ def run_ours(args):
 
     def fwd_loss_bwd(batch_dev):
         reducer.zero()
-        out = model(batch_dev.x[:, 0].view(-1, 1), batch_dev.edge_index, deg_K=batch_dev.x[:, 1])
-        loss_sum = crit_sum(out, batch_dev.y.long())
+        loss_sum, _logits = model.forward_loss(batch_dev.x[:, 0].view(-1, 1), batch_dev.edge_index, batch_dev.y.long(),
+                                               deg_K=batch_dev.x[:, 1], reduction="sum")
         loss_sum.backward()
         return loss_sum
 

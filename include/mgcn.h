@@ -380,6 +380,21 @@ int mgcn_cross_entropy_fwd(const float* logits, const int64_t* target, int64_t N
 int mgcn_cross_entropy_bwd(const float* logits, const int64_t* target, int64_t N, int64_t C, int mean,
                            const float* upstream, float* dlogits, void* stream);
 
+/* The step right behind the hot path, fused: self.final = nn.Linear(H, C) (gcn_model.py:73,108),
+ * nn.CrossEntropyLoss (train_botnet.py:225,287) and the binary counters of optim/metrics.py:8-24
+ * (train_botnet.py:296-305) as ONE forward launch that reads x [N,H] once — logits [N,C] = x w^T + b are written
+ * because the caller returns them; loss[0] = sum (or mean) of the rows' NLL, fixed-order; counts5 = {TP, FP, TN, FN,
+ * correct} (int64, may be NULL) — and ONE backward launch that reads x and the logits once:
+ *   dl = (softmax(logits) - onehot(target)) * (1/N if mean) * upstream[0]
+ *   dx = dl w  (may be NULL);   dw = dl^T x;   db = colsum(dl)      (fixed-order partials: deterministic)
+ * H in {16, 32, 64, 128}, C <= 8, w [C,H] (nn.Linear.weight), b [C] or NULL. */
+int mgcn_head_cross_entropy_fwd(const float* x, int64_t N, int64_t H, const float* w, const float* b, int64_t C,
+                                const int64_t* target, int mean, float* logits, float* loss, int64_t* counts5,
+                                int32_t* bad_target, void* workspace, size_t* workspace_bytes, void* stream);
+int mgcn_head_cross_entropy_bwd(const float* x, const float* logits, int64_t N, int64_t H, const float* w, int64_t C,
+                                const int64_t* target, int mean, const float* upstream, float* dx, float* dw,
+                                float* db, void* workspace, size_t* workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * 'max' aggregation: scatter_('max', src, index, dim_size) (common.py:54-64 — torch_scatter scatter_max with fill
  * -1e38, untouched rows set to 0) and NodeModelAdditive(aggr='max') (gcn_base_models.py:223-237), with

@@ -105,6 +105,10 @@ SIGNATURES = {
     "mgcn_batch_to_offsets": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "mgcn_segment_reduce": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_segment_broadcast": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr]),
+    "mgcn_head_cross_entropy_fwd": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr,
+                                            c_ptr, c_ptr, c_ptr, c_size_p, c_ptr]),
+    "mgcn_head_cross_entropy_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr,
+                                            c_ptr, c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_batchnorm_fwd": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_f32, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                    c_ptr, c_ptr, c_size_p, c_ptr]),
     "mgcn_batchnorm_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr,

@@ -122,6 +122,39 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, dadd, None, None
 
 
+class _HeadCrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, target, mean, want_counts):
+        x = x.contiguous()
+        logits, loss, counts, _bad = ops.head_cross_entropy_fwd_impl(x, weight, bias, target, mean, want_counts)
+        ctx.mean = bool(mean)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, logits, weight, target)
+        ctx.mark_non_differentiable(logits)
+        if counts is not None:
+            ctx.mark_non_differentiable(counts)
+            return loss.view(()), logits, counts
+        return loss.view(()), logits
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        x, logits, weight, target = ctx.saved_tensors
+        dx, dw, db = ops.head_cross_entropy_bwd_impl(x, logits, weight, target, ctx.mean, g.contiguous().view(1),
+                                                     ctx.needs_input_grad[0])
+        return dx, dw, db if ctx.has_bias else None, None, None, None
+
+
+def head_cross_entropy(x, linear, target, reduction="mean", confusion=False):
+    """``CrossEntropyLoss(reduction)(linear(x), target)`` with the output layer, the loss and (optionally) the binary
+    counters TP / FP / TN / FN / correct of optim/metrics.py:8-24 in one forward and one backward launch
+    (csrc/head.cu; gcn_model.py:73,108 + train_botnet.py:287,296-305).  ``linear``: an nn.Linear(H, C), H in
+    {16,32,64,128}, C <= 8.  Returns (loss, logits[, counts int64[5]]); the logits are detached (the loss carries the
+    gradient to x and to the layer's parameters)."""
+    if reduction not in ("mean", "sum"):
+        raise ValueError("reduction must be 'mean' or 'sum'")
+    return _HeadCrossEntropy.apply(x, linear.weight, linear.bias, target, reduction == "mean", bool(confusion))
+
+
 class _BatchNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):

@@ -148,12 +148,13 @@ class GCNModel(nn.Module):
         return fused.residual_gcn_stack(x, graph, pre, post, params, has_bias, aggregate_first=aggregate_first)
 
     def forward(self, x, edge_index_K, edge_attr_K=None, deg_K=None, edge_weight_K=None, **kwargs):
+        hidden = kwargs.pop("_hidden", False)        # forward_loss: stop before the output layer
         dis = self._shared_degree_factors(x, edge_index_K, deg_K, edge_weight_K)
         if self._stack_eligible(edge_index_K, edge_attr_K, edge_weight_K) and not kwargs.get("_no_stack"):
             ei = edge_index_K if isinstance(edge_index_K, torch.Tensor) else edge_index_K[0]
             deg = deg_K if isinstance(deg_K, torch.Tensor) or deg_K is None else deg_K[0]
             x = self._forward_stack(x, ei, dis, deg)
-            return self._head(x, kwargs)
+            return x if hidden else self._head(x, kwargs)
         kwargs.pop("_no_stack", None)
         hop = self.residual_hop
         xr_src, add_xr_at, res_idx = None, -1, -1
@@ -174,7 +175,25 @@ class GCNModel(nn.Module):
                     if not last and not fuse_relu:
                         xo = self.non_linear(xo)
             x = xo
-        return self._head(x, kwargs)
+        return x if hidden else self._head(x, kwargs)
+
+    def forward_loss(self, x, edge_index_K, target, edge_attr_K=None, deg_K=None, edge_weight_K=None,
+                     reduction="mean", confusion=False, **kwargs):
+        """forward + ``nn.CrossEntropyLoss(reduction)`` in one call: for node-level models with a 'proj' output layer
+        the output Linear, the loss and (``confusion=True``) the binary counters of optim/metrics.py run as ONE launch
+        (functional.head_cross_entropy; train_botnet.py:286-305 makes five passes and five host reads of them).
+        Returns (loss, logits[, counts]) — same values as ``forward`` followed by the loss."""
+        fusable = (self.final_type == "proj" and self.pred_on == "node" and self.final.in_features in (16, 32, 64, 128)
+                   and self.final.out_features <= 8)
+        if not fusable:
+            out = self.forward(x, edge_index_K, edge_attr_K, deg_K, edge_weight_K, **kwargs)
+            loss = F_mgcn.cross_entropy(out, target, reduction)
+            if confusion:
+                from ... import ops
+                return loss, out, ops.binary_confusion_impl(target, logits=out.detach())
+            return loss, out
+        h = self.forward(x, edge_index_K, edge_attr_K, deg_K, edge_weight_K, _hidden=True, **kwargs)
+        return F_mgcn.head_cross_entropy(h, self.final, target, reduction, confusion)
 
     def _head(self, x, kwargs):
         if self.final_type == "proj":

@@ -622,6 +622,47 @@ def segment_broadcast_impl(gout, offsets, N, mode):
     return dx
 
 
+def head_cross_entropy_fwd_impl(x, w, b, target, mean, want_counts=False):
+    """mgcn_head_cross_entropy_fwd: returns (logits [N,C], loss [1], counts int64[5] | None, bad int32[1])"""
+    _need_cuda(x, w, b, target)
+    x = _f32c(x, "x")
+    w = _f32c(w, "w")
+    b = _f32c(b, "b")
+    if target.dtype != torch.int64:
+        raise TypeError("target must be int64 (batch.y.long())")
+    target = target.contiguous()
+    N, H = x.shape
+    C = w.size(0)
+    dev = x.device
+    logits = torch.empty(N, C, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    counts = torch.empty(5, dtype=torch.int64, device=dev) if want_counts else None
+    bad = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    args = (_ptr(x), N, H, _ptr(w), _ptr(b), C, _ptr(target), int(bool(mean)), _ptr(logits), _ptr(loss), _ptr(counts),
+            _ptr(bad))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_head_cross_entropy_fwd(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_head_cross_entropy_fwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return logits, loss, counts, bad
+
+
+def head_cross_entropy_bwd_impl(x, logits, w, target, mean, upstream, want_dx=True):
+    """mgcn_head_cross_entropy_bwd: returns (dx | None, dw [C,H], db [C])"""
+    _need_cuda(x, logits, w, target, upstream)
+    N, H = x.shape
+    C = w.size(0)
+    dev = x.device
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.empty(C, H, dtype=torch.float32, device=dev)
+    db = torch.empty(C, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    args = (_ptr(x), _ptr(logits), N, H, _ptr(w), C, _ptr(target), int(bool(mean)), _ptr(upstream), _ptr(dx), _ptr(dw),
+            _ptr(db))
+    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_head_cross_entropy_bwd(*args, w_, nb, stm), dev)
+    _lib.check(lib.mgcn_head_cross_entropy_bwd(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return dx, dw, db
+
+
 def batchnorm_fwd_impl(x, gamma, beta, running_mean, running_var, training, momentum, eps):
     """mgcn_batchnorm_fwd: returns (y, mean [H], rstd [H]); running statistics are updated in place when training"""
     _need_cuda(x, gamma, beta, running_mean, running_var)
