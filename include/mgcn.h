@@ -311,6 +311,14 @@ int mgcn_gcn_layer_fwd_tc(const mgcn_csr_t* g, const float* z, int64_t n_in, con
                           const float* res_b, const float* bias, const float* in_scale, const float* post,
                           const float* out_scale, int act_out, int64_t H, float* z_next, uint32_t* hmask,
                           void* workspace, size_t* workspace_bytes, void* stream);
+/* The same layer with the A operands of its products in TENSOR MEMORY (csrc/gcn_fwd_tm.cu): the gather lanes write
+ * their sums with tcgen05.st.16x256b, the products are tcgen05.mma with A from TMEM — no operand image passes
+ * through shared memory (the layer kernels are bound by the LSU data pipe).  Same contract, same results within
+ * rounding (the contraction index is summed in a permuted order inside the tensor core). */
+int mgcn_gcn_layer_fwd_tm(const mgcn_csr_t* g, const float* z, int64_t n_in, const float* w, const float* res_w,
+                          const float* res_b, const float* bias, const float* in_scale, const float* post,
+                          const float* out_scale, int act_out, int64_t H, float* z_next, uint32_t* hmask,
+                          void* workspace, size_t* workspace_bytes, void* stream);
 
 /* backward, row-local part of layer n (dxw = pre * A^T gs comes from mgcn_aggregate_prescaled on the
  * structure built by source):

@@ -63,6 +63,18 @@ __device__ __forceinline__ void row8_add(Row8& acc, const Row8& b) {
 
 // Sum rows m[nbr_w[k]] for k in [beg, end), in order, for the 8 columns of this lane.  The 4 lanes of
 // a group call this together; gi holds nbr_w[beg + sub] and gi_n holds nbr_w[beg + 4 + sub].
+// gathered row through L1 (allocating): for kernels that leave the L1 most of the SM's 228 KB (no operand stages in
+// shared memory), where the ~840 hub source rows of a botnet graph (12.7 % of all gathered entries) can stay resident
+__device__ __forceinline__ Row8 ld_row8_l1(const float* p) {
+  Row8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]),
+                 "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+template <bool kL1 = false>
 __device__ __forceinline__ Row8 gather_sum(const float* __restrict__ m, const int32_t* __restrict__ nbr_w,
                                            int beg, int end, int gi, int gi_n, int sub, int grp_lane0,
                                            unsigned gmask, int col, uint64_t pol) {
@@ -85,7 +97,7 @@ __device__ __forceinline__ Row8 gather_sum(const float* __restrict__ m, const in
         Row8 xv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t0 + u < cnt) xv[u] = ld_row8(m + (int64_t)j[u] * kGH + col);
+          if (t0 + u < cnt) xv[u] = kL1 ? ld_row8_l1(m + (int64_t)j[u] * kGH + col) : ld_row8(m + (int64_t)j[u] * kGH + col);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {

@@ -487,7 +487,12 @@ def gcn_first_layer_fwd_impl(s, x, w_in, res_w, res_b, w_next, pre, post, act_ou
     return x_next, m_next, hmask
 
 
-def gcn_layer_fwd_tc_impl(csr, z, w, res_w, res_b, bias, in_scale, post, out_scale, act_out):
+# forward layer of the hidden-32 stack: A operands through tensor memory (csrc/gcn_fwd_tm.cu) or as shared-memory
+# images (csrc/gcn_fwd_tc.cu); both pass the same parity tests
+FWD_TMEM_OPERANDS = False
+
+
+def gcn_layer_fwd_tc_impl(csr, z, w, res_w, res_b, bias, in_scale, post, out_scale, act_out, tmem_operands=None):
     """one aggregate-then-transform forward layer at hidden 32 on tcgen05 (mgcn_gcn_layer_fwd_tc): z = in_scale (.) x
     [N,32]; returns (z_next = out_scale (.) x_next [N,32], hmask int32[N])"""
     _need_cuda(z, w, res_w, res_b, bias, in_scale, post, out_scale)
@@ -508,8 +513,10 @@ def gcn_layer_fwd_tc_impl(csr, z, w, res_w, res_b, bias, in_scale, post, out_sca
     lib = _lib.load()
     args = (ctypes.byref(csr.struct()), _ptr(z), z.size(0), _ptr(w), _ptr(res_w), _ptr(res_b), _ptr(bias),
             _ptr(in_scale), _ptr(post), _ptr(out_scale), int(act_out), H, _ptr(z_next), _ptr(hmask))
-    ws, nbytes = _workspace(lambda w_, nb, stm: lib.mgcn_gcn_layer_fwd_tc(*args, w_, nb, stm), dev)
-    _lib.check(lib.mgcn_gcn_layer_fwd_tc(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    fn = lib.mgcn_gcn_layer_fwd_tm if (FWD_TMEM_OPERANDS if tmem_operands is None else tmem_operands) \
+        else lib.mgcn_gcn_layer_fwd_tc
+    ws, nbytes = _workspace(lambda w_, nb, stm: fn(*args, w_, nb, stm), dev)
+    _lib.check(fn(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
     return z_next, hmask
 
 

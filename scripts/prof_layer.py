@@ -59,6 +59,8 @@ timeit("layer_fwd (gather+2 products)", lambda: ops.gcn_layer_fwd_impl(gs.fwd, m
 if hasattr(ops, "gcn_layer_fwd_tc_impl"):
     timeit("layer_fwd_tc (aggregate-then-transform)",
            lambda: ops.gcn_layer_fwd_tc_impl(gs.fwd, x, w, r, rb, None, dis, dis, dis, 1), b_agg(n, e, H))
+    timeit("layer_fwd_tm (A operands in TMEM)",
+           lambda: ops.gcn_layer_fwd_tc_impl(gs.fwd, x, w, r, rb, None, dis, dis, dis, 1, tmem_operands=True), b_agg(n, e, H))
 timeit("layer_fwd last (no next)", lambda: ops.gcn_layer_fwd_impl(gs.fwd, m, x, None, r, rb, None, None, dis, dis, 0),
        4 * e + 8 * n + 3 * nh)
 x1 = torch.ones(n, 1, device=dev)

@@ -221,8 +221,10 @@ def _giant_hub_graph(n=4000):
     (4000, -1, 1, True, False),      # giant hubs (141 / 55 / 8 segments)
     (300001, 1500000, 1, True, False),
 ])
-def test_layer_fwd_tc_aggregate_then_transform(n, e, act_out, scaled, with_bias):
-    """mgcn_gcn_layer_fwd_tc against an fp64 dense / sparse restatement of gcn_model.py:89-106 +
+@pytest.mark.parametrize("tmem_operands", [False, True])
+def test_layer_fwd_tc_aggregate_then_transform(n, e, act_out, scaled, with_bias, tmem_operands):
+    """mgcn_gcn_layer_fwd_tc (operand images in shared memory) and mgcn_gcn_layer_fwd_tm (operands in tensor memory)
+    against an fp64 dense / sparse restatement of gcn_model.py:89-106 +
     gcn_base_models.py:199-243 with the stored format z = sigma (.) x: outputs (scaled by out_scale), mask words;
     ragged tile counts, empty rows, isolated nodes, hub rows, several tiles per CTA."""
     if e == -1:
@@ -242,7 +244,7 @@ def test_layer_fwd_tc_aggregate_then_transform(n, e, act_out, scaled, with_bias)
     gs = GraphStructure(ei.to(DEV), n, hub_threshold=64)
     d = lambda t: None if t is None else t.to(DEV)
     zn, hm = ops.gcn_layer_fwd_tc_impl(gs.fwd, d(z), d(w), d(res_w), d(res_b), d(bias), d(sigma), d(post), d(outs),
-                                       act_out)
+                                       act_out, tmem_operands=tmem_operands)
     D = lambda t: t.double()
     agg = torch.zeros(n, H, dtype=torch.float64).index_add_(0, ei[1], D(z)[ei[0]])
     s = D(post).view(-1, 1) * agg
@@ -261,7 +263,7 @@ def test_layer_fwd_tc_aggregate_then_transform(n, e, act_out, scaled, with_bias)
     assert (got[sure] == (hn[sure] > 0)).all()
     # run-to-run identical (fixed summation orders, no atomics on data)
     zn2, hm2 = ops.gcn_layer_fwd_tc_impl(gs.fwd, d(z), d(w), d(res_w), d(res_b), d(bias), d(sigma), d(post), d(outs),
-                                         act_out)
+                                         act_out, tmem_operands=tmem_operands)
     assert_bitexact(zn, zn2, "run-to-run")
     assert_bitexact(hm, hm2, "run-to-run mask")
 
