@@ -342,6 +342,19 @@ int mgcn_gcn_layer_bwd_tc(const float* dxw, const float* gy, const float* x, con
                           int64_t H, float* gy_prev, float* gs_prev, float* dw, float* d_res_w,
                           float* d_res_b, void* workspace, size_t* workspace_bytes, void* stream);
 
+/* The backward of one hidden-32 layer as ONE launch (csrc/gcn_bwd_fused.cu): mgcn_aggregate_prescaled over the
+ * by-source structure `gt` followed by mgcn_gcn_layer_bwd_tc, without the [N,32] array between them —
+ *     dxw_j = row_scale_j * sum_{e: row[e]=j} gs[col[e]]     (autograd of gcn_base_models.py:237-241, the transposed
+ *                                                             scatter; row_scale = the per-source degree factor or NULL)
+ *     then the contract of mgcn_gcn_layer_bwd_tc with x = z / x_scale (z = the stored input of mgcn_gcn_layer_fwd_tc).
+ * The gather warps write their sums into the tensor core's operand images; per layer the launch reads gs (gathered),
+ * gy and z and writes gy_prev and gs_prev (both NULL: weight gradients only).  gt needs tasks / nbr_w (work order). */
+int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, const float* gy, const float* z,
+                             const float* x_scale, const float* row_scale, const float* w, const float* res_w,
+                             const uint32_t* hmask_prev, const float* post, int64_t H, int static_slots,
+                             float* gy_prev, float* gs_prev, float* dw, float* d_res_w, float* d_res_b, void* workspace,
+                             size_t* workspace_bytes, void* stream);
+
 /* gs[i,c] = post[i] * gy[i,c] * bit c of bits[i]   (H = 32; post may be NULL) */
 int mgcn_mask_bits_scale(const float* gy, const uint32_t* bits, const float* post, int64_t N,
                          int64_t H, float* gs, void* stream);

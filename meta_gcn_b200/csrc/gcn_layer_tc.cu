@@ -479,6 +479,11 @@ __global__ void __launch_bounds__(256) k_bwd_tc_reduce(const float* __restrict__
   }
 }
 
+int launch_bwd_tc_reduce(const float* part, int P, float* dw, float* d_res_w, void* stream) {
+  MGCN_LAUNCH(k_bwd_tc_reduce, 64, 256, 0, stream, part, P, dw, d_res_w);
+  return MGCN_OK;
+}
+
 int bwd_tc_grid(int64_t N) {
   const int64_t tiles = ceil_div(N > 0 ? N : 1, kTRows);
   return (int)(tiles < kNumSMs ? tiles : kNumSMs);

@@ -550,6 +550,43 @@ def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, t
     return gy_prev, gs_prev, dw, drw, drb
 
 
+BWD_FUSED_STATIC_SLOTS = True
+
+
+def gcn_layer_bwd_fused_impl(csr_t, gs, gy, z, w, res_w, hmask_prev, post, row_scale=None, x_scale=None, want_prev=True,
+                             static_slots=None):
+    """the whole backward of one hidden-32 layer in one launch (mgcn_gcn_layer_bwd_fused): transposed aggregation of gs
+    over the by-source structure csr_t (scaled by row_scale) + the row-local products with x = z / x_scale; returns
+    (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b)"""
+    _need_cuda(gs, gy, z, w, res_w, hmask_prev, post, row_scale, x_scale)
+    gs = _f32c(gs, "gs")
+    gy = _f32c(gy, "gy")
+    z = _f32c(z, "z")
+    w = _f32c(w, "w")
+    res_w = _f32c(res_w, "res_w")
+    post = _f32c(post, "post")
+    row_scale = _f32c(row_scale, "row_scale")
+    x_scale = _f32c(x_scale, "x_scale")
+    N, H = z.shape
+    if csr_t.n_rows != N or gs.size(0) != N or gy.size(0) != N:
+        raise ValueError("gcn_layer_bwd_fused needs a square structure and [N,32] operands")
+    dev = z.device
+    gy_prev = torch.empty_like(z) if want_prev else None
+    gs_prev = torch.empty_like(z) if want_prev else None
+    dw = torch.empty(H, H, dtype=torch.float32, device=dev)
+    drw = torch.empty(H, H, dtype=torch.float32, device=dev)
+    drb = torch.empty(H, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    args = (ctypes.byref(csr_t.struct()), _ptr(gs), _ptr(gy), _ptr(z), _ptr(x_scale), _ptr(row_scale), _ptr(w),
+            _ptr(res_w), _ptr(hmask_prev) if want_prev else None, _ptr(post), H,
+            int(BWD_FUSED_STATIC_SLOTS if static_slots is None else static_slots), _ptr(gy_prev), _ptr(gs_prev),
+            _ptr(dw), _ptr(drw), _ptr(drb))
+    fn = lib.mgcn_gcn_layer_bwd_fused
+    ws, nbytes = _workspace(lambda w_, nb, stm: fn(*args, w_, nb, stm), dev)
+    _lib.check(fn(*args, _ptr(ws), ctypes.byref(nbytes), _stream()))
+    return gy_prev, gs_prev, dw, drw, drb
+
+
 def mask_bits_scale_impl(gy, bits, post):
     """gs = post[:,None] * gy * bit(bits, column)   (H = 32)"""
     _need_cuda(gy, bits, post)

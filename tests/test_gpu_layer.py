@@ -287,3 +287,73 @@ def test_layer_bwd_tc_scaled_input(n):
     assert_parity(drb, D(gy).sum(0), "dr")
     G = D(dxw) @ D(w).t() + D(gy) @ D(res_w)
     assert_parity(gyp, G * (x > 0), "gy_prev")
+
+
+@pytest.mark.parametrize("n,e,scaled,want_prev", [
+    (1000, 9000, True, True),
+    (1003, 12000, True, True),
+    (517, 3000, False, True),
+    (131, 700, True, False),
+    (16, 40, True, True),
+    (5, 0, True, True),
+    (40000, 400000, True, True),
+    (4000, -1, True, True),          # giant hubs (141 / 55 / 8 segments)
+    (300001, 1500000, True, True),
+    (151617, 700000, True, False),
+])
+def test_layer_bwd_fused(n, e, scaled, want_prev):
+    """mgcn_gcn_layer_bwd_fused (transposed aggregation + row-local products in one launch) against an fp64 restatement
+    of the autograd of gcn_model.py:89-106 / gcn_base_models.py:199-243 in the stored format z = sigma (.) x: dxw is
+    never materialised, so it is checked through dW, gy_prev and gs_prev; ragged tile counts, rows without entries,
+    hub rows, several tiles per CTA; and the two-launch path (mgcn_aggregate_prescaled + mgcn_gcn_layer_bwd_tc)."""
+    if e == -1:
+        ei = _giant_hub_graph(n)
+    else:
+        ei = rand_graph(n, e, seed=n) if e else torch.zeros(2, 0, dtype=torch.int64)
+    gen = torch.Generator().manual_seed(n + 23)
+    gs_in = torch.randn(n, H, generator=gen)
+    gy = torch.randn(n, H, generator=gen)
+    x = torch.randn(n, H, generator=gen)
+    w = torch.randn(H, H, generator=gen) / H ** 0.5
+    res_w = torch.randn(H, H, generator=gen) / H ** 0.5
+    post = torch.rand(n, generator=gen) + 0.1
+    pre = torch.rand(n, generator=gen) + 0.1 if scaled else None
+    sigma = torch.rand(n, generator=gen) + 0.1 if scaled else None
+    bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), generator=gen, dtype=torch.int64).to(torch.int32)
+    z = x * sigma.view(-1, 1) if scaled else x
+    struct = GraphStructure(ei.to(DEV), n, hub_threshold=64)
+    d = lambda t: None if t is None else t.to(DEV)
+    args = (struct.bwd, d(gs_in), d(gy), d(z), d(w), d(res_w), d(bits), d(post))
+    gyp, gsp, dw, drw, drb = ops.gcn_layer_bwd_fused_impl(*args, row_scale=d(pre), x_scale=d(sigma), want_prev=want_prev)
+    D = lambda t: t.double()
+    # dxw_j = pre_j * sum over edges j -> i of gs_i
+    dxw = torch.zeros(n, H, dtype=torch.float64).index_add_(0, ei[0], D(gs_in)[ei[1]])
+    if scaled:
+        dxw = dxw * D(pre).view(-1, 1)
+    xin = D(z) / D(sigma).view(-1, 1) if scaled else D(z)
+    assert_parity(dw, xin.t() @ dxw, "dW")
+    assert_parity(drw, D(gy).t() @ xin, "dR")
+    assert_parity(drb, D(gy).sum(0), "dr")
+    if not want_prev:
+        assert gyp is None and gsp is None
+        return
+    G = dxw @ D(w).t() + D(gy) @ D(res_w)
+    gy_ref = G * (x > 0)
+    assert_parity(gyp, gy_ref, "gy_prev")
+    b = ((bits.numpy().astype(np.uint32)[:, None] >> np.arange(H, dtype=np.uint32)[None, :]) & 1).astype(np.float64)
+    assert_parity(gsp, D(post).view(-1, 1) * gy_ref * torch.from_numpy(b), "gs_prev")
+    # run-to-run identical (fixed summation orders, no atomics on data)
+    again = ops.gcn_layer_bwd_fused_impl(*args, row_scale=d(pre), x_scale=d(sigma), want_prev=want_prev)
+    for got, ref, name in zip((gyp, gsp, dw, drw, drb), again, ("gy_prev", "gs_prev", "dW", "dR", "dr")):
+        assert_bitexact(got, ref, "run-to-run " + name)
+    # completion-order slots: same results up to the summation order of the weight gradients
+    dyn = ops.gcn_layer_bwd_fused_impl(*args, row_scale=d(pre), x_scale=d(sigma), want_prev=want_prev, static_slots=False)
+    assert_bitexact(gyp, dyn[0], "gy_prev, completion-order slots")
+    assert_parity(dyn[2], xin.t() @ dxw, "dW, completion-order slots")
+    # the two-launch path computes the same thing
+    if n > 0:
+        dxw2 = ops.aggregate_prescaled_impl(struct.bwd, d(gs_in), d(pre), 0, None, None, 0)
+        gyp2, gsp2, dw2, drw2, drb2 = ops.gcn_layer_bwd_impl(dxw2, d(gy), d(z), d(w), d(res_w), d(bits), d(post), True, True,
+                                                             x_scale=d(sigma))
+        assert_parity(gyp, gyp2.double().cpu(), "gy_prev vs two launches")
+        assert_parity(dw, dw2.double().cpu(), "dW vs two launches")
