@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
                     help="BASELINE.json configs[k]; 1 (default) is the contract line, the others print one JSON line "
                          "with their own results and cpu_baseline (scripts/bench_configs.py)")
-    ap.add_argument("--e2e-steps", type=int, default=12)   # the first copy of a loop cannot be overlapped
+    ap.add_argument("--e2e-steps", type=int, default=20)   # the first copy of a loop cannot be overlapped
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong-graphs", default="24,25",

@@ -351,7 +351,7 @@ int mgcn_gcn_layer_bwd_tc(const float* dxw, const float* gy, const float* x, con
  * gy and z and writes gy_prev and gs_prev (both NULL: weight gradients only).  gt needs tasks / nbr_w (work order). */
 int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, const float* gy, const float* z,
                              const float* x_scale, const float* row_scale, const float* w, const float* res_w,
-                             const uint32_t* hmask_prev, const float* post, int64_t H, int static_slots,
+                             const uint32_t* hmask_prev, const float* post, int64_t H,
                              float* gy_prev, float* gs_prev, float* dw, float* d_res_w, float* d_res_b, void* workspace,
                              size_t* workspace_bytes, void* stream);
 

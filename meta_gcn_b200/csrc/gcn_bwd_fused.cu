@@ -8,31 +8,46 @@
 //     gy_prev = G * (x > 0);   gs_prev = post * gy_prev * bits(hmask_prev)
 //
 // k_agg_flat + k_layer_bwd_tc did this in two launches with the [N,32] array dxw written to HBM and read back; here the
-// gather warps put their sums straight into the operand images of the tensor core, so a layer's backward reads gs
-// (gathered), gy and z and writes gy_prev and gs_prev — 0.9 GB less DRAM traffic per layer at the botnet batch.
+// gathered sums go through a small ring in shared memory into the operand images of the tensor core, so a layer's
+// backward reads gs (gathered), gy and z and writes gy_prev and gs_prev — 0.9 GB less DRAM traffic per layer at the
+// botnet batch, and one launch less.
 //
-// One persistent CTA per SM, 24 warps at 80 registers, the skeleton of k_gcn_fwd_tc over 64-row tiles:
-//   producers  20 warps; a pass = 8 consecutive tasks of the by-source work order, one per 4-lane group: gather-sum of
-//              gs (gather.cuh), the row's own gy (registers, in flight during the gather) and z (cp.async into a
-//              per-warp staging kilobyte: no registers while the gather runs).  A finished pass takes the next free
-//              8-row slot of the CTA (tiles fill in COMPLETION order), splits dxw, gy and x into tf32 hi / lo and
-//              stores ten images: SWIZZLE_128B K-major images of dxw and gy for the row-local products and
-//              SWIZZLE_128B_BASE32B MN-major images of dxw, gy and x for the transposed ones (tc05.cuh: a 32-bit
-//              MN-major operand is only read correctly from that image, a K-major one never).  Group g of a warp owns
-//              slot row ((g & 3) << 1) | (g >> 2) and stores its two 16-byte chunks in the order (g & 1): the 8 lanes of
-//              a quarter warp then hit 8 different 16-byte bank groups in BOTH image types.  Slots without a finished
-//              row (hub segments, padding) zero their MN-major rows.  The warp whose pass is the 8th of a tile issues
-//              its 32 tcgen05.mma from one lane:
-//                G      [64 x 64|32]  K-major,  M = 64:  main = dxw_hi Wt_hi + gy_hi R_hi, corrections in their own columns
-//                T      [128 x 64]    MN-major, M = 128: [dxw_hi|gy_hi|dxw_lo|gy_lo]^T [x_hi | x_lo], 8 steps of 8 rows
-//                colsum [64 x 64]     ones[64 x 8] (K-major) x [gy_hi | gy_lo] (MN-major): every row = colsum of the tile
-//   epilogue   4 warps: T and the column sums -> running fp32 registers (RN adds; chains through the TMEM accumulator
-//              stay 8 steps long); G -> both masks, per-target factor -> two staged 144-byte rows -> two 128-byte
-//              cp.async.bulk stores per row (lanes 0..15 of a warp carry the 16 rows of its TMEM quarter)
-//   barriers   as k_gcn_fwd_tc: full[tile % 4] (8 pass arrivals), done[tile % 4] (tcgen05.commit), tfree[stage].
+// One persistent CTA per SM, three roles over 64-row tiles of the by-source work order (tile t of a CTA = its passes
+// 8 t .. 8 t + 7, a pass = 8 consecutive tasks; the assignment is STATIC, so every sum has a fixed order and the
+// results are identical from run to run):
+//   gather     kBfGather warps; warp w owns passes w, w + kBfGather, ...: gather-sum of gs (gather.cuh: 4 lanes x
+//              LDG.256 per gathered row, sums in edge order), nothing else — the sums go as raw fp32 rows (swizzled
+//              16-byte chunks) into slot pass % kBfRing of a ring, one mbarrier pair per slot.  The first version of
+//              this kernel let the gather warps also split and store the ten operand images; a pass then spent a
+//              third of its time outside the gather and waited for operand stages (2 x 8 passes for 20 warps):
+//              1.04 ms.  With the ring a gather warp is never further than its own pass from the next gather.
+//   images     8 warps, warp p owns pass p of every tile: the ring rows, the rows' own gy and z (LDG.256, one tile ahead
+//              when the ring slot is already full) -> scale, tf32 hi / lo split -> ten images per stage: K-major
+//              (interleaved) dxw and gy for the row-local products, SWIZZLE_128B_BASE32B MN-major dxw, gy and x for
+//              the transposed ones (tc05.cuh: a 32-bit MN-major operand is only read correctly from that image, a
+//              K-major one never); lane 8 qq + j owns row j and 32-byte chunk qq, chunk order (j >> 2), conflict-free
+//              in both image types.  Tasks that finish no row (hub segments, padding) contribute zero rows.  Warp
+//              (tile % 8) issues the tile's 24 tcgen05.mma from one lane:
+//                G  [64 x 64|32]  K-major,  M = 64:  main = dxw_hi Wt_hi + gy_hi R_hi, corrections in their own columns
+//                T  [128 x 64]    MN-major, M = 128: [dxw_hi|gy_hi|dxw_lo|gy_lo]^T [x_hi | x_lo], 8 steps of 8 rows
+//              Column sums of gy (dr) stay in registers of these warps.
+//   epilogue   4 warps: T -> running fp32 registers (RN adds; chains through the TMEM accumulator stay 8 steps long);
+//              G (lanes 0..15 of a TMEM quarter carry 16 tile rows) -> both masks, per-target factor -> staged rows ->
+//              whole 64-byte row pieces to HBM
+//   barriers   ring_full / ring_free [slot]; full[tile % 4] (8 image-warp arrivals), done[tile % 4] (tcgen05.commit),
+//              tfree[stage] (epilogue -> issuer).  No wait can be lapped: a ring slot's next phase needs this phase's
+//              consumer, done(t + 4) needs done(t + 2) needs the stores that wait for done(t).
 // Hub rows (longer than the hub threshold): their segments store partial sums in mode 0; a second launch (mode 1) sums
 // the partials per hub row (fixed order) and runs the same tile path.  Per-CTA partials of dW / dR / dr are reduced in a
-// fixed order by k_bwd_tc_reduce / k_reduce_partials.  No atomics on data: run-to-run identical.
+// fixed order by k_bwd_tc_reduce / k_reduce_partials.  No atomics on data.
+//
+// MEASURED (B200, botnet batch, scripts/prof_layer.py, profiles/r2_bwd_fused.md): 1.45 ms per layer against 0.48 + 0.61 ms
+// for k_agg_flat + k_layer_bwd_tc, with 2.59 GB of DRAM traffic against 3.47 GB.  Correct and deterministic, but not
+// faster, so fused.BWD_FUSED is off by default.  Why: the per-row operand-image work (48 tf32 splits, 20 STS.128 per
+// lane and pass, ~560 instructions per 8 rows) needs the 16 warps k_layer_bwd_tc gives it; here 8 image warps share
+// the SM with 16 gather warps and 4 epilogue warps (28 warps x 72 registers is all the register file holds) and every
+// tile waits for its slowest image warp.  The 2-role version before it (20 warps that gather AND build images, tiles
+// filled in completion order) ran 1.04 ms but its weight gradients depended on the completion order.
 #include "common.cuh"
 #include "gather.cuh"
 #include "tc05.cuh"
@@ -40,7 +55,7 @@
 namespace mgcn {
 
 constexpr int kBfRows = 64;                      // rows per tile
-constexpr int kBfPasses = kBfRows / 8;           // 8-row slots per tile
+constexpr int kBfPasses = kBfRows / 8;           // passes (8 rows) per tile = image warps
 constexpr int kBfImg = kBfRows * 128;            // one operand image: 64 rows x 128 bytes
 constexpr int kBfKDh = 0 * kBfImg;               // K-major dxw_hi, dxw_lo, gy_hi, gy_lo
 constexpr int kBfKDl = 1 * kBfImg;
@@ -51,23 +66,31 @@ constexpr int kBfMXh = 8 * kBfImg;               // MN-major x_hi, x_lo
 constexpr int kBfMXl = 9 * kBfImg;
 constexpr int kBfStageB = 10 * kBfImg;           // 80 KB
 constexpr int kBfStages = 2;
-constexpr int kBfOffB1 = kBfStages * kBfStageB;  // [Wt_hi ; Wt_lo]: 64 rows x 128 bytes, SWIZZLE_128B K-major
+constexpr int kBfOffB1 = kBfStages * kBfStageB;  // [Wt_hi ; Wt_lo]: 64 x 32, interleaved K-major
 constexpr int kBfOffB2 = kBfOffB1 + 8192;        // [R_hi ; R_lo]
-constexpr int kBfOffOnes = kBfOffB2 + 8192;      // ones[64 x 8], interleaved K-major (2 KB)
-constexpr int kBfLdo = 20;                       // floats per staged half row (64 + 16 bytes: conflict-free both ways)
-constexpr int kBfOffOut = kBfOffOnes + 2048;     // [8 epilogue warps][gy_prev | gs_prev][16 rows][kBfLdo]
-#ifndef MGCN_BF_PROD
-#define MGCN_BF_PROD 16
+#ifndef MGCN_BF_RING
+#define MGCN_BF_RING 24
 #endif
-constexpr int kBfProdWarps = MGCN_BF_PROD;
-constexpr int kBfEpiWarps = 8;                   // TMEM quarter = warp & 3, column half = warp >> 2
-constexpr int kBfThreads = 32 * (kBfEpiWarps + kBfProdWarps);
-constexpr int kBfOffZst = kBfOffOut + kBfEpiWarps * 2 * 16 * kBfLdo * 4;   // per producer warp: 8 rows x 128 bytes of z
-constexpr int kBfOffScal = kBfOffZst + kBfProdWarps * 1024;            // [tile % 4][64] {row id, x > 0 bits, hmask_prev, post}
-constexpr int kBfOffMisc = kBfOffScal + 2 * kBfStages * kBfRows * 16;  // barriers, counters, tmem slot
-constexpr int kBfSmem = kBfOffMisc + 256 + 1024;
-constexpr int kBfTmemBuf = 192;                  // columns per accumulator buffer: G [0,64), T [64,128), colsum [128,192)
+constexpr int kBfRing = MGCN_BF_RING;            // ring slots (passes): 1 KB of rows + 8 row ids each
+constexpr int kBfOffRing = kBfOffB2 + 8192;
+constexpr int kBfOffMeta = kBfOffRing + kBfRing * 1024;
+constexpr int kBfLdo = 36;                       // floats per staged output row (144 bytes: conflict-free)
+constexpr int kBfOffOut = kBfOffMeta + kBfRing * 32;       // [4 epilogue warps][gy_prev | gs_prev][16 rows][kBfLdo]
+#ifndef MGCN_BF_GATHER
+#define MGCN_BF_GATHER 16
+#endif
+constexpr int kBfGather = MGCN_BF_GATHER;
+constexpr int kBfImgWarps = kBfPasses;
+constexpr int kBfEpiWarps = 4;
+constexpr int kBfThreads = 32 * (kBfEpiWarps + kBfImgWarps + kBfGather);
+constexpr int kBfOffScal = kBfOffOut + kBfEpiWarps * 2 * 16 * kBfLdo * 4;   // [tile % 4][64] {row id, x > 0 bits, hmask_prev, post}
+constexpr int kBfOffDr = kBfOffScal + 2 * kBfStages * kBfRows * 16;         // [8 image warps][32]
+constexpr int kBfOffMisc = kBfOffDr + kBfImgWarps * 32 * 4;                 // barriers, tmem slot
+constexpr int kBfSmem = kBfOffMisc + 1024 + 1024;
+constexpr int kBfTmemBuf = 128;                  // columns per accumulator buffer: G [0,64), T [64,128)
 static_assert(kBfSmem <= 232448, "shared memory");
+static_assert((10 + 2 * kBfRing) * 8 + 16 <= 1024, "barrier block");
+static_assert(kBfRing >= 16, "the image warps look one tile ahead");
 
 struct BwdFusedArgs {
   const int4* tasks;
@@ -90,23 +113,22 @@ struct BwdFusedArgs {
   float* gs_prev;
   float* partial;            // [seg_cap,32] hub segment sums
   float* part_t;             // [grid][128][32] of THIS launch
-  float* part_b;             // [grid][2][32]
+  float* part_b;             // [grid][32]
   int64_t n_rows;
   int64_t seg_cap;
   int64_t hub_cap;
   int hub_threshold;
-  int static_slots;          // 1: pass g of a CTA always fills slot g (weight gradients identical from run to run)
 };
 
-__device__ __forceinline__ int bf_sw128_off(int r, int q) {   // bytes; 16-byte chunk q of row r, SWIZZLE_128B K-major
-  return (r << 7) + ((q ^ (r & 7)) << 4);
+__device__ __forceinline__ int bf_k_off(int r, int q) {       // bytes; 16-byte chunk q of row r, interleaved K-major
+  return ((r >> 3) << 10) + (q << 7) + ((r & 7) << 4);
 }
 __device__ __forceinline__ int bf_mn_off(int r, int q) {      // bytes; SWIZZLE_128B_BASE32B
   return (r << 7) + ((((q >> 1) ^ (r & 3)) << 5) | ((q & 1) << 4));
 }
 
-__device__ __forceinline__ void bf_split4(float a, float b, float c, float d, float4& hi, float4& lo) {
-  const float e[4] = {a, b, c, d};
+__device__ __forceinline__ void bf_split4(const float4 v, float4& hi, float4& lo) {
+  const float e[4] = {v.x, v.y, v.z, v.w};
   float h[4], l[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -117,35 +139,47 @@ __device__ __forceinline__ void bf_split4(float a, float b, float c, float d, fl
   lo = make_float4(l[0], l[1], l[2], l[3]);
 }
 
-// the lane's 8 columns of one row -> hi / lo images; first the chunk 2 sub + flip, then the other one
-template <bool kWithK>
-__device__ __forceinline__ void bf_store_row(unsigned char* k_hi, unsigned char* k_lo, unsigned char* m_hi,
-                                             unsigned char* m_lo, int r, int sub, int flip, const Row8& v) {
-  float4 hi, lo;
-  const int ca = 2 * sub + flip, cb = 2 * sub + 1 - flip;
-  bf_split4(flip ? v.v[4] : v.v[0], flip ? v.v[5] : v.v[1], flip ? v.v[6] : v.v[2], flip ? v.v[7] : v.v[3], hi, lo);
-  if (kWithK) {
-    *reinterpret_cast<float4*>(k_hi + bf_sw128_off(r, ca)) = hi;
-    *reinterpret_cast<float4*>(k_lo + bf_sw128_off(r, ca)) = lo;
-  }
-  *reinterpret_cast<float4*>(m_hi + bf_mn_off(r, ca)) = hi;
-  *reinterpret_cast<float4*>(m_lo + bf_mn_off(r, ca)) = lo;
-  bf_split4(flip ? v.v[0] : v.v[4], flip ? v.v[1] : v.v[5], flip ? v.v[2] : v.v[6], flip ? v.v[3] : v.v[7], hi, lo);
-  if (kWithK) {
-    *reinterpret_cast<float4*>(k_hi + bf_sw128_off(r, cb)) = hi;
-    *reinterpret_cast<float4*>(k_lo + bf_sw128_off(r, cb)) = lo;
-  }
-  *reinterpret_cast<float4*>(m_hi + bf_mn_off(r, cb)) = hi;
-  *reinterpret_cast<float4*>(m_lo + bf_mn_off(r, cb)) = lo;
-}
-
-__device__ __forceinline__ Row8 bf_ld_row8_stream(const float* p, uint64_t pol) {   // one LDG.256, streamed
-  Row8 r;
+struct BfF8 {
+  float4 lo, hi;
+};
+__device__ __forceinline__ BfF8 bf_ld_f8_stream(const float* p, uint64_t pol) {   // one LDG.256, streamed
+  BfF8 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
-                 "=f"(r.v[7])
+               : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
                : "l"(p), "l"(pol));
   return r;
+}
+
+__device__ __forceinline__ bool bf_mbar_test(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+// mbarrier wait that does not hammer the issue slots and the shared-memory pipe while it waits: the first version of
+// this kernel spent half of its executed instructions in try_wait loops of warps that had nothing to do (ncu: 190 M
+// polls per launch).  try_wait with a suspend-time hint parks the warp in hardware; a failed attempt sleeps `ns` more.
+#ifndef MGCN_BF_SLEEP_G
+#define MGCN_BF_SLEEP_G 200   // gather warps waiting for a ring slot
+#endif
+#ifndef MGCN_BF_SLEEP_I
+#define MGCN_BF_SLEEP_I 32    // image warps (stage, issuer)
+#endif
+#ifndef MGCN_BF_SLEEP_E
+#define MGCN_BF_SLEEP_E 64    // epilogue
+#endif
+#ifndef MGCN_BF_HINT
+#define MGCN_BF_HINT 2000
+#endif
+__device__ __forceinline__ void bf_wait(uint64_t* b, uint32_t parity, unsigned ns) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)MGCN_BF_HINT) : "memory");
+    if (ok) break;
+    if (ns) __nanosleep(ns);
+  }
 }
 
 __device__ __forceinline__ void bf_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -153,30 +187,25 @@ __device__ __forceinline__ void bf_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
-__device__ __forceinline__ void bf_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 
 template <int kMode>   // 0: tiles of the work order (rows + hub segments), 1: tiles of the hub list
 __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bar_done = reinterpret_cast<uint64_t*>(smem + kBfOffMisc);         // [2 S]
-  uint64_t* bar_tfree = bar_done + 2 * kBfStages;                               // [S]
-  uint64_t* bar_full = bar_tfree + kBfStages;                                   // [2 S] 8 pass arrivals per tile
-  uint32_t* arrivals = reinterpret_cast<uint32_t*>(bar_full + 2 * kBfStages);   // [S] passes stored, never reset
-  uint32_t* next_slot = arrivals + kBfStages;                                   // passes finished by this CTA so far
-  uint32_t* tmem_slot = next_slot + 1;
+  uint64_t* bar_done = reinterpret_cast<uint64_t*>(smem + kBfOffMisc);   // [4]
+  uint64_t* bar_full = bar_done + 4;                                      // [4] 8 image-warp arrivals per tile
+  uint64_t* bar_tfree = bar_full + 4;                                     // [2]
+  uint64_t* ring_full = bar_tfree + 2;                                    // [kBfRing]
+  uint64_t* ring_free = ring_full + kBfRing;                              // [kBfRing]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_free + kBfRing);
   uint4* scal = reinterpret_cast<uint4*>(smem + kBfOffScal);
+  int32_t* meta = reinterpret_cast<int32_t*>(smem + kBfOffMeta);          // [kBfRing][8] row ids (-1: no row)
+  float* dr_red = reinterpret_cast<float*>(smem + kBfOffDr);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const bool want_prev = a.gy_prev != nullptr;
 
-  // weight images (SWIZZLE_128B K-major, 64 rows: hi then lo): B1(n, k) = W[n][k], B2(n, k) = R[k][n]
+  // weight images (interleaved K-major, 64 rows: hi then lo): B1(n, k) = W[n][k], B2(n, k) = R[k][n]
   for (int i = tid; i < 32 * 32; i += kBfThreads) {
     const int n = i >> 5, k = i & 31;
     const float w1 = __ldg(a.w + n * 32 + k), w2 = __ldg(a.res_w + k * 32 + n);
@@ -184,28 +213,26 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
     const float h2 = __uint_as_float(round_tf32_bits(__float_as_uint(w2)));
     float* b1 = reinterpret_cast<float*>(smem + kBfOffB1);
     float* b2 = reinterpret_cast<float*>(smem + kBfOffB2);
-    const int o_hi = (bf_sw128_off(n, k >> 2) >> 2) + (k & 3), o_lo = (bf_sw128_off(n + 32, k >> 2) >> 2) + (k & 3);
+    const int o_hi = (bf_k_off(n, k >> 2) >> 2) + (k & 3), o_lo = (bf_k_off(n + 32, k >> 2) >> 2) + (k & 3);
     b1[o_hi] = h1;
     b1[o_lo] = __uint_as_float(round_tf32_bits(__float_as_uint(w1 - h1)));
     b2[o_hi] = h2;
     b2[o_lo] = __uint_as_float(round_tf32_bits(__float_as_uint(w2 - h2)));
   }
-  for (int i = tid; i < 512; i += kBfThreads) reinterpret_cast<float*>(smem + kBfOffOnes)[i] = 1.f;
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kBfStages; ++s) {
-      arrivals[s] = 0;
-      if (s == 0) *next_slot = 0;
+    for (int s = 0; s < 4; ++s) {
       mbar_init(bar_done + s, 1);
-      mbar_init(bar_done + kBfStages + s, 1);
-      mbar_init(bar_tfree + s, kBfEpiWarps);
-      mbar_init(bar_full + s, kBfPasses);
-      mbar_init(bar_full + kBfStages + s, kBfPasses);
+      mbar_init(bar_full + s, kBfImgWarps);
+    }
+    for (int s = 0; s < kBfStages; ++s) mbar_init(bar_tfree + s, kBfEpiWarps);
+    for (int s = 0; s < kBfRing; ++s) {
+      mbar_init(ring_full + s, 1);
+      mbar_init(ring_free + s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -228,27 +255,20 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
     if (limit > a.hub_cap) limit = a.hub_cap;
   }
   const int64_t n_tiles = (limit + kBfRows - 1) / kBfRows;
+  const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
 
-  if (warp >= kBfEpiWarps) {
-    // ------------------------------- producers -------------------------------
-    const int pw = warp - kBfEpiWarps;
-    const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32);
-    const uint32_t idT = umma_idesc_tf32(128, 64, 1, 1), idC = umma_idesc_tf32(64, 64, 0, 1);
-    const uint64_t dK = umma_desc(smem_u32(smem), 16, 1024, 2);          // SWIZZLE_128B K-major: SBO = 8 rows x 128 bytes
-    const uint64_t dM = umma_desc(smem_u32(smem), kBfImg, 512, 1);       // BASE32B MN-major, atoms one image apart
-    const uint64_t dM2 = umma_desc(smem_u32(smem), 2 * kBfImg, 512, 1);  // atoms two images apart: gy_hi | gy_lo
-    const uint64_t dOnes = umma_desc(smem_u32(smem + kBfOffOnes), 128, 256, 0);
+  if (warp >= kBfEpiWarps + kBfImgWarps) {
+    // ------------------------------- gather warps -------------------------------
+    const int gw = warp - kBfEpiWarps - kBfImgWarps;
     const int sub = lane & 3, grp = lane >> 2, grp_lane0 = grp * 4;
     const unsigned gmask = 0xfu << grp_lane0;
     const int col = sub * 8;
-    const int rslot = ((grp & 3) << 1) | (grp >> 2), flip = grp & 1;
-    // this lane's 32 bytes of its row's z: two 16-byte chunks, positions swapped in odd rows (the 8 lanes of a quarter
-    // warp then cover 8 different bank groups)
-    unsigned char* zst0 = smem + kBfOffZst + pw * 1024 + grp * 128 + (((2 * sub) ^ (grp & 1)) << 4);
-    unsigned char* zst1 = smem + kBfOffZst + pw * 1024 + grp * 128 + (((2 * sub + 1) ^ (grp & 1)) << 4);
-    auto load_desc = [&](int64_t g) {
+    // ring row grp of a slot, 16-byte chunk c at position c ^ grp: conflict-free for these stores (a quarter warp = two
+    // rows of opposite parity) and for the image warps' reads (8 rows, one chunk)
+    const int ring_o0 = grp * 128 + (((2 * sub) ^ grp) << 4), ring_o1 = grp * 128 + (((2 * sub + 1) ^ grp) << 4);
+    auto load_desc = [&](int g) {
       int4 d = make_int4(-1, 0, 0, 0);
-      const int64_t tile = blockIdx.x + (g / kBfPasses) * (int64_t)gridDim.x;
+      const int64_t tile = blockIdx.x + (int64_t)(g / kBfPasses) * gridDim.x;
       const int64_t e = tile * kBfRows + (g % kBfPasses) * 8 + lane;
       if (lane < 8 && tile < n_tiles && e < limit) {
         if (kMode == 0) {
@@ -274,33 +294,19 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
       }
       return p;
     };
-    int4 d = load_desc(pw);
-    int4 dn = load_desc(pw + kBfProdWarps);
+    int4 d = load_desc(gw);
+    int4 dn = load_desc(gw + kBfGather);
     PassIdx pi = load_idx(d);
-    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    for (int64_t g = pw; g < my_tiles * kBfPasses; g += kBfProdWarps) {
+    const int n_pass = my_tiles * kBfPasses;
+    for (int g = gw; g < n_pass; g += kBfGather) {
       const int rowp = __shfl_sync(0xffffffffu, d.x, grp);
       const int slot = __shfl_sync(0xffffffffu, d.w, grp);
       const bool finish = rowp >= 0 && slot == 0;   // this group completes a row
-      const int64_t own = (int64_t)(finish ? rowp : 0) * kGH + col;
-      // the row's own gy (registers) and z (cp.async: lands in shared memory while the gather runs); its scalars, one
-      // per lane of the group: row_scale, x_scale, hmask_prev, post — looked at only when the row is stored
-      const Row8 gyrow = bf_ld_row8_stream(a.gy + own, pol);
-      cp_async16_hint(zst0, a.z + own, 16, pol);
-      cp_async16_hint(zst1, a.z + own + 4, 16, pol);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      uint32_t sc = 0x3f800000u;   // 1.0f
-      if (sub == 2) sc = 0;
-      {
-        const void* sp = sub == 0 ? (const void*)a.row_scale : sub == 1 ? (const void*)a.x_scale
-                         : sub == 2 ? (const void*)a.hmask_prev : (const void*)a.post;
-        if (finish && sp) sc = __ldg(reinterpret_cast<const uint32_t*>(sp) + rowp);
-      }
       const PassIdx pc = pi;
       const int4 dc = d;
       d = dn;
       pi = load_idx(d);                               // next pass: index batches in flight during this gather
-      dn = load_desc(g + 2 * kBfProdWarps);
+      dn = load_desc(g + 2 * kBfGather);
       Row8 acc;
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
@@ -332,77 +338,149 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
           if (grp == i) acc = tot;
         }
       }
-      // next free 8-row slot of this CTA: tile tl (in completion order), rows 8 ps .. 8 ps + 7
-      uint32_t my = (uint32_t)g;
-      if (!a.static_slots) {
-        if (lane == 0) asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(my) : "r"(smem_u32(next_slot)) : "memory");
-        my = __shfl_sync(0xffffffffu, my, 0);
-      }
-      const int64_t tl = my / kBfPasses;
-      const int ps = (int)(my % kBfPasses), stage = (int)(tl % kBfStages);
-      // the tensor core has consumed this stage's previous tile (tile tl - S of this CTA)
-      if (tl >= kBfStages) {
-        const int64_t tp = tl - kBfStages;
-        mbar_wait(bar_done + (int)(tp % (2 * kBfStages)), (uint32_t)(tp / (2 * kBfStages)) & 1u);
-      }
-      const float pre_v = __uint_as_float(__shfl_sync(0xffffffffu, sc, grp_lane0));
-      const float xs_v = __uint_as_float(__shfl_sync(0xffffffffu, sc, grp_lane0 + 1));
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      uint32_t xb = 0;
-      {
-        const int r = ps * 8 + rslot;
-        unsigned char* st = smem + stage * kBfStageB;
-        if (finish) {
-          if (a.row_scale) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc.v[q] *= pre_v;
-          }
-          bf_store_row<true>(st + kBfKDh, st + kBfKDl, st + kBfMN, st + kBfMN + 2 * kBfImg, r, sub, flip, acc);
-          bf_store_row<true>(st + kBfKGh, st + kBfKGl, st + kBfMN + kBfImg, st + kBfMN + 3 * kBfImg, r, sub, flip, gyrow);
-          Row8 xr;
-          {
-            const float4 z0 = *reinterpret_cast<const float4*>(zst0), z1 = *reinterpret_cast<const float4*>(zst1);
-            xr.v[0] = z0.x; xr.v[1] = z0.y; xr.v[2] = z0.z; xr.v[3] = z0.w;
-            xr.v[4] = z1.x; xr.v[5] = z1.y; xr.v[6] = z1.z; xr.v[7] = z1.w;
-          }
-          if (a.x_scale) {
-            const float inv = __frcp_rn(xs_v);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) xr.v[q] *= inv;
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) xb |= (xr.v[q] > 0.f ? 1u : 0u) << q;
-          xb <<= 8 * sub;
-          bf_store_row<false>(nullptr, nullptr, st + kBfMXh, st + kBfMXl, r, sub, flip, xr);
-        } else {
-          // no row in this slot: its MN-major rows must not contribute to the transposed products
-          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int im = 4; im < 10; ++im) {
-            *reinterpret_cast<float4*>(st + im * kBfImg + bf_mn_off(r, 2 * sub + flip)) = zero;
-            *reinterpret_cast<float4*>(st + im * kBfImg + bf_mn_off(r, 2 * sub + 1 - flip)) = zero;
-          }
-        }
-        xb |= __shfl_xor_sync(0xffffffffu, xb, 1);
-        xb |= __shfl_xor_sync(0xffffffffu, xb, 2);
-        uint32_t sv = sc;                                  // sub 2: hmask_prev, sub 3: post
-        if (sub == 0) sv = (uint32_t)(finish ? rowp : -1);
-        if (sub == 1) sv = xb;
-        reinterpret_cast<uint32_t*>(scal + (int)(tl % (2 * kBfStages)) * kBfRows + r)[sub] = sv;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's image stores -> async proxy
+      // ring slot of this pass: free once the image warp has read the pass that used it before
+      const int q = g % kBfRing, use = g / kBfRing;
+      if (use >= 1) bf_wait(ring_free + q, (uint32_t)(use - 1) & 1u, MGCN_BF_SLEEP_G);
+      unsigned char* slot_p = smem + kBfOffRing + q * 1024;
+      *reinterpret_cast<float4*>(slot_p + ring_o0) = make_float4(acc.v[0], acc.v[1], acc.v[2], acc.v[3]);
+      *reinterpret_cast<float4*>(slot_p + ring_o1) = make_float4(acc.v[4], acc.v[5], acc.v[6], acc.v[7]);
+      if (sub == 0) meta[q * 8 + grp] = finish ? rowp : -1;
       __syncwarp();
-      uint32_t old = 0;
-      if (lane == 0) {
-        mbar_arrive(bar_full + (int)(tl % (2 * kBfStages)));
-        asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(arrivals + stage)) : "memory");
+      if (lane == 0) mbar_arrive(ring_full + q);
+    }
+  } else if (warp >= kBfEpiWarps) {
+    // ------------------------------- image warps -------------------------------
+    // lane 8 qq + j owns row j of the warp's pass and the 32-byte chunk qq; the two 16-byte chunks are stored in the
+    // order (j >> 2): the 8 lanes of a quarter warp hit 8 different 16-byte bank groups in the K-major images (bank
+    // group = row & 7) and in the swizzled MN-major ones (bank group = (((q >> 1) ^ (row & 3)) << 1) | (q & 1))
+    const int pw = warp - kBfEpiWarps;
+    const int j = lane & 7, qq = lane >> 3, flip = j >> 2;
+    const int r0 = 8 * pw + j;
+    const int qa = 2 * qq + flip, qb = 2 * qq + (flip ^ 1);
+    const int ko_a = bf_k_off(r0, qa), ko_b = bf_k_off(r0, qb);
+    const int mo_a = bf_mn_off(r0, qa), mo_b = bf_mn_off(r0, qb);
+    const int ring_a = j * 128 + ((qa ^ j) << 4), ring_b = j * 128 + ((qb ^ j) << 4);
+    const uint32_t idG64 = umma_idesc_tf32(64, 64), idG32 = umma_idesc_tf32(64, 32), idT = umma_idesc_tf32(128, 64, 1, 1);
+    const uint64_t dK = umma_desc(smem_u32(smem), 128, 1024, 0), dM = umma_desc(smem_u32(smem), kBfImg, 512, 1);
+    float acc_dr[2][4];   // column sums of gy over this thread's rows
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc_dr[i][t] = 0.f;
+    // own rows of a pass: row id from the ring's meta words, gy and z chunks, one scalar per chunk lane
+    // (qq = 0: row_scale, 1: x_scale, 2: hmask_prev, 3: post)
+    struct Own {
+      int row;
+      uint32_t sc;
+      BfF8 gy, z;
+    };
+    auto load_own = [&](int tl) {
+      Own o;
+      o.row = meta[((tl * kBfPasses + pw) % kBfRing) * 8 + j];
+      const int64_t off = (int64_t)(o.row >= 0 ? o.row : 0) * kGH + 8 * qq;
+      o.gy = bf_ld_f8_stream(a.gy + off, pol);
+      o.z = bf_ld_f8_stream(a.z + off, pol);
+      o.sc = qq == 2 ? 0u : 0x3f800000u;
+      const void* sp = qq == 0 ? (const void*)a.row_scale : qq == 1 ? (const void*)a.x_scale
+                       : qq == 2 ? (const void*)a.hmask_prev : (const void*)a.post;
+      if (o.row >= 0 && sp) o.sc = __ldg(reinterpret_cast<const uint32_t*>(sp) + o.row);
+      return o;
+    };
+    auto slot_parity = [&](int tl) { return (uint32_t)((tl * kBfPasses + pw) / kBfRing) & 1u; };
+    Own cur, nxt;
+    if (my_tiles > 0) {
+      bf_wait(ring_full + (pw % kBfRing), 0, MGCN_BF_SLEEP_I);
+      cur = load_own(0);
+    }
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int gp = tl * kBfPasses + pw, q = gp % kBfRing;
+      const int stage = tl & 1;
+      // next tile's pass: its own rows are requested now if the gather warps are already there
+      bool have_nxt = false;
+      if (tl + 1 < my_tiles) {
+        have_nxt = bf_mbar_test(ring_full + ((gp + kBfPasses) % kBfRing), slot_parity(tl + 1));
+        if (have_nxt) nxt = load_own(tl + 1);
       }
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if ((old % kBfPasses) == kBfPasses - 1) {
-        // last pass of the tile: wait for the other passes' arrivals (acquire), then the accumulator buffer
-        const uint32_t use = (uint32_t)(tl / kBfStages);
-        mbar_wait(bar_full + (int)(tl % (2 * kBfStages)), (uint32_t)(tl / (2 * kBfStages)) & 1u);
-        if (use >= 1) mbar_wait(bar_tfree + stage, (use - 1) & 1u);
+      // the ring rows of this pass, then the slot goes back to the gather warps
+      const unsigned char* slot_p = smem + kBfOffRing + q * 1024;
+      float4 da = *reinterpret_cast<const float4*>(slot_p + ring_a), db = *reinterpret_cast<const float4*>(slot_p + ring_b);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring_free + q);
+      const bool valid = cur.row >= 0;
+      const float pre_v = __uint_as_float(__shfl_sync(0xffffffffu, cur.sc, j));        // lane j: qq = 0
+      const float xs_v = __uint_as_float(__shfl_sync(0xffffffffu, cur.sc, 8 + j));     // qq = 1
+      const uint32_t hm_v = __shfl_sync(0xffffffffu, cur.sc, 16 + j);
+      const uint32_t post_v = __shfl_sync(0xffffffffu, cur.sc, 24 + j);
+      if (!valid) {
+        da = db = make_float4(0.f, 0.f, 0.f, 0.f);
+        cur.gy.lo = cur.gy.hi = cur.z.lo = cur.z.hi = da;
+      } else if (a.row_scale) {
+        da.x *= pre_v; da.y *= pre_v; da.z *= pre_v; da.w *= pre_v;
+        db.x *= pre_v; db.y *= pre_v; db.z *= pre_v; db.w *= pre_v;
+      }
+      // the tensor core has consumed this stage's previous tile
+      if (tl >= 2) bf_wait(bar_done + ((tl - 2) & 3), (uint32_t)((tl - 2) >> 2) & 1u, MGCN_BF_SLEEP_I);
+      unsigned char* st = smem + stage * kBfStageB;
+      float4 hi, lo;
+      // dxw (da = chunk qa, db = chunk qb)
+      bf_split4(da, hi, lo);
+      *reinterpret_cast<float4*>(st + kBfKDh + ko_a) = hi;
+      *reinterpret_cast<float4*>(st + kBfKDl + ko_a) = lo;
+      *reinterpret_cast<float4*>(st + kBfMN + 0 * kBfImg + mo_a) = hi;
+      *reinterpret_cast<float4*>(st + kBfMN + 2 * kBfImg + mo_a) = lo;
+      bf_split4(db, hi, lo);
+      *reinterpret_cast<float4*>(st + kBfKDh + ko_b) = hi;
+      *reinterpret_cast<float4*>(st + kBfKDl + ko_b) = lo;
+      *reinterpret_cast<float4*>(st + kBfMN + 0 * kBfImg + mo_b) = hi;
+      *reinterpret_cast<float4*>(st + kBfMN + 2 * kBfImg + mo_b) = lo;
+      // gy
+      {
+        const float4 g0 = cur.gy.lo, g1 = cur.gy.hi;
+        acc_dr[0][0] += g0.x; acc_dr[0][1] += g0.y; acc_dr[0][2] += g0.z; acc_dr[0][3] += g0.w;
+        acc_dr[1][0] += g1.x; acc_dr[1][1] += g1.y; acc_dr[1][2] += g1.z; acc_dr[1][3] += g1.w;
+      }
+      bf_split4(flip ? cur.gy.hi : cur.gy.lo, hi, lo);
+      *reinterpret_cast<float4*>(st + kBfKGh + ko_a) = hi;
+      *reinterpret_cast<float4*>(st + kBfKGl + ko_a) = lo;
+      *reinterpret_cast<float4*>(st + kBfMN + 1 * kBfImg + mo_a) = hi;
+      *reinterpret_cast<float4*>(st + kBfMN + 3 * kBfImg + mo_a) = lo;
+      bf_split4(flip ? cur.gy.lo : cur.gy.hi, hi, lo);
+      *reinterpret_cast<float4*>(st + kBfKGh + ko_b) = hi;
+      *reinterpret_cast<float4*>(st + kBfKGl + ko_b) = lo;
+      *reinterpret_cast<float4*>(st + kBfMN + 1 * kBfImg + mo_b) = hi;
+      *reinterpret_cast<float4*>(st + kBfMN + 3 * kBfImg + mo_b) = lo;
+      // x = z / x_scale
+      if (a.x_scale) {
+        const float inv = __frcp_rn(xs_v);
+        BfF8& v = cur.z;
+        v.lo.x *= inv; v.lo.y *= inv; v.lo.z *= inv; v.lo.w *= inv;
+        v.hi.x *= inv; v.hi.y *= inv; v.hi.z *= inv; v.hi.w *= inv;
+      }
+      uint32_t xb;
+      {
+        const float4 x0 = cur.z.lo, x1 = cur.z.hi;
+        xb = (x0.x > 0.f ? 1u : 0u) | (x0.y > 0.f ? 2u : 0u) | (x0.z > 0.f ? 4u : 0u) | (x0.w > 0.f ? 8u : 0u) |
+             (x1.x > 0.f ? 16u : 0u) | (x1.y > 0.f ? 32u : 0u) | (x1.z > 0.f ? 64u : 0u) | (x1.w > 0.f ? 128u : 0u);
+        xb <<= 8 * qq;
+      }
+      bf_split4(flip ? cur.z.hi : cur.z.lo, hi, lo);
+      *reinterpret_cast<float4*>(st + kBfMXh + mo_a) = hi;
+      *reinterpret_cast<float4*>(st + kBfMXl + mo_a) = lo;
+      bf_split4(flip ? cur.z.lo : cur.z.hi, hi, lo);
+      *reinterpret_cast<float4*>(st + kBfMXh + mo_b) = hi;
+      *reinterpret_cast<float4*>(st + kBfMXl + mo_b) = lo;
+      xb |= __shfl_xor_sync(0xffffffffu, xb, 8);
+      xb |= __shfl_xor_sync(0xffffffffu, xb, 16);
+      // scalar ring (slot tile % 4: its previous tile was drained by the epilogue before MMA(tl - 2) was issued)
+      if (qq == 0) scal[(tl & 3) * kBfRows + r0] = make_uint4((uint32_t)cur.row, xb, hm_v, post_v);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + (tl & 3));
+      if (pw == (tl & 7)) {
+        // this warp issues the tile's 24 tcgen05.mma (lane 0) once all 8 image warps have arrived and the epilogue has
+        // drained the accumulator buffer
+        bf_wait(bar_full + (tl & 3), (uint32_t)(tl >> 2) & 1u, MGCN_BF_SLEEP_I);
+        if (tl >= 2) bf_wait(bar_tfree + stage, (uint32_t)((tl >> 1) - 1) & 1u, MGCN_BF_SLEEP_I);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t tb = tmem + stage * kBfTmemBuf;
@@ -410,7 +488,7 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
           if (want_prev) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint32_t ko = 2 * k;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+              const uint32_t ko = (256 * k) >> 4;   // 8 columns = two 16-byte chunks
               const uint64_t b1 = dK + ((kBfOffB1 >> 4) + ko), b2 = dK + ((kBfOffB2 >> 4) + ko);
               umma_tf32(tb + 0, dK + (so + (kBfKDh >> 4) + ko), b1, idG64, k > 0);    // dxw_hi [Wt_hi | Wt_lo]
               umma_tf32(tb + 0, dK + (so + (kBfKGh >> 4) + ko), b2, idG64, 1);        // gy_hi  [R_hi | R_lo]
@@ -421,87 +499,95 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
 #pragma unroll
           for (int k = 0; k < kBfRows / 8; ++k) {
             const uint32_t ko = (1024 * k) >> 4;    // 8 rows = two 4-row atoms
-#ifndef MGCN_BF_NO_T
             umma_tf32(tb + 64, dM + (so + (kBfMN >> 4) + ko), dM + (so + (kBfMXh >> 4) + ko), idT, k > 0);
-#endif
-#ifndef MGCN_BF_NO_COLSUM
-            umma_tf32(tb + 128, dOnes, dM2 + (so + ((kBfMN + kBfImg) >> 4) + ko), idC, k > 0);
-#endif
           }
-          umma_commit(bar_done + (int)(tl % (2 * kBfStages)));
+          umma_commit(bar_done + (tl & 3));
         }
         __syncwarp();
       }
+      if (tl + 1 < my_tiles) {
+        if (!have_nxt) {
+          bf_wait(ring_full + ((gp + kBfPasses) % kBfRing), slot_parity(tl + 1), MGCN_BF_SLEEP_I);
+          nxt = load_own(tl + 1);
+        }
+        cur = nxt;
+      }
     }
+    // dr[c]: this thread holds columns 8 qq + 4 i + t summed over its rows; rows of the warp are added in a fixed
+    // butterfly order, the 8 warps by one thread per column at the end of the kernel
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float v = acc_dr[i][t];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (j == 0) dr_red[pw * 32 + 8 * qq + 4 * i + t] = v;
+      }
   } else {
     // ------------------------------- epilogue -------------------------------
-    // warp = (column half, TMEM quarter).  T: TMEM lane 32 quarter + lane = row of [dxw_hi | gy_hi | dxw_lo | gy_lo]^T x,
-    // this warp's 16 columns; G: lanes 0..15 of the quarter carry tile rows 16 quarter .. + 15, this warp's 16 columns
-    const int quarter = warp & 3, half = warp >> 2;
-    float acc_t[16], acc_b[8];
+    // T: TMEM lane 32 warp + lane = row of [dxw_hi | gy_hi | dxw_lo | gy_lo]^T x; G: lanes 0..15 of quarter `warp` carry
+    // tile rows 16 warp .. 16 warp + 15
+    float acc_t[32];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) acc_t[t] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) acc_b[t] = 0.f;
-    const int r = 16 * quarter + (lane & 15);
+    for (int t = 0; t < 32; ++t) acc_t[t] = 0.f;
+    const int r = 16 * warp + (lane & 15);
     float* stg_y = reinterpret_cast<float*>(smem + kBfOffOut) + warp * (2 * 16 * kBfLdo);   // [16][kBfLdo]
     float* stg_s = stg_y + 16 * kBfLdo;
-    int tl = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
-      const int stage = tl % kBfStages;
-      mbar_wait(bar_done + tl % (2 * kBfStages), (uint32_t)(tl / (2 * kBfStages)) & 1u);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int stage = tl & 1;
+      bf_wait(bar_done + (tl & 3), (uint32_t)(tl >> 2) & 1u, MGCN_BF_SLEEP_E);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t ta = tmem + stage * kBfTmemBuf + ((uint32_t)(32 * quarter) << 16);
-      {
-        uint32_t d1[16], d2[16], cs[8];
-        bf_tmem_ld16(ta + 64 + 16 * half, d1);
-        bf_tmem_ld16(ta + 96 + 16 * half, d2);
-        bf_tmem_ld8(ta + 128 + 8 * warp, cs);
+      const uint32_t ta = tmem + stage * kBfTmemBuf + ((uint32_t)(32 * warp) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < 32; c0 += 8) {
+        uint32_t d1[8], d2[8];
+        bf_tmem_ld8(ta + 64 + c0, d1);
+        bf_tmem_ld8(ta + 96 + c0, d2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int t = 0; t < 16; ++t) acc_t[t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc_b[t] += __uint_as_float(cs[t]);
+        for (int t = 0; t < 8; ++t) acc_t[c0 + t] += __uint_as_float(d1[t]) + __uint_as_float(d2[t]);
       }
       if (want_prev) {
-        mbar_wait(bar_full + tl % (2 * kBfStages), (uint32_t)(tl / (2 * kBfStages)) & 1u);   // acquire the scalar ring
-        const uint4* ring = scal + (tl % (2 * kBfStages)) * kBfRows;
+        mbar_wait(bar_full + (tl & 3), (uint32_t)(tl >> 2) & 1u);   // acquire the scalar ring
+        const uint4* ring = scal + (tl & 3) * kBfRows;
         const uint4 sc4 = ring[r];
-        const int row_a = (int)ring[16 * quarter + (lane & 7)].x, row_b = (int)ring[16 * quarter + 8 + (lane & 7)].x;
-        const uint32_t xb = sc4.y >> (16 * half), hb = sc4.z >> (16 * half);
+        const int row_a = (int)ring[16 * warp + (lane & 7)].x, row_b = (int)ring[16 * warp + 8 + (lane & 7)].x;
+        const uint32_t xb = sc4.y, hb = sc4.z;
         const float postv = __uint_as_float(sc4.w);
-        uint32_t m[16], c1[16];
-        bf_tmem_ld16(ta + 0 + 16 * half, m);
-        bf_tmem_ld16(ta + 32 + 16 * half, c1);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        // the accumulator buffer is in registers: hand it back; the warp barrier also orders the previous tile's reads of
-        // the staging rows before this tile's writes
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tfree + stage);
+        __syncwarp();   // the previous tile's staged rows have been read by every lane
 #pragma unroll
-        for (int c0 = 0; c0 < 16; c0 += 4) {
-          float g[4], sv[4];
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+          uint32_t m[8], c1[8];
+          bf_tmem_ld8(ta + 0 + c0, m);
+          bf_tmem_ld8(ta + 32 + c0, c1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float g[8], sv[8];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
+          for (int t = 0; t < 8; ++t) {
             const int c = c0 + t;
-            const float gv = __uint_as_float(m[c]) + __uint_as_float(c1[c]);
+            const float gv = __uint_as_float(m[t]) + __uint_as_float(c1[t]);
             g[t] = ((xb >> c) & 1u) ? gv : 0.f;
             sv[t] = ((hb >> c) & 1u) ? g[t] * postv : 0.f;
           }
           if (lane < 16) {
-            *reinterpret_cast<float4*>(stg_y + (lane & 15) * kBfLdo + c0) = make_float4(g[0], g[1], g[2], g[3]);
-            *reinterpret_cast<float4*>(stg_s + (lane & 15) * kBfLdo + c0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            *reinterpret_cast<float4*>(stg_y + lane * kBfLdo + c0) = make_float4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<float4*>(stg_y + lane * kBfLdo + c0 + 4) = make_float4(g[4], g[5], g[6], g[7]);
+            *reinterpret_cast<float4*>(stg_s + lane * kBfLdo + c0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            *reinterpret_cast<float4*>(stg_s + lane * kBfLdo + c0 + 4) = make_float4(sv[4], sv[5], sv[6], sv[7]);
           }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        // staged half rows -> global: lane j moves the 16-byte chunk j >> 3 of rows j & 7 and 8 + (j & 7)
+        if (lane == 0) mbar_arrive(bar_tfree + stage);
+        // staged rows -> global: lane l moves the 16-byte chunks (l >> 3) and 4 + (l >> 3) of rows l & 7 and 8 + (l & 7)
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int lr = 8 * it + (lane & 7), ch = lane >> 3;
-          const int row = it == 0 ? row_a : row_b;
+        for (int it = 0; it < 4; ++it) {
+          const int lr = 8 * (it & 1) + (lane & 7), ch = (lane >> 3) + 4 * (it >> 1);
+          const int row = (it & 1) ? row_b : row_a;
           if (row >= 0) {
-            const int64_t o = (int64_t)row * kGH + 16 * half + 4 * ch;
+            const int64_t o = (int64_t)row * kGH + 4 * ch;
             st_f4_hint(a.gy_prev + o, *reinterpret_cast<const float4*>(stg_y + lr * kBfLdo + 4 * ch), pol);
             st_f4_hint(a.gs_prev + o, *reinterpret_cast<const float4*>(stg_s + lr * kBfLdo + 4 * ch), pol);
           }
@@ -512,21 +598,22 @@ __global__ void __launch_bounds__(kBfThreads, 1) k_gcn_bwd_fused(const BwdFusedA
         if (lane == 0) mbar_arrive(bar_tfree + stage);
       }
     }
-    // per-CTA partials: row = TMEM lane of the transposed products; column sums of gy from lane 0 of every warp
-    float* p = a.part_t + ((int64_t)blockIdx.x * 128 + 32 * quarter + lane) * 32 + 16 * half;
+    // per-CTA partials of the transposed products: row = TMEM lane
+    float* p = a.part_t + ((int64_t)blockIdx.x * 128 + 32 * warp + lane) * 32;
 #pragma unroll
-    for (int t = 0; t < 16; t += 4) *reinterpret_cast<float4*>(p + t) = make_float4(acc_t[t], acc_t[t + 1], acc_t[t + 2], acc_t[t + 3]);
-    if (lane == 0) {
-      float* pb = a.part_b + (int64_t)blockIdx.x * 64 + 8 * warp;   // [gy_hi 0..31 | gy_lo 0..31]
-#pragma unroll
-      for (int t = 0; t < 8; ++t) pb[t] = acc_b[t];
-    }
+    for (int t = 0; t < 32; t += 4) *reinterpret_cast<float4*>(p + t) = make_float4(acc_t[t], acc_t[t + 1], acc_t[t + 2], acc_t[t + 3]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    if (my_tiles > 0)
+      for (int w = 0; w < kBfImgWarps; ++w) s += dr_red[w * 32 + tid];
+    a.part_b[(int64_t)blockIdx.x * 32 + tid] = s;
+  }
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
   }
 }
 
@@ -537,7 +624,7 @@ using namespace mgcn;
 extern "C" int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, const float* gy, const float* z,
                                         const float* x_scale, const float* row_scale, const float* w,
                                         const float* res_w, const uint32_t* hmask_prev, const float* post, int64_t H,
-                                        int static_slots, float* gy_prev, float* gs_prev, float* dw, float* d_res_w, float* d_res_b,
+                                        float* gy_prev, float* gs_prev, float* dw, float* d_res_w, float* d_res_b,
                                         void* workspace, size_t* workspace_bytes, void* stream) {
   MGCN_REQUIRE(workspace_bytes != nullptr && gt != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(H == kGH, MGCN_ERR_SHAPE);
@@ -552,7 +639,7 @@ extern "C" int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, c
   WorkspaceCarver ws(workspace);
   float* partial = ws.take<float>((size_t)seg_cap * kGH);
   float* part_t = ws.take<float>((size_t)(P0 + P1) * 128 * 32);
-  float* part_b = ws.take<float>((size_t)(P0 + P1) * 2 * 32);
+  float* part_b = ws.take<float>((size_t)(P0 + P1) * 32);
   if (workspace == nullptr) {
     *workspace_bytes = ws.bytes();
     return MGCN_OK;
@@ -569,8 +656,10 @@ extern "C" int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, c
   }
   MGCN_REQUIRE(gs && gy && z && w && res_w && gt->rowptr && gt->tasks, MGCN_ERR_NULL);
   MGCN_REQUIRE(gt->nnz_cap == 0 || gt->nbr_w, MGCN_ERR_NULL);
-  MGCN_REQUIRE((reinterpret_cast<uintptr_t>(gs) & 31u) == 0 && (reinterpret_cast<uintptr_t>(gy) & 31u) == 0, MGCN_ERR_ALIGN);
-  MGCN_REQUIRE(aligned16(gt->tasks) && aligned16(z) && aligned16(partial) && (!gy_prev || aligned16(gy_prev)) &&
+  MGCN_REQUIRE((reinterpret_cast<uintptr_t>(gs) & 31u) == 0 && (reinterpret_cast<uintptr_t>(gy) & 31u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(z) & 31u) == 0,
+               MGCN_ERR_ALIGN);   // 256-bit row loads
+  MGCN_REQUIRE(aligned16(gt->tasks) && aligned16(partial) && (!gy_prev || aligned16(gy_prev)) &&
                    (!gs_prev || aligned16(gs_prev)),
                MGCN_ERR_ALIGN);
   BwdFusedArgs a{};
@@ -590,16 +679,15 @@ extern "C" int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, c
   a.n_rows = gt->n_rows;
   a.seg_cap = seg_cap;
   a.hub_cap = hub_cap;
-  a.static_slots = static_slots ? 1 : 0;
   MGCN_CHECK_CUDA(cudaFuncSetAttribute(k_gcn_bwd_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBfSmem));
   MGCN_CHECK_CUDA(cudaFuncSetAttribute(k_gcn_bwd_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBfSmem));
   MGCN_LAUNCH(k_gcn_bwd_fused<0>, (unsigned)P0, kBfThreads, kBfSmem, stream, a);
   if (hubs) {
     a.part_t = part_t + (size_t)P0 * 128 * 32;
-    a.part_b = part_b + (size_t)P0 * 2 * 32;
+    a.part_b = part_b + (size_t)P0 * 32;
     MGCN_LAUNCH(k_gcn_bwd_fused<1>, (unsigned)P1, kBfThreads, kBfSmem, stream, a);
   }
   const int rc = launch_bwd_tc_reduce(part_t, P0 + P1, dw, d_res_w, stream);
   if (rc != MGCN_OK) return rc;
-  return launch_reduce_partials(part_b, 2 * (P0 + P1), 32, 32, d_res_b, 0, 1, stream);
+  return launch_reduce_partials(part_b, P0 + P1, 32, 32, d_res_b, 0, 1, stream);
 }

@@ -20,6 +20,11 @@ BWD_TENSOR_MEMORY = True
 # hidden-32 stack: aggregate-then-transform forward on tcgen05 (csrc/gcn_fwd_tc.cu; one [N,32] read + one write per
 # layer) or the transform-then-aggregate kernels of round 1 (csrc/gcn_layer.cu); both pass the same parity tests
 FORWARD_AGGREGATE_FIRST = True
+# aggregate-then-transform stack: transposed aggregation + row-local backward as ONE launch per layer
+# (csrc/gcn_bwd_fused.cu: no dxw array, 0.9 GB less DRAM traffic per layer) instead of two.  Same parity tests,
+# identical from run to run — but measured SLOWER at the botnet batch (1.45 ms against 0.48 + 0.61 ms: the per-row
+# operand-image work needs more warps than fit next to a 16-warp gather), so it is off by default
+BWD_FUSED = False
 
 
 class _ResidualGCNStack(torch.autograd.Function):
@@ -217,11 +222,16 @@ class _ResidualGCNStack32AT(torch.autograd.Function):
         gs = ops.mask_bits_scale_impl(gy, hmasks[L - 1], post)
         last = 1 if ctx.agg_first else 0
         for n in range(L - 1, last - 1, -1):
-            dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
             want_prev = n > 0
-            gy_prev, gs_prev, dw, drw, drb = ops.gcn_layer_bwd_impl(
-                dxw, gy, zs[n], layers[n][0], layers[n][1], hmasks[n - 1] if want_prev else None, post,
-                want_prev, True, x_scale=sigma)
+            if BWD_FUSED:
+                gy_prev, gs_prev, dw, drw, drb = ops.gcn_layer_bwd_fused_impl(
+                    bwd, gs, gy, zs[n], layers[n][0], layers[n][1], hmasks[n - 1] if want_prev else None, post,
+                    row_scale=pre, x_scale=sigma, want_prev=want_prev)
+            else:
+                dxw = ops.aggregate_prescaled_impl(bwd, gs, pre, 0, None, None, 0)
+                gy_prev, gs_prev, dw, drw, drb = ops.gcn_layer_bwd_impl(
+                    dxw, gy, zs[n], layers[n][0], layers[n][1], hmasks[n - 1] if want_prev else None, post,
+                    want_prev, True, x_scale=sigma)
             grads[3 * n], grads[3 * n + 1], grads[3 * n + 2] = dw, drw, drb
             if want_prev:
                 gy, gs = gy_prev, gs_prev

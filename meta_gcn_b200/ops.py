@@ -550,11 +550,7 @@ def gcn_layer_bwd_impl(dxw, gy, x, w, res_w, hmask_prev, post, want_prev=True, t
     return gy_prev, gs_prev, dw, drw, drb
 
 
-BWD_FUSED_STATIC_SLOTS = True
-
-
-def gcn_layer_bwd_fused_impl(csr_t, gs, gy, z, w, res_w, hmask_prev, post, row_scale=None, x_scale=None, want_prev=True,
-                             static_slots=None):
+def gcn_layer_bwd_fused_impl(csr_t, gs, gy, z, w, res_w, hmask_prev, post, row_scale=None, x_scale=None, want_prev=True):
     """the whole backward of one hidden-32 layer in one launch (mgcn_gcn_layer_bwd_fused): transposed aggregation of gs
     over the by-source structure csr_t (scaled by row_scale) + the row-local products with x = z / x_scale; returns
     (gy_prev | None, gs_prev | None, dw, d_res_w, d_res_b)"""
@@ -578,8 +574,7 @@ def gcn_layer_bwd_fused_impl(csr_t, gs, gy, z, w, res_w, hmask_prev, post, row_s
     drb = torch.empty(H, dtype=torch.float32, device=dev)
     lib = _lib.load()
     args = (ctypes.byref(csr_t.struct()), _ptr(gs), _ptr(gy), _ptr(z), _ptr(x_scale), _ptr(row_scale), _ptr(w),
-            _ptr(res_w), _ptr(hmask_prev) if want_prev else None, _ptr(post), H,
-            int(BWD_FUSED_STATIC_SLOTS if static_slots is None else static_slots), _ptr(gy_prev), _ptr(gs_prev),
+            _ptr(res_w), _ptr(hmask_prev) if want_prev else None, _ptr(post), H, _ptr(gy_prev), _ptr(gs_prev),
             _ptr(dw), _ptr(drw), _ptr(drb))
     fn = lib.mgcn_gcn_layer_bwd_fused
     ws, nbytes = _workspace(lambda w_, nb, stm: fn(*args, w_, nb, stm), dev)

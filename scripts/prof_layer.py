@@ -73,11 +73,7 @@ timeit("agg_plain fwd structure", lambda: ops.aggregate_prescaled_impl(gs.fwd, g
 timeit("layer_bwd (row-local, 4 products)", lambda: ops.gcn_layer_bwd_impl(m, gy, x, w, r, bits, dis, True), 5 * nh + 8 * n)
 timeit("layer_bwd tcgen05 variant", lambda: ops.gcn_layer_bwd_impl(m, gy, x, w, r, bits, dis, True, True), 5 * nh + 8 * n)
 if hasattr(ops, "gcn_layer_bwd_fused_impl"):
-    timeit("layer_bwd fused, completion-order slots",
-           lambda: ops.gcn_layer_bwd_fused_impl(gs.bwd, m, gy, x, w, r, bits, dis, row_scale=dis, x_scale=dis, static_slots=False),
-           b_agg(n, e, H) + nh)
-    timeit("layer_bwd fused, static slots",
-           lambda: ops.gcn_layer_bwd_fused_impl(gs.bwd, m, gy, x, w, r, bits, dis, row_scale=dis, x_scale=dis, static_slots=True),
-           b_agg(n, e, H) + nh)
+    timeit("layer_bwd fused (gather + 4 products)",
+           lambda: ops.gcn_layer_bwd_fused_impl(gs.bwd, m, gy, x, w, r, bits, dis, row_scale=dis, x_scale=dis), b_agg(n, e, H) + nh)
 timeit("mask_bits_scale", lambda: ops.mask_bits_scale_impl(gy, bits, dis), 2 * nh + 8 * n)
 timeit("torch copy", lambda: m.copy_(x), 2 * nh)

@@ -346,10 +346,6 @@ def test_layer_bwd_fused(n, e, scaled, want_prev):
     again = ops.gcn_layer_bwd_fused_impl(*args, row_scale=d(pre), x_scale=d(sigma), want_prev=want_prev)
     for got, ref, name in zip((gyp, gsp, dw, drw, drb), again, ("gy_prev", "gs_prev", "dW", "dR", "dr")):
         assert_bitexact(got, ref, "run-to-run " + name)
-    # completion-order slots: same results up to the summation order of the weight gradients
-    dyn = ops.gcn_layer_bwd_fused_impl(*args, row_scale=d(pre), x_scale=d(sigma), want_prev=want_prev, static_slots=False)
-    assert_bitexact(gyp, dyn[0], "gy_prev, completion-order slots")
-    assert_parity(dyn[2], xin.t() @ dxw, "dW, completion-order slots")
     # the two-launch path computes the same thing
     if n > 0:
         dxw2 = ops.aggregate_prescaled_impl(struct.bwd, d(gs_in), d(pre), 0, None, None, 0)
