@@ -38,6 +38,13 @@ class GCNConv(torch.nn.Module):
         if edge_weight is None and not self.improved:
             deg = graph.out_degree()
         else:
+            # PyG's add_remaining_self_loops keeps the weight of a self loop that is already in edge_index and gives
+            # `fill` only to the nodes without one; this structure drops existing loops and appends one of weight `fill`
+            # per node, which is the same thing only when there are none (kernel/gcn.py's unweighted default never
+            # comes here).  Refuse the other case instead of returning different numbers.
+            if graph.has_self_loops():
+                raise NotImplementedError("GCNConv with improved=True or edge_weight on an edge_index that already "
+                                          "contains self loops (their weights would have to be carried over)")
             ew = edge_weight if edge_weight is not None else torch.ones(
                 edge_index.size(1), dtype=x.dtype, device=x.device)
             edge_weight = ew

@@ -43,7 +43,10 @@ struct HeadArgs {
   int C;
 };
 
-template <int L>
+// CM = compile-time bound on the class count (2: the botnet head; 8: anything up to kHeadMaxC) — the per-class arrays
+// live in registers, and at CM = 8 they cost the occupancy that hides the latency of the row loads.  Two rows per
+// thread and iteration are loaded before either is used (same summation order as one row per iteration).
+template <int L, int CM>
 __global__ void __launch_bounds__(kHeadThreads) k_head_ce_fwd(const HeadArgs a) {
   constexpr int H = 4 * L, RPW = 32 / L;
   __shared__ float ws[kHeadMaxC][H];
@@ -55,50 +58,49 @@ __global__ void __launch_bounds__(kHeadThreads) k_head_ce_fwd(const HeadArgs a) 
   const int sub = lane % L, rw = lane / L;
   float loss = 0.f;
   unsigned long long cnt[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+  float bv[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) bv[c] = (c < a.C && a.b) ? __ldg(a.b + c) : 0.f;
   const int64_t rows_per_iter = (int64_t)gridDim.x * (kHeadThreads / 32) * RPW;
   // a block owns a contiguous slab of rows (fixed summation order per block)
   const int64_t iters = (a.N + rows_per_iter - 1) / rows_per_iter;
   const int64_t slab0 = (int64_t)blockIdx.x * iters * (kHeadThreads / 32) * RPW;
-  for (int64_t it = 0; it < iters; ++it) {
-    const int64_t n = slab0 + (it * (kHeadThreads / 32) + warp) * RPW + rw;
-    const bool ok = n < a.N && n < slab0 + iters * (kHeadThreads / 32) * RPW;
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) xv = __ldg(reinterpret_cast<const float4*>(a.x + n * H) + sub);
-    float z[kHeadMaxC];
+  auto row_of = [&](int64_t it) { return slab0 + (it * (kHeadThreads / 32) + warp) * RPW + rw; };
+  auto process = [&](int64_t n, bool ok, const float4 xv, int64_t y) {
+    float z[CM];
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c) {
+    for (int c = 0; c < CM; ++c) {
       if (c < a.C) {
         const float4 wv = *reinterpret_cast<const float4*>(&ws[c][4 * sub]);
         float p = xv.x * wv.x;
         p = fmaf(xv.y, wv.y, p);
         p = fmaf(xv.z, wv.z, p);
         p = fmaf(xv.w, wv.w, p);
-        z[c] = group_sum<L>(p) + (a.b ? __ldg(a.b + c) : 0.f);
+        z[c] = group_sum<L>(p) + bv[c];
       }
     }
     if (ok && sub == 0) {
       float m = z[0];
       int am = 0;
 #pragma unroll
-      for (int c = 1; c < kHeadMaxC; ++c)
+      for (int c = 1; c < CM; ++c)
         if (c < a.C && z[c] > m) {
           m = z[c];
           am = c;
         }
       float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < kHeadMaxC; ++c)
+      for (int c = 0; c < CM; ++c)
         if (c < a.C) {
           s += expf(z[c] - m);
           a.logits[n * a.C + c] = z[c];
         }
-      const int64_t y = a.target[n];
       if (y < 0 || y >= a.C) {
         *a.bad = 1;
       } else {
         float zy = z[0];
 #pragma unroll
-        for (int c = 1; c < kHeadMaxC; ++c)
+        for (int c = 1; c < CM; ++c)
           if (c == (int)y) zy = z[c];
         loss += (m + logf(s)) - zy;
         if (a.counts) {   // optim/metrics.py:8-24: positives are class 1
@@ -110,6 +112,18 @@ __global__ void __launch_bounds__(kHeadThreads) k_head_ce_fwd(const HeadArgs a) 
         }
       }
     }
+  };
+  for (int64_t it = 0; it < iters; it += 2) {
+    const int64_t n0 = row_of(it), n1 = row_of(it + 1);
+    const bool ok0 = n0 < a.N, ok1 = it + 1 < iters && n1 < a.N;
+    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+    int64_t y0 = 0, y1 = 0;
+    if (ok0) x0 = __ldg(reinterpret_cast<const float4*>(a.x + n0 * H) + sub);
+    if (ok1) x1 = __ldg(reinterpret_cast<const float4*>(a.x + n1 * H) + sub);
+    if (ok0 && sub == 0) y0 = __ldg(a.target + n0);
+    if (ok1 && sub == 0) y1 = __ldg(a.target + n1);
+    process(n0, ok0, x0, y0);
+    process(n1, ok1, x1, y1);
   }
   // warp: lanes in a fixed butterfly; block: warps in order
   for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
@@ -152,66 +166,87 @@ __global__ void __launch_bounds__(256) k_head_loss_finish(const float* __restric
 }
 
 // dl = (softmax(logits) - onehot) * g;  dx = dl F;  dF[c] += dl[c] x;  df[c] += dl[c]
-template <int L>
+template <int L, int CM>
 __global__ void __launch_bounds__(kHeadThreads) k_head_ce_bwd(const HeadArgs a) {
   constexpr int H = 4 * L, RPW = 32 / L;
   __shared__ float ws[kHeadMaxC][H];
-  __shared__ float redw[kHeadThreads / 32][kHeadMaxC][H];
-  __shared__ float redb[kHeadThreads / 32][kHeadMaxC];
+  __shared__ float redw[kHeadThreads / 32][CM][H];
+  __shared__ float redb[kHeadThreads / 32][CM];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < a.C * H; i += kHeadThreads) ws[i / H][i % H] = __ldg(a.w + i);
   __syncthreads();
   const int sub = lane % L, rw = lane / L;
   const float g = a.scale_const * (a.scale ? __ldg(a.scale) : 1.f);
-  float4 accw[kHeadMaxC];
-  float accb[kHeadMaxC];
+  float4 accw[CM];
+  float accb[CM];
 #pragma unroll
-  for (int c = 0; c < kHeadMaxC; ++c) {
+  for (int c = 0; c < CM; ++c) {
     accw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     accb[c] = 0.f;
   }
   const int64_t rows_per_iter = (int64_t)gridDim.x * (kHeadThreads / 32) * RPW;
   const int64_t iters = (a.N + rows_per_iter - 1) / rows_per_iter;
   const int64_t slab0 = (int64_t)blockIdx.x * iters * (kHeadThreads / 32) * RPW;
-  for (int64_t it = 0; it < iters; ++it) {
-    const int64_t n = slab0 + (it * (kHeadThreads / 32) + warp) * RPW + rw;
-    if (n >= a.N) continue;   // whole groups leave together: no shuffles below
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + n * H) + sub);
-    float z[kHeadMaxC];
+  auto row_of = [&](int64_t it) { return slab0 + (it * (kHeadThreads / 32) + warp) * RPW + rw; };
+  struct Row {
+    float4 xv;
+    float z[CM];
+    int64_t y;
+  };
+  auto load = [&](int64_t n, bool ok) {
+    Row r;
+    r.xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.y = 0;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) r.z[c] = 0.f;
+    if (ok) {
+      r.xv = __ldg(reinterpret_cast<const float4*>(a.x + n * H) + sub);
+#pragma unroll
+      for (int c = 0; c < CM; ++c)
+        if (c < a.C) r.z[c] = __ldg(a.logits + n * a.C + c);
+      r.y = __ldg(a.target + n);
+    }
+    return r;
+  };
+  auto process = [&](int64_t n, bool ok, const Row& r) {
+    if (!ok) return;   // whole groups leave together
     float m = -3.4e38f;
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c)
-      if (c < a.C) {
-        z[c] = __ldg(a.logits + n * a.C + c);
-        m = fmaxf(m, z[c]);
-      }
+    for (int c = 0; c < CM; ++c)
+      if (c < a.C) m = fmaxf(m, r.z[c]);
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c)
-      if (c < a.C) s += expf(z[c] - m);
+    for (int c = 0; c < CM; ++c)
+      if (c < a.C) s += expf(r.z[c] - m);
     const float inv = 1.f / s;
-    const int64_t y = a.target[n];
     float4 dxv = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < kHeadMaxC; ++c)
+    for (int c = 0; c < CM; ++c)
       if (c < a.C) {
-        const float dl = (expf(z[c] - m) * inv - (c == (int)y ? 1.f : 0.f)) * g;
+        const float dl = (expf(r.z[c] - m) * inv - (c == (int)r.y ? 1.f : 0.f)) * g;
         const float4 wv = *reinterpret_cast<const float4*>(&ws[c][4 * sub]);
         dxv.x = fmaf(dl, wv.x, dxv.x);
         dxv.y = fmaf(dl, wv.y, dxv.y);
         dxv.z = fmaf(dl, wv.z, dxv.z);
         dxv.w = fmaf(dl, wv.w, dxv.w);
-        accw[c].x = fmaf(dl, xv.x, accw[c].x);
-        accw[c].y = fmaf(dl, xv.y, accw[c].y);
-        accw[c].z = fmaf(dl, xv.z, accw[c].z);
-        accw[c].w = fmaf(dl, xv.w, accw[c].w);
+        accw[c].x = fmaf(dl, r.xv.x, accw[c].x);
+        accw[c].y = fmaf(dl, r.xv.y, accw[c].y);
+        accw[c].z = fmaf(dl, r.xv.z, accw[c].z);
+        accw[c].w = fmaf(dl, r.xv.w, accw[c].w);
         if (sub == 0) accb[c] += dl;
       }
     if (a.dx) reinterpret_cast<float4*>(a.dx + n * H)[sub] = dxv;
+  };
+  for (int64_t it = 0; it < iters; it += 2) {
+    const int64_t n0 = row_of(it), n1 = row_of(it + 1);
+    const bool ok0 = n0 < a.N, ok1 = it + 1 < iters && n1 < a.N;
+    const Row r0 = load(n0, ok0), r1 = load(n1, ok1);   // both rows in flight before either is used
+    process(n0, ok0, r0);
+    process(n1, ok1, r1);
   }
   // rows of a warp (lanes with the same sub) added in a fixed butterfly, warps in order
 #pragma unroll
-  for (int c = 0; c < kHeadMaxC; ++c) {
+  for (int c = 0; c < CM; ++c) {
     if (c < a.C) {
       float4 v = accw[c];
       float bsum = accb[c];
@@ -245,7 +280,7 @@ __global__ void __launch_bounds__(kHeadThreads) k_head_ce_bwd(const HeadArgs a) 
 
 static int head_grid(int64_t N) {
   int64_t b = ceil_div(N > 0 ? N : 1, 2048);
-  const int64_t cap = (int64_t)kNumSMs * 4;
+  const int64_t cap = (int64_t)kNumSMs * 6;
   return (int)(b < cap ? b : cap);
 }
 
@@ -277,11 +312,20 @@ extern "C" int mgcn_head_cross_entropy_fwd(const float* x, int64_t N, int64_t H,
   HeadArgs a{};
   a.x = x; a.w = w; a.b = b; a.target = target; a.logits = logits; a.part_loss = part;
   a.counts = reinterpret_cast<unsigned long long*>(counts5); a.bad = bad_target; a.N = N; a.C = (int)C;
-  switch (H) {
-    case 16: MGCN_LAUNCH(k_head_ce_fwd<4>, P, kHeadThreads, 0, stream, a); break;
-    case 32: MGCN_LAUNCH(k_head_ce_fwd<8>, P, kHeadThreads, 0, stream, a); break;
-    case 64: MGCN_LAUNCH(k_head_ce_fwd<16>, P, kHeadThreads, 0, stream, a); break;
-    default: MGCN_LAUNCH(k_head_ce_fwd<32>, P, kHeadThreads, 0, stream, a); break;
+  if (C <= 2) {
+    switch (H) {
+      case 16: MGCN_LAUNCH((k_head_ce_fwd<4, 2>), P, kHeadThreads, 0, stream, a); break;
+      case 32: MGCN_LAUNCH((k_head_ce_fwd<8, 2>), P, kHeadThreads, 0, stream, a); break;
+      case 64: MGCN_LAUNCH((k_head_ce_fwd<16, 2>), P, kHeadThreads, 0, stream, a); break;
+      default: MGCN_LAUNCH((k_head_ce_fwd<32, 2>), P, kHeadThreads, 0, stream, a); break;
+    }
+  } else {
+    switch (H) {
+      case 16: MGCN_LAUNCH((k_head_ce_fwd<4, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+      case 32: MGCN_LAUNCH((k_head_ce_fwd<8, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+      case 64: MGCN_LAUNCH((k_head_ce_fwd<16, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+      default: MGCN_LAUNCH((k_head_ce_fwd<32, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+    }
   }
   const float scale = mean ? (N > 0 ? 1.0f / (float)N : 0.f) : 1.f;
   MGCN_LAUNCH(k_head_loss_finish, 1, 256, 0, stream, part, P, scale, loss);
@@ -311,11 +355,20 @@ extern "C" int mgcn_head_cross_entropy_bwd(const float* x, const float* logits, 
   a.x = x; a.w = w; a.target = target; a.logits = const_cast<float*>(logits); a.scale = upstream;
   a.scale_const = mean ? (N > 0 ? 1.0f / (float)N : 0.f) : 1.f;
   a.dx = dx; a.part_w = part_w; a.part_b = part_b; a.N = N; a.C = (int)C;
-  switch (H) {
-    case 16: MGCN_LAUNCH(k_head_ce_bwd<4>, P, kHeadThreads, 0, stream, a); break;
-    case 32: MGCN_LAUNCH(k_head_ce_bwd<8>, P, kHeadThreads, 0, stream, a); break;
-    case 64: MGCN_LAUNCH(k_head_ce_bwd<16>, P, kHeadThreads, 0, stream, a); break;
-    default: MGCN_LAUNCH(k_head_ce_bwd<32>, P, kHeadThreads, 0, stream, a); break;
+  if (C <= 2) {
+    switch (H) {
+      case 16: MGCN_LAUNCH((k_head_ce_bwd<4, 2>), P, kHeadThreads, 0, stream, a); break;
+      case 32: MGCN_LAUNCH((k_head_ce_bwd<8, 2>), P, kHeadThreads, 0, stream, a); break;
+      case 64: MGCN_LAUNCH((k_head_ce_bwd<16, 2>), P, kHeadThreads, 0, stream, a); break;
+      default: MGCN_LAUNCH((k_head_ce_bwd<32, 2>), P, kHeadThreads, 0, stream, a); break;
+    }
+  } else {
+    switch (H) {
+      case 16: MGCN_LAUNCH((k_head_ce_bwd<4, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+      case 32: MGCN_LAUNCH((k_head_ce_bwd<8, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+      case 64: MGCN_LAUNCH((k_head_ce_bwd<16, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+      default: MGCN_LAUNCH((k_head_ce_bwd<32, kHeadMaxC>), P, kHeadThreads, 0, stream, a); break;
+    }
   }
   int rc = launch_reduce_partials(part_w, P, (int)(C * H), (int)H, dw, H, 1, stream);
   if (rc == MGCN_OK) rc = launch_reduce_partials(part_b, P, (int)C, (int)C, db, 0, 1, stream);

@@ -9,6 +9,8 @@ masks of the backward are folded into operand loads; no autograd graph, no [N,H]
 beyond the saved layer outputs.  Per layer: forward = transform, aggregation, residual transform
 (3 launches); backward = weight-gradient x2, transform x2, mask/scale, transposed aggregation.
 """
+import os
+
 import torch
 
 from . import ops
@@ -24,7 +26,7 @@ FORWARD_AGGREGATE_FIRST = True
 # (csrc/gcn_bwd_fused.cu: no dxw array, 0.9 GB less DRAM traffic per layer) instead of two.  Same parity tests,
 # identical from run to run — but measured SLOWER at the botnet batch (1.45 ms against 0.48 + 0.61 ms: the per-row
 # operand-image work needs more warps than fit next to a 16-warp gather), so it is off by default
-BWD_FUSED = False
+BWD_FUSED = os.environ.get("MGCN_BWD_FUSED", "0") == "1"
 
 
 class _ResidualGCNStack(torch.autograd.Function):

@@ -201,6 +201,18 @@ class GCNModel(nn.Module):
         if self.pred_on == "graph":
             assert "batch_slices_x" in kwargs
             sl = kwargs["batch_slices_x"]
-            offsets = torch.as_tensor(list(sl), dtype=torch.int32).to(x.device)
+            if torch.is_tensor(sl) and sl.is_cuda:
+                offsets = sl.to(torch.int32)           # device offsets: no host traffic, capture-safe
+            else:
+                # the boundaries of a batch as a device vector, uploaded once per distinct batch (a pageable copy per
+                # forward would synchronise the step and cannot be captured in a CUDA graph)
+                key = (tuple(int(v) for v in sl), x.device)
+                cache = self.__dict__.setdefault("_offsets_cache", {})
+                offsets = cache.get(key)
+                if offsets is None:
+                    if len(cache) >= 8:
+                        cache.pop(next(iter(cache)))
+                    offsets = torch.as_tensor(key[0], dtype=torch.int32).to(x.device)
+                    cache[key] = offsets
             x = F_mgcn.segment_pool(x, offsets, "mean")
         return x

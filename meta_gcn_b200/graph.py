@@ -121,6 +121,13 @@ class GraphStructure:
             return self.fwd_plain
         return self.bwd
 
+    def has_self_loops(self):
+        """True iff edge_index holds an (i, i) entry — one device reduction and one host read per edge_index, cached"""
+        if "loops" not in self._deg:
+            ei = self.edge_index
+            self._deg["loops"] = bool((ei[0] == ei[1]).any().item()) if self.num_edges else False
+        return self._deg["loops"]
+
     def out_degree(self):
         """float degree over edge_index[0] (after loop handling): gcn_base_models.py:126"""
         if "out" not in self._deg:

@@ -37,7 +37,7 @@ bits = torch.randint(-2 ** 31, 2 ** 31 - 1, (n,), device=dev, dtype=torch.int64)
 
 
 def timeit(name, fn, byts):
-    if args.only and args.only not in name:
+    if args.only and not any(o in name for o in args.only.split("|")):
         return
     for _ in range(2):
         fn()
@@ -77,3 +77,17 @@ if hasattr(ops, "gcn_layer_bwd_fused_impl"):
            lambda: ops.gcn_layer_bwd_fused_impl(gs.bwd, m, gy, x, w, r, bits, dis, row_scale=dis, x_scale=dis), b_agg(n, e, H) + nh)
 timeit("mask_bits_scale", lambda: ops.mask_bits_scale_impl(gy, bits, dis), 2 * nh + 8 * n)
 timeit("torch copy", lambda: m.copy_(x), 2 * nh)
+# the step's first and last stages (H_in = 1 first layer, output layer + loss)
+hw = torch.randn(2, H, device=dev) / H ** 0.5
+hb = torch.zeros(2, device=dev)
+tgt = torch.randint(0, 2, (n,), device=dev)
+timeit("head fwd (Linear 32->2 + CE)", lambda: ops.head_cross_entropy_fwd_impl(x, hw, hb, tgt, False), nh + 16 * n)
+logits_ = ops.head_cross_entropy_fwd_impl(x, hw, hb, tgt, False)[0]
+one = torch.ones(1, device=dev)
+timeit("head bwd", lambda: ops.head_cross_entropy_bwd_impl(x, logits_, hw, tgt, False, one), 2 * nh + 16 * n)
+s1 = torch.randn(n, 1, device=dev)
+w0 = torch.randn(1, H, device=dev)
+r0 = torch.randn(H, 1, device=dev)
+timeit("first layer fwd (narrow input)", lambda: ops.gcn_first_layer_fwd_impl(s1, x1, w0, r0, rb, None, None, dis, 1, out_scale=dis),
+       nh + 20 * n)
+timeit("wgrad narrow (x0^T gy)", lambda: ops.linear_wgrad_impl(x1, gy, True, True), nh + 4 * n)

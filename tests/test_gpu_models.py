@@ -406,3 +406,35 @@ def test_from_data_list_collates_on_the_device():
     for name in ("x", "edge_index", "y", "batch"):
         assert torch.equal(getattr(devb, name).cpu(), getattr(host, name)), name
     assert devb.slices_x == host.slices_x and devb.num_graphs == 7
+
+
+def test_gcnconv_improved_and_weighted_without_and_with_existing_loops():
+    """PyG-1.3 GCNConv.norm with improved=True / edge_weight (appended loops of weight 2 / 1): against a dense fp64
+    restatement on a loop-free graph; an edge_index that already holds self loops is refused (PyG would carry their
+    weights over, this structure appends `fill` — ADVICE r1)"""
+    from meta_gcn_b200.compat.torch_geometric.nn import GCNConv
+    g = torch.Generator().manual_seed(5)
+    n, e = 60, 400
+    row = torch.randint(0, n, (e,), generator=g)
+    col = torch.randint(0, n, (e,), generator=g)
+    keep = row != col
+    ei = torch.stack([row[keep], col[keep]])
+    ew = torch.rand(ei.size(1), generator=g) + 0.5
+    x = torch.randn(n, 6, generator=g)
+    for improved, weight in ((True, None), (False, ew), (True, ew)):
+        torch.manual_seed(1)
+        conv = GCNConv(6, 8, improved=improved).to(DEV)
+        out = conv(x.to(DEV), ei.to(DEV), None if weight is None else weight.to(DEV))
+        fill = 2.0 if improved else 1.0
+        w_e = torch.cat([torch.ones(ei.size(1)) if weight is None else weight, torch.full((n,), fill)]).double()
+        r = torch.cat([ei[0], torch.arange(n)])
+        c = torch.cat([ei[1], torch.arange(n)])
+        deg = torch.zeros(n, dtype=torch.float64).index_add_(0, r, w_e)
+        norm = deg[r].pow(-0.5) * w_e * deg[c].pow(-0.5)
+        xw = x.double() @ conv.weight.detach().cpu().double()
+        ref = torch.zeros(n, 8, dtype=torch.float64).index_add_(0, c, norm.view(-1, 1) * xw[r]) + conv.bias.detach().cpu().double()
+        assert_parity(out, ref, f"GCNConv improved={improved} weighted={weight is not None}")
+    with_loop = torch.cat([ei, torch.tensor([[3], [3]])], dim=1)
+    with pytest.raises(NotImplementedError):
+        GCNConv(6, 8, improved=True).to(DEV)(x.to(DEV), with_loop.to(DEV))
+    GCNConv(6, 8).to(DEV)(x.to(DEV), with_loop.to(DEV))      # the unweighted default (kernel/gcn.py) is unaffected
