@@ -51,29 +51,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
-// MGCN_MBAR_HINT (ns): suspend-time hint of try_wait; MGCN_MBAR_SLEEP (ns): pause after a failed attempt.  Experiment
-// switches (profiles/r2_bwd_fused.md): a third of the instructions k_layer_bwd_tc executes are these polls.
-#ifndef MGCN_MBAR_HINT
-#define MGCN_MBAR_HINT 0
-#endif
-#ifndef MGCN_MBAR_SLEEP
-#define MGCN_MBAR_SLEEP 0
-#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   uint32_t ok;
-  for (;;) {
-#if MGCN_MBAR_HINT
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)MGCN_MBAR_HINT) : "memory");
-#else
+  do {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-#endif
-    if (ok) break;
-#if MGCN_MBAR_SLEEP
-    __nanosleep(MGCN_MBAR_SLEEP);
-#endif
-  }
+  } while (!ok);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
