@@ -252,11 +252,13 @@ __global__ void __launch_bounds__(kTmThreads, 1) k_gcn_fwd_tm(const FwdTmArgs a)
       Row8 accA, accB;
 #pragma unroll
       for (int q = 0; q < 8; ++q) accA.v[q] = accB.v[q] = 0.f;
+      // partial-sum slots of the two passes' tasks: read with the FULL mask before the groups diverge (the source lanes
+      // grp / 8 + grp belong to other groups, which may not take the branches below)
+      const int slotA = __shfl_sync(0xffffffffu, dc.w, grp), slotB = __shfl_sync(0xffffffffu, dc.w, 8 + grp);
       if (kMode == 0) {
         // a hub segment stores its partial sum at once and leaves its row of the block empty (row id -1)
         if (rowA >= 0) {
           accA = gather_sum<MGCN_TM_L1 != 0>(a.z, a.nbr_w, pa.beg, pa.end, pa.gi, pa.gin, sub, grp_lane0, gmask, col, pol);
-          const int slotA = __shfl_sync(gmask, dc.w, grp);
           if (slotA != 0) {
             store_partial(a.partial, slotA, col, accA);
             rowA = -1;
@@ -264,7 +266,6 @@ __global__ void __launch_bounds__(kTmThreads, 1) k_gcn_fwd_tm(const FwdTmArgs a)
         }
         if (rowB >= 0) {
           accB = gather_sum<MGCN_TM_L1 != 0>(a.z, a.nbr_w, pb.beg, pb.end, pb.gi, pb.gin, sub, grp_lane0, gmask, col, pol);
-          const int slotB = __shfl_sync(gmask, dc.w, 8 + grp);
           if (slotB != 0) {
             store_partial(a.partial, slotB, col, accB);
             rowB = -1;
