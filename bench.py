@@ -398,7 +398,7 @@ def run_ours(args):
                     out.append(float(step(b).item()))      # D2H read of the step's result
                 return out
 
-            e2e_loop(1)
+            e2e_loop(max(3, args.warmup))      # both loader slots, their structures and the allocator in steady state
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
