@@ -230,6 +230,8 @@ def run_ours(args):
         raise RuntimeError("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # several ranks on one host: each keeps its pinned batch buffers on its GPU's NUMA node (first touch after binding)
+    numa_node = mdist.bind_to_gpu_numa_node(local) if world > 1 else None
     mdist.init_from_env("nccl")
     # the whole run, eager warm-up included, on one non-default stream: autograd's AccumulateGrad nodes remember the
     # stream they were created on, and the CUDA-graph capture of the step must not touch the legacy default stream
@@ -487,6 +489,7 @@ def run_ours(args):
                        "graphs_per_s": args.graphs * world / (e2e_ms / 1e3), "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": 4,
                        "index_dtype": "int32 on the host (converted once at dataset load)",
+                       "numa_node_of_rank0": numa_node,
                        "int64_indices": {"value": edges_global * LAYERS * 2 / (e2e64_ms / 1e3) / 1e9,
                                          "graphs_per_s": args.graphs * world / (e2e64_ms / 1e3),
                                          "ms_per_step": e2e64_ms, "h2d_bytes_per_step": int(e2e64_h2d),

@@ -87,3 +87,40 @@ def init_from_env(backend=None):
         else:
             dist.init_process_group(backend)
     return rank, local, world
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off (Linux sysfs), so that the pinned host
+    buffers it allocates afterwards (first touch) and its loader thread sit next to the GPU's PCIe root.  With 8 ranks
+    copying a batch per step each, buffers that all live on one socket share that socket's memory controllers and the
+    inter-socket link.  Returns the node id, or None when the topology cannot be read (single node, no sysfs, not
+    Linux) — then nothing is changed."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        if bus is None:
+            return None
+        bdf = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
