@@ -662,7 +662,13 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// out[0..3]: the multiset fingerprints (k_edge_fingerprint); out[4] entries e with (src,dst)[e] > (src,dst)[e+1]
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+// out[0..3]: the multiset fingerprints (as k_edge_fingerprint; accumulated here in the same pass over the list — one
+// read of edge_index instead of two); out[4] entries e with (src,dst)[e] > (src,dst)[e+1]
 // over the whole list, out[5] the same over the first E-N entries, out[6] entries of the last N that are not the
 // loop (e-(E-N), e-(E-N)), out[7] adjacent equal entries (whole list).
 template <typename IndexT>
@@ -670,10 +676,18 @@ __global__ void __launch_bounds__(256) k_edge_order_check(const IndexT* __restri
                                                           const int32_t* __restrict__ node_off,
                                                           const int32_t* __restrict__ edge_off,
                                                           unsigned long long* __restrict__ out) {
-  unsigned long long f[4] = {0ull, 0ull, 0ull, 0ull};
+  unsigned long long f[4] = {0ull, 0ull, 0ull, 0ull}, h[4] = {0ull, 0ull, 0ull, 0ull};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
+    {
+      const uint64_t a = (uint64_t)s, b = (uint64_t)d;
+      const uint64_t ab = a * 0x9e3779b97f4a7c15ull + b, ba = b * 0x9e3779b97f4a7c15ull + a;
+      h[0] += mix64(ab);
+      h[1] += mix64(ba);
+      h[2] += mix64(ab ^ 0xd6e8feb86659fd93ull);
+      h[3] += mix64(ba ^ 0xd6e8feb86659fd93ull);
+    }
     int64_t n0 = 0, e0 = 0, ng = N, eg = E;
     if (G > 0) {
       const int g = segment_of(edge_off, G, e);
@@ -698,20 +712,20 @@ __global__ void __launch_bounds__(256) k_edge_order_check(const IndexT* __restri
     if (Ep < 0) f[2] += 1u;
     else if (e >= Ep) f[2] += (s == n0 + e - Ep && d == n0 + e - Ep) ? 0u : 1u;
   }
-  __shared__ unsigned long long red[8][4];
+  __shared__ unsigned long long red[8][8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    unsigned long long v = f[q];
+  for (int q = 0; q < 8; ++q) {
+    unsigned long long v = q < 4 ? h[q] : f[q - 4];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < 8) {
     unsigned long long v = 0ull;
 #pragma unroll
     for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-    if (v) atomicAdd(out + 4 + threadIdx.x, v);
+    if (v) atomicAdd(out + threadIdx.x, v);   // integer sums: exact in any order
   }
 }
 
@@ -895,11 +909,6 @@ namespace mgcn {
 // of (src, dst) resp. (dst, src).  Equal fingerprints <=> the directed edge multiset is symmetric (up to a
 // 2^-128 collision chance), in which case the structure by source lists, row by row, the same neighbour
 // multisets as the structure by target and need not be built.  Integer sums: independent of scheduling.
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-  return z ^ (z >> 31);
-}
 template <typename IndexT>
 __global__ void __launch_bounds__(256) k_edge_fingerprint(const IndexT* __restrict__ ei, int64_t E,
                                                           unsigned long long* __restrict__ out) {
@@ -959,9 +968,10 @@ static int edge_layout_any(const IndexT* edge_index, int64_t E, int64_t N, int64
   MGCN_REQUIRE(out8 != nullptr, MGCN_ERR_NULL);
   MGCN_REQUIRE(N >= 0 && G >= 0 && G < (1 << 24), MGCN_ERR_RANGE);
   MGCN_REQUIRE(G == 0 || (node_off && edge_off), MGCN_ERR_NULL);
-  MGCN_CHECK_CUDA(cudaMemsetAsync(out8 + 4, 0, 4 * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
-  const int rc = edge_fingerprint_any<IndexT>(edge_index, E, out8, stream);
-  if (rc != MGCN_OK || E == 0) return rc;
+  MGCN_REQUIRE(E >= 0 && E < (int64_t(1) << 31), MGCN_ERR_RANGE);
+  MGCN_CHECK_CUDA(cudaMemsetAsync(out8, 0, 8 * sizeof(uint64_t), static_cast<cudaStream_t>(stream)));
+  if (E == 0) return MGCN_OK;
+  MGCN_REQUIRE(edge_index != nullptr, MGCN_ERR_NULL);
   int64_t blocks = ceil_div(E, 256 * 8);
   if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
   MGCN_LAUNCH(k_edge_order_check<IndexT>, (unsigned)blocks, 256, 0, stream, edge_index, E, N, (int)G, node_off,
