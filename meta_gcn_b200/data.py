@@ -70,12 +70,13 @@ class GraphBatch:
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())
 
-    def structure(self, loop_mode=0):
+    def structure(self, loop_mode=0, recycle=False):
         """the row structures of this batch's edge_index (meta_gcn_b200.graph.GraphStructure), registered in the
         structure cache together with the batch boundaries, so that the model classes — which only see edge_index —
         find it: an ordered batch (every graph in the reference's preprocessed layout) then needs no sort"""
         from .graph import structure_of
-        return structure_of(self.edge_index, self.num_nodes, loop_mode, segments=(self.slices_x, self.slices_e))
+        return structure_of(self.edge_index, self.num_nodes, loop_mode, segments=(self.slices_x, self.slices_e),
+                            recycle=recycle)
 
     def with_int32_indices(self):
         """edge_index as int32 (N, E < 2^31): half the bytes of the host -> device copy, which is what bounds a
@@ -164,7 +165,10 @@ class DeviceLoader:
             ev = torch.cuda.Event()
             ev.record(self.stream)
         b = GraphBatch(out["x"], out["edge_index"], out.get("y"), out.get("batch"), host.slices_x, host.slices_e)
-        b.structure()       # the (lazy) structure object carries the batch boundaries; nothing is launched here
+        # the (lazy) structure object carries the batch boundaries; nothing is launched here.  It takes over the
+        # buffers of the structure this slot's previous batch had (same shapes): no allocation in the steady state,
+        # and the same addresses, which is what lets a CUDA graph captured for the slot be replayed
+        b.structure(recycle=True)
         return b, ev
 
     def bytes_per_batch(self, host):

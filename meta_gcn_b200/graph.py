@@ -28,7 +28,7 @@ class GraphStructure:
     """Lazily built forward (by target) and backward (by source) structures of an edge_index."""
 
     def __init__(self, edge_index, num_nodes, loop_mode=LOOPS_KEEP,
-                 hub_threshold=ops.DEFAULT_HUB_THRESHOLD, segments=None):
+                 hub_threshold=ops.DEFAULT_HUB_THRESHOLD, segments=None, recycle=None):
         if not edge_index.is_cuda:
             raise RuntimeError("GraphStructure needs a CUDA edge_index (no CPU fallback)")
         self.edge_index = edge_index
@@ -45,6 +45,8 @@ class GraphStructure:
         self._segments_host = segments if segments is not None and len(segments[0]) > 2 else None
         self._segments = None
         self._deg = {}
+        # buffers of a dead structure of the same shape ({by: Csr}), overwritten instead of allocating (loader slots)
+        self._recycle = recycle or {}
 
     @property
     def facts(self):
@@ -71,7 +73,12 @@ class GraphStructure:
             if f["layout"] and (by == 0 or (f["symmetric"] and self.segments is None)):
                 layout = f["layout"]
         return ops.csr_build_impl(self.edge_index, self.num_nodes, by, self.loop_mode,
-                                  self.hub_threshold, layout, self.segments if layout else None)
+                                  self.hub_threshold, layout, self.segments if layout else None,
+                                  reuse=self._recycle.pop(by, None))
+
+    def built(self):
+        """the structures built so far (Csr objects)"""
+        return [c for c in (self._fwd, self._bwd) if c is not None]
 
     @property
     def fwd(self):
@@ -174,7 +181,11 @@ class _StructureCache:
         self.capacity = capacity
         self._items = OrderedDict()
 
-    def get(self, edge_index, num_nodes, loop_mode, hub_threshold=ops.DEFAULT_HUB_THRESHOLD, segments=None):
+    def get(self, edge_index, num_nodes, loop_mode, hub_threshold=ops.DEFAULT_HUB_THRESHOLD, segments=None,
+            recycle=False):
+        """recycle: when this storage was rewritten in place (a loader slot), the new structure overwrites the buffers
+        of the old one instead of allocating — the caller guarantees that nothing enqueued LATER still needs the old
+        structure (DeviceLoader: a slot is refilled only after its batch's step)."""
         version = _version_of(edge_index)
         if version is None:
             return GraphStructure(edge_index, num_nodes, loop_mode, hub_threshold, segments)
@@ -184,9 +195,15 @@ class _StructureCache:
         if hit is not None:
             self._items.move_to_end(key)
             return hit
+        dead = {}
         for stale in [k for k in self._items if k[0] == ident and (k[1] != key[1] or k[2] != version)]:
-            del self._items[stale]          # the storage was rewritten: its old structures are dead
-        gs = GraphStructure(edge_index, num_nodes, loop_mode, hub_threshold, segments)
+            old = self._items.pop(stale)    # the storage was rewritten: its old structures are dead
+            if recycle and stale[1] == key[1] and stale[3:] == key[3:]:
+                if old._fwd is not None:
+                    dead[1] = old._fwd
+                if old._bwd is not None:
+                    dead[0] = old._bwd
+        gs = GraphStructure(edge_index, num_nodes, loop_mode, hub_threshold, segments, recycle=dead)
         self._items[key] = gs  # holds edge_index alive, so the data_ptr cannot be recycled
         while len(self._items) > self.capacity:
             self._items.popitem(last=False)
@@ -200,11 +217,11 @@ _CACHE = _StructureCache()
 
 
 def structure_of(edge_index, num_nodes, loop_mode=LOOPS_KEEP,
-                 hub_threshold=ops.DEFAULT_HUB_THRESHOLD, segments=None):
+                 hub_threshold=ops.DEFAULT_HUB_THRESHOLD, segments=None, recycle=False):
     """the (cached) GraphStructure of an edge_index.  segments = (cumulative node counts, cumulative edge counts) of
     the graphs of a batch, when known (GraphBatch.structure / DeviceLoader pass them): only consulted when the
     structure object is created"""
-    return _CACHE.get(edge_index, num_nodes, loop_mode, hub_threshold, segments)
+    return _CACHE.get(edge_index, num_nodes, loop_mode, hub_threshold, segments, recycle)
 
 
 _INDEX_CACHE = OrderedDict()

@@ -45,3 +45,45 @@ class GraphedCall:
     def __call__(self):
         self.graph.replay()
         return self.out
+
+
+class GraphedSlots:
+    """One captured graph per distinct set of input ADDRESSES — for batches that arrive in the preallocated slots of a
+    `DeviceLoader` (meta_gcn_b200/data.py): a slot's tensors and (with recycled structure buffers) its row structures
+    keep their addresses from batch to batch, so the graph captured for the slot the first time it is seen can be
+    replayed for every later batch of the same shapes that lands in it.
+
+        graphs = GraphedSlots(fwd_loss_bwd)               # fwd_loss_bwd(batch) -> loss tensor
+        for batch in DeviceLoader(host_batches, "cuda"):
+            gs = batch.structure(recycle=True); gs.fwd_plain; gs.bwd_plain     # built eagerly (one host read)
+            loss = graphs(batch, extra_key=(...))        # capture on first sight of these addresses, replay after
+
+    The key is made of the data pointers and shapes of the batch fields and of every built structure buffer; anything
+    else the step depends on and that may change between batches (a branch taken on the data, say) goes into
+    `extra_key`.  A key that was never seen costs an eager warm-up, a capture and a replay."""
+
+    def __init__(self, fn, warmup=1, capacity=4):
+        self.fn = fn
+        self.warmup = warmup
+        self.capacity = capacity
+        self.graphs = {}
+
+    @staticmethod
+    def key_of(batch):
+        parts = []
+        for t in (batch.x, batch.edge_index, batch.y):
+            if t is not None:
+                parts.append((t.data_ptr(), tuple(t.shape), t.dtype))
+        for csr in batch.structure().built():
+            parts.append(tuple(t.data_ptr() for t in csr.tensors()))
+        return tuple(parts)
+
+    def __call__(self, batch, extra_key=()):
+        key = (self.key_of(batch), extra_key)
+        g = self.graphs.get(key)
+        if g is None:
+            while len(self.graphs) >= self.capacity:
+                self.graphs.pop(next(iter(self.graphs)))
+            g = GraphedCall(lambda: self.fn(batch), warmup=self.warmup)
+            self.graphs[key] = g
+        return g()

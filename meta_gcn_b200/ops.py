@@ -88,9 +88,12 @@ def _as_csr(csr, hub_threshold=None):
 # ------------------------------------------------------------------------------------------------
 # implementations (plain functions; also what meta_gcn_b200.functional calls directly)
 # ------------------------------------------------------------------------------------------------
-def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRESHOLD, layout=0, segments=None):
+def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRESHOLD, layout=0, segments=None,
+                   reuse=None):
     """layout != 0 (from edge_layout_impl; loop_mode 0 only): the list is already in (src,dst) order — no sort.
-    segments = (node_off, edge_off) int32 device tensors [G+1] for a batch of graphs (by = 0 only)."""
+    segments = (node_off, edge_off) int32 device tensors [G+1] for a batch of graphs (by = 0 only).
+    reuse: a Csr whose buffers may be overwritten (same sizes, device and hub threshold, else ignored): the new
+    structure then lives at the same addresses and nothing is allocated for it."""
     _need_cuda(edge_index)
     if edge_index.dtype not in (torch.int64, torch.int32) or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise TypeError("edge_index must be int64 (the reference's dtype) or int32, shape [2,E]")
@@ -116,8 +119,14 @@ def csr_build_impl(edge_index, N, by, loop_mode, hub_threshold=DEFAULT_HUB_THRES
     sizes = dict(rowptr=N + 1, nbr=nnz_cap, perm=nnz_cap, order=N, hub_rows=hub_cap, hub_seg0=hub_cap,
                  hub_count=1, seg_row=seg_cap, seg_beg=seg_cap, seg_count=1, tasks=4 * (N + seg_cap),
                  nbr_w=nnz_cap)
-    csr = Csr([torch.empty(sizes[n], **i32) for n in CSR_FIELDS], hub_threshold,
-              torch.empty(1, **i32))
+    csr = None
+    if reuse is not None and reuse.hub_threshold == int(hub_threshold) and reuse.bad is not None:
+        old = reuse.tensors()
+        if all(t is not None and t.device == dev and t.numel() == sizes[n] for n, t in zip(CSR_FIELDS, old)):
+            csr = Csr(old, hub_threshold, reuse.bad)
+    if csr is None:
+        csr = Csr([torch.empty(sizes[n], **i32) for n in CSR_FIELDS], hub_threshold,
+                  torch.empty(1, **i32))
     nbytes = ctypes.c_size_t(0)
     st = csr.struct()
     _lib.check(build(_ptr(ei), E, N, int(by), *mode_arg, ctypes.byref(st),

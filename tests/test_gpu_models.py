@@ -393,6 +393,68 @@ def test_graphed_call_replays_the_eager_step_bit_exactly():
         assert torch.equal(p.grad, gg)
 
 
+def test_graphed_slots_replay_per_loader_slot_with_recycled_structures():
+    """meta_gcn_b200.graphed.GraphedSlots over DeviceLoader batches: the structures of a refilled slot are rebuilt into
+    the buffers of the slot's previous batch (same addresses, no allocation), and the graph captured for a slot gives,
+    for every later batch of the same shapes in it, the loss and gradients of the eager step bit for bit — although the
+    graphs differ (a relabelled copy: same N and E, other rows)."""
+    from meta_gcn_b200 import functional as F
+    from meta_gcn_b200.data import DeviceLoader, GraphBatch, symmetrise_sorted_with_loops, synth_botnet_graph
+    from meta_gcn_b200.gcn_meta.models import GCNModel
+    from meta_gcn_b200.graph import clear_structure_cache
+    from meta_gcn_b200.graphed import GraphedSlots
+    clear_structure_cache()
+    torch.manual_seed(0)
+    cfg = dict(in_channels=1, enc_sizes=[32] * 3, num_classes=2, non_linear="relu", non_linear_layer_wise="relu",
+               residual_hop=1, dropout=0.0, final_type="proj", pred_on="node", nodemodel="additive", deg_norm="sm",
+               edge_gate=None, aggr="add", bias=False)
+    model = GCNModel(**cfg).to("cuda")
+    params = [p for p in model.parameters()]
+    for p in params:
+        p.grad = torch.zeros_like(p)
+    g0 = synth_botnet_graph(seed=7, num_nodes=5000, edge_entries=40000, evil=300)
+    n = g0["x"].shape[0]
+    hosts = []
+    for k in range(5):
+        rng = np.random.default_rng(100 + k)
+        perm = rng.permutation(n)                             # relabel the nodes: same N and E, another graph
+        ei = g0["edge_index"]
+        keep = ei[0] != ei[1]
+        ei_k = symmetrise_sorted_with_loops(perm[ei[0][keep]], perm[ei[1][keep]], n)
+        assert ei_k.shape == ei.shape
+        deg = np.bincount(ei_k[0], minlength=n).astype(np.float32)
+        x = np.stack([np.ones(n, dtype=np.float32), deg], axis=1)
+        y = rng.integers(0, 2, n).astype(np.uint8)
+        hosts.append(GraphBatch.from_data_list([{"x": x, "edge_index": ei_k, "y": y}]).pin_memory())
+
+    def fwd_loss_bwd(b):
+        for p in params:
+            p.grad.zero_()
+        loss = F.cross_entropy(model(b.x[:, 0].view(-1, 1), b.edge_index, deg_K=b.x[:, 1]), b.y.long(), "sum")
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        slots = GraphedSlots(fwd_loss_bwd, warmup=1)
+        addrs = {}
+        for k, b in enumerate(DeviceLoader(hosts, "cuda", fields=("x", "edge_index", "y"))):
+            gs = b.structure(recycle=True)
+            gs.fwd_plain, gs.bwd_plain
+            slot_id = b.x.data_ptr()
+            ptrs = tuple(t.data_ptr() for c in gs.built() for t in c.tensors())
+            assert addrs.setdefault(slot_id, ptrs) == ptrs, "a refilled slot's structure moved"
+            loss_g = float(slots(b))
+            grads_g = [p.grad.clone() for p in params]
+            loss_e = float(fwd_loss_bwd(b))
+            assert loss_g == loss_e, (k, loss_g, loss_e)
+            for p, gg in zip(params, grads_g):
+                assert torch.equal(p.grad, gg), k
+        assert len(slots.graphs) == 2 and len(addrs) == 2      # two loader slots, two captures for five batches
+    torch.cuda.current_stream().wait_stream(side)
+    clear_structure_cache()
+
+
 def test_from_data_list_collates_on_the_device():
     """GraphBatch.from_data_list with CUDA inputs (Batch.from_data_list of data/dataloader.py:11): same batch as the
     host collation, built on the device"""
