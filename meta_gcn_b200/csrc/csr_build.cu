@@ -143,24 +143,33 @@ __global__ void __launch_bounds__(256) k_make_keys(const IndexT* __restrict__ ei
                                                    int32_t* __restrict__ counts,
                                                    int32_t* __restrict__ bad_index) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    uint32_t key;
-    if (e < E) {
-      const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
-      const bool ok = s >= 0 && s < N && d >= 0 && d < N;
-      if (!ok) {
-        *bad_index = 1;
-        key = (uint32_t)N;
-      } else if (loop_mode != 0 && s == d) {
-        key = (uint32_t)N;  // dropped
+  const int lane = threadIdx.x & 31;
+  // warp-uniform loop bound: every lane reaches the match below in every iteration
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total; base += stride) {
+    const int64_t e = base + lane;
+    const bool in = e < total;
+    uint32_t key = 0xffffffffu;
+    if (in) {
+      if (e < E) {
+        const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
+        const bool ok = s >= 0 && s < N && d >= 0 && d < N;
+        if (!ok) {
+          *bad_index = 1;
+          key = (uint32_t)N;
+        } else if (loop_mode != 0 && s == d) {
+          key = (uint32_t)N;  // dropped
+        } else {
+          key = (uint32_t)(by == 0 ? s : d);
+        }
       } else {
-        key = (uint32_t)(by == 0 ? s : d);
+        key = (uint32_t)(e - E);  // appended self loop of node e-E (loop_mode 2)
       }
-    } else {
-      key = (uint32_t)(e - E);  // appended self loop of node e-E (loop_mode 2)
+      if (keys != nullptr) keys[e] = key;   // a sort-free build needs no keys
     }
-    keys[e] = key;
-    if (key < (uint32_t)N) atomicAdd(&counts[key], 1);
+    // row histogram: the lanes of a warp that hold the same key add once (an ordered list has ~10 equal keys in a
+    // row: a tenth of the atomics; integer sums, so the grouping does not change the result)
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (in && key < (uint32_t)N && lane == __ffs(peers) - 1) atomicAdd(&counts[key], __popc(peers));
   }
 }
 
@@ -828,7 +837,7 @@ static int csr_build_any(const IndexT* edge_index, int64_t E, int64_t N, int by,
     // (a presorted list is counted by source: its prefix is indexed through these row starts; a symmetric list has
     // the same counts by target)
     MGCN_LAUNCH(k_make_keys<IndexT>, grid_for(total, 256), 256, 0, stream, edge_index, E, N, presorted ? 0 : by,
-                loop_mode, total, keys_a, rowptr, bad_index);
+                loop_mode, total, presorted ? nullptr : keys_a, rowptr, bad_index);   // a sort-free build needs no keys
   }
   int rc = exclusive_scan_i32(rowptr, rowptr, N + 1, tile_sums, stream);
   if (rc != MGCN_OK) return rc;
