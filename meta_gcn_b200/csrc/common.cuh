@@ -101,7 +101,8 @@ int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const
                         const uint32_t* hmask_prev, const float* post, int64_t N, float* gy_prev, float* gs_prev,
                         float* dw, float* d_res_w, float* d_res_b, float* ws, void* stream);
 // dW / dR from per-CTA partials [P][128][32] of the transposed tcgen05 products, fixed order (gcn_layer_tc.cu)
-int launch_bwd_tc_reduce(const float* part, int P, float* dw, float* d_res_w, void* stream);
+int launch_bwd_tc_reduce(const float* part, int P, float* dw, float* d_res_w, const float* part_b, int Pb,
+                         float* d_res_b, void* stream);
 // narrow-side dense transforms (dense_narrow.cu)
 bool narrow_linear_applies(int64_t Hi, int64_t Ho, const float* x, const float* xmask, const float* add,
                            const float* y);

@@ -39,7 +39,7 @@
 //              consumer, done(t + 4) needs done(t + 2) needs the stores that wait for done(t).
 // Hub rows (longer than the hub threshold): their segments store partial sums in mode 0; a second launch (mode 1) sums
 // the partials per hub row (fixed order) and runs the same tile path.  Per-CTA partials of dW / dR / dr are reduced in a
-// fixed order by k_bwd_tc_reduce / k_reduce_partials.  No atomics on data.
+// fixed order by k_bwd_tc_reduce.  No atomics on data.
 //
 // MEASURED (B200, botnet batch, scripts/prof_layer.py, profiles/r2_bwd_fused.md): 1.45 ms per layer against 0.48 + 0.61 ms
 // for k_agg_flat + k_layer_bwd_tc, with 2.59 GB of DRAM traffic against 3.47 GB.  Correct and deterministic, but not
@@ -687,7 +687,5 @@ extern "C" int mgcn_gcn_layer_bwd_fused(const mgcn_csr_t* gt, const float* gs, c
     a.part_b = part_b + (size_t)P0 * 32;
     MGCN_LAUNCH(k_gcn_bwd_fused<1>, (unsigned)P1, kBfThreads, kBfSmem, stream, a);
   }
-  const int rc = launch_bwd_tc_reduce(part_t, P0 + P1, dw, d_res_w, stream);
-  if (rc != MGCN_OK) return rc;
-  return launch_reduce_partials(part_b, P0 + P1, 32, 32, d_res_b, 0, 1, stream);
+  return launch_bwd_tc_reduce(part_t, P0 + P1, dw, d_res_w, part_b, P0 + P1, d_res_b, stream);
 }

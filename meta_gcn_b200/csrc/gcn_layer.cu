@@ -615,19 +615,77 @@ __global__ void __launch_bounds__(MGCN_AGG_WARPS * 32, MGCN_AGG_MINB) k_agg_flat
   }
 }
 
-__global__ void __launch_bounds__(256) k_agg_flat_hubs(const AggFlatArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int sub = lane & 3, grp = lane >> 2;
-  const int col = sub * 8;
-  const int64_t G = (int64_t)gridDim.x * 64;
+// k_hub_reduce and the finishing pass over the hub rows in one launch: the warp (or, for giant hubs, the CTA) that has summed a hub row's
+// segment partials — same runs, same order, same sums — finishes the row itself instead of storing the sum for a
+// second kernel.  One launch less per aggregation (11 per botnet step).
+__global__ void __launch_bounds__(256) k_agg_flat_hub_finish(const AggFlatArgs a) {
+  __shared__ int giant_k[kGiantList];
+  __shared__ int n_giant;
+  __shared__ __align__(16) float red[64][kH];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3, grp = lane >> 2, col = sub * 8;
+  if (threadIdx.x == 0) n_giant = 0;
+  __syncthreads();
   int64_t nh = *a.hub_count;
   if (nh > a.hub_cap) nh = a.hub_cap;
   const uint64_t pol = policy_evict_first();
-  for (int64_t k = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 8 + grp; k < nh; k += G) {
+  const int64_t W = (int64_t)gridDim.x * 8;
+  for (int64_t k = (int64_t)blockIdx.x * 8 + warp; k < nh; k += W) {
     const int64_t row = __ldg(a.hub_rows + k);
     const int s0 = __ldg(a.hub_seg0 + k);
-    const Row8 tot = sum_partials(a.partial, s0, 1, col);   // reduced by k_hub_reduce
-    agg_finish_row(a, tot, a.post ? __ldg(a.post + row) : 1.f, row, col, pol);
+    const int len = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+    const int ns = (len + a.hub_threshold - 1) / a.hub_threshold;
+    if (ns > kGiantSegs) {   // queue for the CTA-wide pass below (the slot order never reaches the results)
+      int slot = 0;
+      if (lane == 0) slot = atomicAdd(&n_giant, 1);
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+      if (slot < kGiantList) {
+        if (lane == 0) giant_k[slot] = (int)k;
+        continue;
+      }
+    }
+    Row8 tot;
+    if (ns <= 1) {
+      tot = sum_partials(a.partial, s0, 1, col);
+    } else {
+      const int per = (ns + 7) >> 3;
+      const Row8 run = hub_run_sum(a.partial, s0, grp * per, min(ns, grp * per + per), col);
+      tot = run;   // group 0: its own run; then runs 1..7 in order
+#pragma unroll
+      for (int g = 1; g < 8; ++g) {
+        Row8 other;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) other.v[q] = __shfl_sync(0xffffffffu, run.v[q], 4 * g + sub);
+        if (g * per < ns) row8_add(tot, other);
+      }
+    }
+    if (grp == 0) agg_finish_row(a, tot, a.post ? __ldg(a.post + row) : 1.f, row, col, pol);
+  }
+  __syncthreads();
+  // giants: 64 lane groups of the CTA sum 64 contiguous runs concurrently, group 0 adds the 64 run sums in order
+  const int ng = min(n_giant, kGiantList);
+  for (int gi = 0; gi < ng; ++gi) {
+    const int64_t k = giant_k[gi];
+    const int64_t row = __ldg(a.hub_rows + k);
+    const int s0 = __ldg(a.hub_seg0 + k);
+    const int len = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+    const int ns = (len + a.hub_threshold - 1) / a.hub_threshold;
+    const int per = (ns + 63) >> 6, gid = warp * 8 + grp;
+    const Row8 run = hub_run_sum(a.partial, s0, gid * per, min(ns, gid * per + per), col);
+    *reinterpret_cast<float4*>(&red[gid][col]) = make_float4(run.v[0], run.v[1], run.v[2], run.v[3]);
+    *reinterpret_cast<float4*>(&red[gid][col + 4]) = make_float4(run.v[4], run.v[5], run.v[6], run.v[7]);
+    __syncthreads();
+    if (warp == 0 && grp == 0) {
+      Row8 tot = run;
+      for (int g = 1; g < 64 && g * per < ns; ++g) {
+        const float4 lo = *reinterpret_cast<const float4*>(&red[g][col]), hi = *reinterpret_cast<const float4*>(&red[g][col + 4]);
+        Row8 o;
+        o.v[0] = lo.x; o.v[1] = lo.y; o.v[2] = lo.z; o.v[3] = lo.w;
+        o.v[4] = hi.x; o.v[5] = hi.y; o.v[6] = hi.z; o.v[7] = hi.w;
+        row8_add(tot, o);
+      }
+      agg_finish_row(a, tot, a.post ? __ldg(a.post + row) : 1.f, row, col, pol);
+    }
+    __syncthreads();
   }
 }
 
@@ -656,11 +714,9 @@ int launch_agg_flat32(const mgcn_csr_t* g, const float* x, const float* post, in
   if (blocks > (int64_t)kNumSMs * MGCN_AGG_MINB) blocks = (int64_t)kNumSMs * MGCN_AGG_MINB;
   MGCN_LAUNCH(k_agg_flat, (unsigned)blocks, MGCN_AGG_WARPS * 32, 0, stream, a);
   if (hubs) {
-    const int rc = launch_hub_reduce(g, partial, stream);
-    if (rc != MGCN_OK) return rc;
-    int64_t hb = ceil_div(a.hub_cap, 64);
-    if (hb > (int64_t)kNumSMs * 2) hb = (int64_t)kNumSMs * 2;
-    MGCN_LAUNCH(k_agg_flat_hubs, (unsigned)hb, 256, 0, stream, a);
+    int64_t hb = ceil_div(a.hub_cap, 8);
+    if (hb > (int64_t)kNumSMs * 8) hb = (int64_t)kNumSMs * 8;
+    MGCN_LAUNCH(k_agg_flat_hub_finish, (unsigned)hb, 256, 0, stream, a);
   }
   return MGCN_OK;
 }

@@ -455,10 +455,26 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) k_layer_bwd_tc(const BwdTcAr
 }
 
 // dW[j][c] = sum_p part[p][c][j] + part[p][64 + c][j];   dR[c][j] = sum_p part[p][32 + c][j] + part[p][96 + c][j]
+// block 64 (when part_b is given): dr[c] = sum_p part_b[p][c], the same two-level fixed order
 __global__ void __launch_bounds__(256) k_bwd_tc_reduce(const float* __restrict__ part, int P, float* __restrict__ dw,
-                                                       float* __restrict__ d_res_w) {
+                                                       float* __restrict__ d_res_w, const float* __restrict__ part_b,
+                                                       int Pb, float* __restrict__ d_res_b) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 64) {
+    const int per = (Pb + 7) / 8, p0 = warp * per, p1 = min(Pb, p0 + per);
+    float sb = 0.f;
+    for (int p = p0; p < p1; ++p) sb += part_b[(int64_t)p * 32 + lane];
+    red[warp][lane] = sb;
+    __syncthreads();
+    if (warp == 0) {
+      float t = red[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += red[w][lane];
+      d_res_b[lane] = t;
+    }
+    return;
+  }
   const int o = blockIdx.x * 32 + lane;          // 0..2047
   const int which = o >> 10, a0 = (o >> 5) & 31, b0 = o & 31;
   // dW[j = a0][c = b0]: rows c, 64 + c, column j;  dR[c = a0][j = b0]: rows 32 + c, 96 + c, column j
@@ -479,8 +495,9 @@ __global__ void __launch_bounds__(256) k_bwd_tc_reduce(const float* __restrict__
   }
 }
 
-int launch_bwd_tc_reduce(const float* part, int P, float* dw, float* d_res_w, void* stream) {
-  MGCN_LAUNCH(k_bwd_tc_reduce, 64, 256, 0, stream, part, P, dw, d_res_w);
+int launch_bwd_tc_reduce(const float* part, int P, float* dw, float* d_res_w, const float* part_b, int Pb,
+                         float* d_res_b, void* stream) {
+  MGCN_LAUNCH(k_bwd_tc_reduce, part_b ? 65 : 64, 256, 0, stream, part, P, dw, d_res_w, part_b, Pb, d_res_b);
   return MGCN_OK;
 }
 
@@ -509,8 +526,7 @@ int launch_layer_bwd_tc(const float* dxw, const float* gy, const float* x, const
   }
   MGCN_CHECK_CUDA(attr_err);
   MGCN_LAUNCH(k_layer_bwd_tc, P, kBwdTcThreads, kBwdTcSmem, stream, a);
-  MGCN_LAUNCH(k_bwd_tc_reduce, 64, 256, 0, stream, a.part_t, P, dw, d_res_w);
-  return launch_reduce_partials(a.part_b, P, 32, 32, d_res_b, 0, 1, stream);
+  return launch_bwd_tc_reduce(a.part_t, P, dw, d_res_w, a.part_b, P, d_res_b, stream);   // dW, dR and dr: one launch
 }
 
 }  // namespace mgcn

@@ -539,7 +539,5 @@ extern "C" int mgcn_gcn_layer_bwd_tma(const float* dxw, const float* gy, const f
   MGCN_CHECK_CUDA(cudaFuncSetAttribute(mgcn_tma::k_layer_bwd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        mgcn_tma::kTmaSmem));
   MGCN_LAUNCH(mgcn_tma::k_layer_bwd_tma, P, mgcn_tma::kTmaThreads, mgcn_tma::kTmaSmem, stream, a, tm_dk, tm_dm, tm_gk, tm_gm);
-  const int rc = launch_bwd_tc_reduce(a.part_t, P, dw, d_res_w, stream);
-  if (rc != MGCN_OK) return rc;
-  return launch_reduce_partials(a.part_b, P, 32, 32, d_res_b, 0, 1, stream);
+  return launch_bwd_tc_reduce(a.part_t, P, dw, d_res_w, a.part_b, P, d_res_b, stream);
 }
