@@ -139,3 +139,26 @@ def test_shard_helpers():
     assert sorted(sum(parts, [])) == list(range(6))
     loads = [sum([5, 9, 1, 7, 3, 3][i] for i in p) for p in parts]
     assert max(loads) - min(loads) <= 3
+
+
+def test_numa_binding_is_a_noop_without_a_readable_topology():
+    """dist.bind_to_gpu_numa_node: on a host without CUDA / sysfs topology nothing changes and None comes back"""
+    import os
+    from meta_gcn_b200 import dist as mdist
+    before = os.sched_getaffinity(0)
+    assert mdist.bind_to_gpu_numa_node(0) is None or isinstance(mdist.bind_to_gpu_numa_node(0), int)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
+
+
+def test_csr_reuse_argument_is_checked_on_the_host():
+    """ops.csr_build_impl refuses CPU tensors before looking at `reuse` (no CPU fallback), and structure_of accepts the
+    recycle flag"""
+    import inspect
+    import pytest
+    import torch
+    from meta_gcn_b200 import graph, ops
+    assert "reuse" in inspect.signature(ops.csr_build_impl).parameters
+    assert "recycle" in inspect.signature(graph.structure_of).parameters
+    with pytest.raises(RuntimeError):
+        ops.csr_build_impl(torch.zeros(2, 3, dtype=torch.int64), 4, 0, 0, reuse=None)
