@@ -481,6 +481,63 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 4) k_first_layer_fwd(const Lay
   }
 }
 
+// The same layer without a following transform (w_next == NULL: the aggregate-then-transform stack): nothing needs a
+// tile — a lane group of 4 owns a row, 8 columns per lane, the operations and their order are those of
+// k_first_layer_fwd + fwd_tile_tail (identical results), the outputs leave as whole 128-byte rows.  A pure streaming pass.
+__global__ void __launch_bounds__(256) k_first_layer_fwd_stream(const LayerFwdArgs a) {
+  __shared__ float nws[288];   // W_in [k][c] at 0, R^T [k][c] at 128, r at 256
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < a.nhin * kH; i += 256) {
+    const int k = i / kH, c = i % kH;
+    nws[i] = __ldg(a.nw + i);
+    nws[128 + i] = __ldg(a.res_w + c * a.nhin + k);
+  }
+  if (tid < kH) nws[256 + tid] = a.res_b ? __ldg(a.res_b + tid) : 0.f;
+  __syncthreads();
+  const int sub = lane & 3, col = sub * 8;
+  const unsigned gmask = 0xfu << (lane & ~3);
+  const uint64_t pol = policy_evict_first();
+  const int64_t groups = (int64_t)gridDim.x * 64;
+  for (int64_t row = (int64_t)blockIdx.x * 64 + (tid >> 2); row < a.n_rows; row += groups) {
+    Row8 z, rs;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      z.v[q] = 0.f;
+      rs.v[q] = 0.f;
+    }
+    for (int k = 0; k < a.nhin; ++k) {
+      const float sv = __ldg(a.ns + row * a.nhin + k);
+      const float xv = __ldg(a.nx + row * a.nhin + k);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        z.v[q] = fmaf(sv, nws[k * kH + col + q], z.v[q]);
+        rs.v[q] = fmaf(xv, nws[128 + k * kH + col + q], rs.v[q]);
+      }
+    }
+    const float ps = a.npost ? __ldg(a.npost + row) : 1.f;
+    const float os = a.out_scale ? __ldg(a.out_scale + row) : 1.f;
+    uint32_t bits = 0;
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float h = z.v[q] * ps;
+      if (a.bias) h = __fadd_rn(h, __ldg(a.bias + col + q));
+      h = h > 0.f ? h : 0.f;
+      bits |= (h > 0.f ? 1u : 0u) << q;
+      float v = h + (rs.v[q] + nws[256 + col + q]);
+      if (a.act_out == 1) v = v > 0.f ? v : 0.f;
+      o[q] = v * os;
+    }
+    bits <<= col;
+    bits |= __shfl_xor_sync(gmask, bits, 1);
+    bits |= __shfl_xor_sync(gmask, bits, 2);
+    if (sub == 0) a.hmask[row] = bits;
+    float* out = a.x_next + row * kH + col;
+    st_f4_hint(out, make_float4(o[0], o[1], o[2], o[3]), pol);
+    st_f4_hint(out + 4, make_float4(o[4], o[5], o[6], o[7]), pol);
+  }
+}
+
 // hub rows: partial sums of the row's segments added left to right, then the same tile tail
 __global__ void __launch_bounds__(kFwdWarps * 32, 2) k_layer_fwd_hubs(const LayerFwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -1028,6 +1085,12 @@ extern "C" int mgcn_gcn_first_layer_fwd(const float* s, const float* x, int64_t 
   a.x_next = x_next; a.m_next = m_next; a.hmask = hmask;
   a.n_rows = N;
   a.act_out = act_out;
+  if (w_next == nullptr) {   // no following transform: the streaming pass
+    int64_t sb = ceil_div(N, 64);
+    if (sb > (int64_t)kNumSMs * 8) sb = (int64_t)kNumSMs * 8;
+    MGCN_LAUNCH(k_first_layer_fwd_stream, (unsigned)sb, 256, 0, stream, a);
+    return MGCN_OK;
+  }
   const size_t smem = sizeof(float) * kFwdSmemFloats;
   // the attribute belongs to (function, device): set on every call (cheap), so a second GPU in the same process
   // gets it too and a failure is reported every time
