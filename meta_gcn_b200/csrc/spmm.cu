@@ -96,6 +96,34 @@ __device__ __forceinline__ void accumulate_range(const SpmmArgs& a, int beg, int
                                                  bool col_ok, float rs, Vals<VEC4>& acc) {
   constexpr int V = Vals<VEC4>::V;
   constexpr int U = LPR < 8 ? LPR : 8;  // gathers in flight per lane
+  if constexpr (LPR == 1 && MODE != kExact) {
+    // one lane per row (H <= 4): four index loads, then four gathers in flight per lane instead of a chain of
+    // dependent load pairs (the H_in = 1 aggregation of the botnet stack's first layer); same sums, same order
+    int e = beg;
+    for (; e + 4 <= end; e += 4) {
+      int j[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) j[u] = __ldg(a.gather_idx + e + u);
+      Vals<VEC4> xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (col_ok) xv[u] = load_row<VEC4>(a.x + (int64_t)j[u] * a.H + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (col_ok) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc.v[i] = __fadd_rn(acc.v[i], xv[u].v[i]);
+        }
+    }
+    for (; e < end; ++e) {
+      const int j = __ldg(a.gather_idx + e);
+      if (col_ok) {
+        const Vals<VEC4> xv = load_row<VEC4>(a.x + (int64_t)j * a.H + col);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] = __fadd_rn(acc.v[i], xv.v[i]);
+      }
+    }
+  } else {
   for (int e = beg; e < end; e += LPR) {
     // cooperative, coalesced fetch of up to LPR entries: lane `sub` takes entry e+sub
     const int k = e + sub;
@@ -147,6 +175,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmArgs& a, int beg, int
         }
       }
     }
+  }
   }
 }
 

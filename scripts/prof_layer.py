@@ -65,6 +65,7 @@ timeit("layer_fwd last (no next)", lambda: ops.gcn_layer_fwd_impl(gs.fwd, m, x, 
        4 * e + 8 * n + 3 * nh)
 x1 = torch.ones(n, 1, device=dev)
 timeit("first layer: spmm H=1 (pre-scaled)", lambda: ops.spmm_impl(gs.fwd, x1, nbr_scale=dis), 4 * e + 16 * n)
+timeit("first layer: spmm H=1 (plain, as the stack calls it)", lambda: ops.spmm_impl(gs.fwd, x1), 4 * e + 16 * n)
 timeit("first layer: row-local fwd", lambda: ops.gcn_layer_fwd_impl(None, m, None, x, None, None, w, None, dis, None, 1), 4 * nh)
 timeit("agg_plain bwd structure", lambda: ops.aggregate_prescaled_impl(gs.bwd, gy, dis, 0, None, None, 0),
        b_agg(n, e, H))
