@@ -651,6 +651,12 @@ __device__ __forceinline__ int segment_of(const int32_t* __restrict__ off, int G
   }
   return lo;
 }
+// the same with the previous answer as a hint: a thread's entries advance monotonically and a graph of a batch spans
+// millions of them, so two cached loads usually replace the dependent chain of the search
+__device__ __forceinline__ int segment_of_hint(const int32_t* __restrict__ off, int G, int64_t v, int hint) {
+  if (hint >= 0 && hint < G && (int64_t)off[hint] <= v && v < (int64_t)off[hint + 1]) return hint;
+  return segment_of(off, G, v);
+}
 
 // A BATCH of such lists (Batch.from_data_list: graph after graph, node ids shifted; dataloader.py:11) is the same
 // layout per graph: node_off / edge_off [G+1] delimit the graphs (G = 0: the whole list is one graph).
@@ -659,11 +665,12 @@ __global__ void __launch_bounds__(256)
     k_fill_presorted(const IndexT* __restrict__ ei, int64_t E, int64_t N, int by, int tail, int dups, int G,
                      const int32_t* __restrict__ node_off, const int32_t* __restrict__ edge_off,
                      const int32_t* __restrict__ rowptr, int32_t* __restrict__ nbr, int32_t* __restrict__ perm) {
+  int seg_hint = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     int64_t n0 = 0, e0 = 0, ng = N, eg = E;   // this entry's graph: first node, first entry, sizes
     if (G > 0) {
-      const int g = segment_of(edge_off, G, e);
+      const int g = seg_hint = segment_of_hint(edge_off, G, e, seg_hint);
       n0 = node_off[g];
       e0 = edge_off[g];
       ng = node_off[g + 1] - n0;
@@ -716,6 +723,7 @@ __global__ void __launch_bounds__(256) k_edge_order_check(const IndexT* __restri
                                                           const int32_t* __restrict__ edge_off,
                                                           unsigned long long* __restrict__ out) {
   unsigned long long f[4] = {0ull, 0ull, 0ull, 0ull}, h[4] = {0ull, 0ull, 0ull, 0ull};
+  int seg_hint = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += stride) {
     const int64_t s = (int64_t)ei[e], d = (int64_t)ei[E + e];
@@ -729,7 +737,7 @@ __global__ void __launch_bounds__(256) k_edge_order_check(const IndexT* __restri
     }
     int64_t n0 = 0, e0 = 0, ng = N, eg = E;
     if (G > 0) {
-      const int g = segment_of(edge_off, G, e);
+      const int g = seg_hint = segment_of_hint(edge_off, G, e, seg_hint);
       n0 = node_off[g];
       e0 = edge_off[g];
       ng = node_off[g + 1] - n0;
